@@ -1,0 +1,154 @@
+/*
+ * visfly_b200.h — C-ABI of the B200-native quadrotor dynamics engine.
+ *
+ * This is the drop-in boundary for ONE hot path of SJTU-ViSYS-team/VisFly: the batched rigid-body
+ * control step `Dynamics.step` (reference envs/base/dynamics.py:319-372) with its integrator
+ * (reference utils/maths.py:300-389) and the reverse-mode gradient that PyTorch autograd would
+ * otherwise build op by op (consumers: reference utils/algorithms/BPTT.py:107-134).
+ *
+ * Rules of the boundary
+ *   - plain C linkage, plain pointers and sizes, no torch / C++ types in any signature;
+ *   - every buffer is allocated and owned by the caller; nothing is retained after return;
+ *   - all launches are asynchronous on the `stream` argument (a cudaStream_t passed as void*;
+ *     NULL = legacy default stream) and are CUDA-graph capturable; only the *_host entry points
+ *     synchronise (they have to: they hand results back in host memory);
+ *   - return value 0 = success, non-zero = error; `vf_last_error()` describes the last failure of
+ *     the calling thread.
+ *
+ * HBM layout of the agent state ("packed state", float32):
+ *
+ *     state[plane][agent][lane]      plane in 0..4, agent in 0..n-1, lane in 0..3   (5*n*4 floats)
+ *
+ *     plane 0 : p.x   p.y   p.z   alpha.x        position            | angular acceleration x
+ *     plane 1 : q.w   q.x   q.y   q.z            orientation quaternion (w first)
+ *     plane 2 : v.x   v.y   v.z   alpha.y        ground velocity     | angular acceleration y
+ *     plane 3 : w.x   w.y   w.z   alpha.z        body rates          | angular acceleration z
+ *     plane 4 : W0    W1    W2    W3             motor speeds (rad/s)
+ *
+ * i.e. structure-of-arrays of 16-byte groups: a warp reads one plane as 512 contiguous bytes with one
+ * 128-bit load per thread.  These 20 floats are exactly the quantities that carry value (and gradient)
+ * across control steps in the reference: p, q, v, w, motor speed, and the angular
+ * acceleration that feeds the body-rate controller's D term (reference dynamics.py:407).
+ *
+ * Actions are row-major (n,4) float32 in [-1,1] — the reference's own layout (dynamics.py:704-710) —
+ * so one agent's action is one 128-bit load as well.
+ */
+#ifndef VISFLY_B200_H
+#define VISFLY_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VF_ABI_VERSION 3
+
+/* integrator: reference `integrator=` kwarg, utils/maths.py:331 (euler) and :353 (rk4, repaired R1-R3) */
+#define VF_INTEGRATOR_EULER 0
+#define VF_INTEGRATOR_RK4   1
+
+/* action type: values of reference utils/type.py:14-18 ACTION_TYPE */
+#define VF_ACTION_THRUST   0
+#define VF_ACTION_BODYRATE 1
+
+/* flags */
+#define VF_FLAG_CTRL_DELAY 1u  /* first-order motor lag, reference dynamics.py:510-516; off => T = T_des (:518) */
+
+#define VF_STATE_PLANES 5
+#define VF_STATE_FLOATS 20     /* floats per agent in the packed state  */
+#define VF_OBS_FLOATS   13     /* [p(3) q(4) v+wind(3) w(3)], reference dynamics.py:778-786 */
+#define VF_EXT_FLOATS   8      /* [acc(3) 0 thrust(4)], reference dynamics.py:347,516/518 */
+#define VF_MAX_SUBSTEPS_BWD 64 /* reverse sweep keeps per-substep inputs in thread-local memory */
+
+/* Everything the control step needs besides per-agent data.  All matrices row-major.
+ * Filled on the host from the drone JSON exactly as the reference does (dynamics.py:562-689, :94-114). */
+typedef struct VfParams {
+    float dt;              /* integration sub-step                               dynamics.py:69      */
+    float mass;            /*                                                    :565                */
+    float inv_mass;
+    float J[3];            /* diagonal inertia                                   :108                */
+    float J_inv[3];        /*                                                    :110                */
+    float B[16];           /* allocation  [F,tx,ty,tz] = B @ thrusts             :111-113            */
+    float B_inv[16];       /*                                                    :114                */
+    float thrust_map[3];   /* T = a W^2 + b W + c                                :579, :530-534      */
+    float motor_c;         /* exp(-dt / motor_tau)                               :581                */
+    float thrust_min;      /* 0                                                  :592                */
+    float thrust_max;      /* thrust at motor_omega_max                          :587-590            */
+    float k_lin[3];        /* linear body drag                                   :568                */
+    float k_quad[3];       /* 0.5 * 1.225 * Cd * A                               :567                */
+    float JKp[9];          /* J @ Kp of the body-rate PID                        :405                */
+    float Kd[9];           /* Kd of the body-rate PID                            :407                */
+    float act_half[4];     /* de-normalisation: cmd = a * half + mean            :704-713            */
+    float act_mean[4];
+    float gravity[3];      /* (0,0,-9.81)                                        :15                 */
+    float wind[3];         /* constant wind, added to p-dot and to reported v    :135, maths.py:310  */
+    float pos_lo[3];       /* post-step clamps ("_ugly_fix")                     :374-382            */
+    float pos_hi[3];
+    float vel_lim;
+    float rate_lim;
+} VfParams;
+
+int         vf_abi_version(void);
+const char* vf_last_error(void);
+int         vf_params_size(void);   /* sizeof(VfParams) as compiled into the library (binding self-check) */
+
+/* Number of streaming multiprocessors of the current device (grid sizing / bench reporting). */
+int vf_device_sm_count(void);
+
+/*
+ * One control step for n agents = reference Dynamics.step (dynamics.py:319-372) minus the host-side
+ * comm-delay FIFO (the caller hands in the already-delayed action, dynamics.py:323-328).
+ *
+ *   state_in   [5][n][4]  packed state at the start of the step           (device, 16B aligned)
+ *   action     [n][4]     normalised action in [-1,1]                     (device, 16B aligned)
+ *   state_out  [5][n][4]  packed state after ctrl_dt = substeps*dt        (device, must not alias state_in)
+ *   obs_out    [n][13]    reference `state` property, or NULL             (device, 16B aligned)
+ *   ext_out    [n][8]     [acc, 0, thrusts] diagnostics, or NULL          (device, 16B aligned)
+ */
+int vf_step_fwd(const VfParams* params, int n, int substeps, int integrator, int action_type,
+                unsigned flags, const float* state_in, const float* action,
+                float* state_out, float* obs_out, float* ext_out, void* stream);
+
+/*
+ * Reverse-mode gradient of vf_step_fwd: re-runs the substeps from (state_in, action) in registers /
+ * thread-local memory, then sweeps them in reverse.  No forward intermediates are ever stored in HBM.
+ *
+ *   grad_state_out [5][n][4]  dL/d state_out                    (device; NULL = zeros)
+ *   grad_obs       [n][13]    dL/d obs_out                      (device; NULL = zeros)
+ *   grad_state_in  [5][n][4]  dL/d state_in      (written)
+ *   grad_action    [n][4]     dL/d action        (written)
+ *
+ * torch.autograd conventions are reproduced exactly: clamp passes gradient on the
+ * closed interval, d(v|v|)/dv = 2|v|.  substeps must be <= VF_MAX_SUBSTEPS_BWD.
+ */
+int vf_step_bwd(const VfParams* params, int n, int substeps, int integrator, int action_type,
+                unsigned flags, const float* state_in, const float* action,
+                const float* grad_state_out, const float* grad_obs,
+                float* grad_state_in, float* grad_action, void* stream);
+
+/*
+ * Host-buffer variant of vf_step_fwd (what a caller that lives in host memory binds, e.g. an SB3/numpy
+ * training loop: reference envs/base/droneGymEnv.py:218 returns numpy).  Copies `action_host` to the
+ * device, runs the step on the caller's device-resident state, copies obs back and synchronises the stream.
+ * `action_dev` / `obs_dev` are caller-owned device staging buffers ([n][4] and [n][13]); host buffers
+ * should be page-locked for the copies to be asynchronous.
+ */
+int vf_step_fwd_host(const VfParams* params, int n, int substeps, int integrator, int action_type,
+                     unsigned flags, const float* state_in, const float* action_host, float* action_dev,
+                     float* state_out, float* obs_dev, float* obs_host, void* stream);
+
+/*
+ * Layout conversion between the reference's row-major per-field tensors and the packed state
+ * (reference Dynamics.reset takes (n,k) row-major inputs, dynamics.py:229-236; properties return them,
+ * :735-776).  Any input pointer may be NULL (pack: field left zero, identity quaternion; unpack: skipped).
+ * `index` is NULL (all agents, dense) or int64[m] agent ids to scatter into (pack) — fields are then [m][k].
+ */
+int vf_pack_state(int n, int m, const long long* index,
+                  const float* pos, const float* quat, const float* vel, const float* rate,
+                  const float* motor, const float* alpha, float* state, void* stream);
+int vf_unpack_state(int n, const float* state, float* pos, float* quat, float* vel, float* rate,
+                    float* motor, float* alpha, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VISFLY_B200_H */

@@ -1,0 +1,435 @@
+"""Parity of the sm_100a kernels (called through the C-ABI) with the oracle and with the golden vectors recorded
+from the real reference.  Tolerances are the north-star's: state trajectories within 1e-5 rel-L2 of the
+reference, analytic gradients within 1e-4 of torch.autograd (both are met with >10x margin)."""
+import os
+
+import numpy as np
+import pytest
+import torch as th
+
+from _util import (ACTION, FLAG_CTRL_DELAY, INTEGRATOR, make_oracle, oracle_grads, oracle_step_packed, pack,
+                   random_flight_state, rel_l2, unpack, vf_params)
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+CONFIGS = {
+    "euler": dict(action_type="bodyrate", integrator="euler", dt=0.005, ctrl_dt=0.02, comm_delay=0.06, ctrl_delay=True),
+    "rk4": dict(action_type="bodyrate", integrator="rk4", dt=0.0025, ctrl_dt=0.02, comm_delay=0.06, ctrl_delay=True),
+    "rk4_nolag": dict(action_type="bodyrate", integrator="rk4", dt=0.0025, ctrl_dt=0.02, comm_delay=0.0, ctrl_delay=False),
+    "euler_thrust": dict(action_type="thrust", integrator="euler", dt=0.005, ctrl_dt=0.02, comm_delay=0.0, ctrl_delay=True),
+    "rk4_s12": dict(action_type="bodyrate", integrator="rk4", dt=0.0025, ctrl_dt=0.03, comm_delay=0.06, ctrl_delay=True),
+}
+TRAJ_TOL = 1e-5      # north-star: state trajectories within 1e-5 rel-L2 of the reference
+GRAD_TOL = 1e-4      # north-star: analytic gradients within 1e-4 of PyTorch autograd
+
+
+def cuda_fwd(P, packed, action, S, integ, at="bodyrate", lag=True, obs=True, ext=False):
+    from visfly_b200 import _lib
+    st = packed.cuda().contiguous()
+    ac = action.cuda().float().contiguous()
+    out = th.empty_like(st)
+    n = st.shape[1]
+    o = th.empty((n, 13), device="cuda") if obs else None
+    e = th.empty((n, 8), device="cuda") if ext else None
+    _lib.step_fwd(P, S, INTEGRATOR[integ], ACTION[at], FLAG_CTRL_DELAY if lag else 0, st, ac, out, o, e)
+    th.cuda.synchronize()
+    return out.cpu(), (None if o is None else o.cpu()), (None if e is None else e.cpu())
+
+
+def cuda_bwd(P, packed, action, g_out, g_obs, S, integ, at="bodyrate", lag=True):
+    from visfly_b200 import _lib
+    st, ac = packed.cuda().contiguous(), action.cuda().float().contiguous()
+    go = None if g_out is None else g_out.cuda().float().contiguous()
+    gb = None if g_obs is None else g_obs.cuda().float().contiguous()
+    gs, ga = th.empty_like(st), th.empty_like(ac)
+    _lib.step_bwd(P, S, INTEGRATOR[integ], ACTION[at], FLAG_CTRL_DELAY if lag else 0, st, ac, go, gb, gs, ga)
+    th.cuda.synchronize()
+    return gs.cpu(), ga.cpu()
+
+
+def make_dynamics(n, **kw):
+    from visfly_b200.dynamics import Dynamics
+    return Dynamics(num=n, device="cuda", **kw)
+
+
+# -- one step, seeded inputs, all kernel variants ---------------------------------------------------------
+@pytest.mark.parametrize("integ,dt", [("euler", 0.005), ("rk4", 0.0025)])
+@pytest.mark.parametrize("at", ["bodyrate", "thrust"])
+@pytest.mark.parametrize("lag", [True, False])
+def test_forward_one_step_vs_oracle(integ, dt, at, lag):
+    n, S, wind = 1000, int(0.02 / dt), (0.3, -0.2, 0.1)          # 1000: ragged last warp and last CTA
+    P = vf_params(at, dt, wind=wind)
+    packed = pack(*random_flight_state(n, seed=3))
+    g = th.Generator().manual_seed(5)
+    action = th.rand(n, 4, generator=g) * 2 - 1
+    o32 = make_oracle(n, at, integ, dt, ctrl_delay=lag, wind=wind)
+    o64 = make_oracle(n, at, integ, dt, ctrl_delay=lag, wind=wind, dtype=th.float64)
+    r32, robs32 = oracle_step_packed(o32, packed, action)
+    r64, robs64 = oracle_step_packed(o64, packed.double(), action.double())
+    out, obs, ext = cuda_fwd(P, packed, action, S, integ, at, lag, ext=True)
+    floor = max(rel_l2(r32, r64), 1e-7)
+    assert rel_l2(out, r64) < 3 * floor
+    assert rel_l2(obs, robs64) < 3 * max(rel_l2(robs32, robs64), 1e-7)
+    for got, ref in zip(unpack(out), unpack(r64)):
+        assert rel_l2(got, ref) < 2e-6
+    assert rel_l2(ext[:, :3], o64.acceleration) < 1e-5
+    assert rel_l2(ext[:, 4:], o64.thrusts.T) < 1e-6
+    # the observation is the packed state re-laid out (+ wind on the velocity)
+    assert th.equal(obs[:, 0:3], out[0, :, :3]) and th.equal(obs[:, 3:7], out[1])
+    assert th.equal(obs[:, 10:13], out[3, :, :3])
+    assert th.allclose(obs[:, 7:10], out[2, :, :3] + th.tensor(wind), atol=1e-6)
+
+
+@pytest.mark.parametrize("cfg", list(CONFIGS))
+def test_forward_one_step_vs_reference_golden(cfg):
+    kw = CONFIGS[cfg]
+    z = np.load(os.path.join(GOLD, f"step_{cfg}.npz"))
+    P = vf_params(kw["action_type"], kw["dt"])
+    S = int(kw["ctrl_dt"] / kw["dt"])
+    before = [th.from_numpy(z[f"before_{k}_f32"]) for k in ("pos", "quat", "vel", "rate", "motor", "alpha")]
+    out, obs, ext = cuda_fwd(P, pack(*before), th.from_numpy(z["action"]), S, kw["integrator"], kw["action_type"],
+                             kw["ctrl_delay"], ext=True)
+    assert rel_l2(obs, z["obs_f32"]) < 1e-6
+    tag = "f64" if "obs_f64" in z.files else "f32"
+    assert rel_l2(obs, z[f"obs_{tag}"]) < max(2e-7, 3 * rel_l2(z["obs_f32"], z[f"obs_{tag}"]))
+    for k, got in zip(("pos", "quat", "vel", "rate", "motor", "alpha"), unpack(out)):
+        assert rel_l2(got, z[f"after_{k}_f32"]) < 2e-6, k
+    assert rel_l2(ext[:, :3], z["acc_f32"]) < 1e-5 and rel_l2(ext[:, 4:], z["thrusts_f32"]) < 1e-6
+
+
+# -- trajectories through the drop-in Dynamics class ---------------------------------------------------------
+def test_known_answer_vectors():
+    z = np.load(os.path.join(GOLD, "kat.npz"))
+    a = th.from_numpy(z["action"]).cuda()
+    for name, kw, steps in [("B1_euler", dict(dt=0.005, integrator="euler", comm_delay=0.0), 3),
+                            ("B2_euler_fifo3", dict(dt=0.005, integrator="euler", comm_delay=0.06), 4),
+                            ("B3_rk4", dict(dt=0.0025, integrator="rk4", comm_delay=0.0), 3)]:
+        d = make_dynamics(1, action_type="bodyrate", ctrl_dt=0.02, **kw)
+        d.reset(pos=th.tensor([[1.0, 0.0, 1.5]]))
+        for k in range(steps):
+            s = d.step(a)
+            fs = z[name + "_full_state"][k]
+            assert s.shape == (1, 13)
+            np.testing.assert_allclose(s.cpu().numpy()[0], fs[:13], rtol=2e-5, atol=2e-7)
+            np.testing.assert_allclose(d.full_state.cpu().numpy()[0], fs, rtol=2e-5, atol=2e-7)
+            np.testing.assert_allclose(d.angular_acceleration.cpu().numpy()[0], z[name + "_alpha"][k], rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("cfg", list(CONFIGS))
+@pytest.mark.parametrize("law", ["uniform", "hover"])
+def test_trajectory_vs_reference_golden(cfg, law):
+    kw = CONFIGS[cfg]
+    z = np.load(os.path.join(GOLD, f"traj_{cfg}.npz"))
+    n = z["init_pos"].shape[0]
+    d = make_dynamics(n, **kw)
+    d.reset(pos=th.from_numpy(z["init_pos"]), ori=th.from_numpy(z["init_quat"]), vel=th.from_numpy(z["init_vel"]),
+            ori_vel=th.from_numpy(z["init_rate"]))
+    acts = th.from_numpy(z[f"actions_{law}"]).cuda()
+    states = th.stack([d.step(acts[t]).clone() for t in range(acts.shape[0])]).cpu()
+    ref32 = z[f"states_{law}_f32"]
+    assert rel_l2(states, ref32) < TRAJ_TOL
+    if f"states_{law}_f64" in z.files:          # float64 reference arbitrates: we are as close to it as float32 gets
+        ref64 = z[f"states_{law}_f64"]
+        assert rel_l2(states, ref64) < max(TRAJ_TOL, 2 * rel_l2(ref32, ref64))
+    fs = d.full_state.cpu()
+    assert rel_l2(fs[:, :21], z[f"final_full_state_{law}_f32"][:, :21]) < TRAJ_TOL
+    assert th.allclose(fs[:, 21], th.from_numpy(z[f"final_full_state_{law}_f32"][:, 21]), atol=1e-5)
+
+
+@pytest.mark.parametrize("integ,dt", [("euler", 0.005), ("rk4", 0.0025)])
+def test_256_step_trajectory_vs_oracle(integ, dt):
+    """256 control steps, N=256, both action laws; 1e-5 rel-L2 with the float64 oracle as arbiter."""
+    n, T = 256, 256
+    init = random_flight_state(n, seed=40, spread=0.3)
+    for law_seed, hover in ((0, False), (1, True)):
+        g = th.Generator().manual_seed(law_seed)
+        acts = th.rand(T, n, 4, generator=g) * 2 - 1
+        if hover:
+            acts = acts * 0.1
+            acts[..., 0] += -1.0 / 3.0
+        d = make_dynamics(n, action_type="bodyrate", integrator=integ, dt=dt, ctrl_dt=0.02)
+        o32 = make_oracle(n, "bodyrate", integ, dt, comm_delay=0.06)
+        o64 = make_oracle(n, "bodyrate", integ, dt, comm_delay=0.06, dtype=th.float64)
+        for obj in (d, o32, o64):
+            obj.reset(pos=init[0], ori=init[1], vel=init[2], ori_vel=init[3])
+        acts_gpu = acts.cuda()
+        got = th.stack([d.step(acts_gpu[t]).clone() for t in range(T)]).cpu()
+        r32 = th.stack([o32.step(acts[t]).clone() for t in range(T)])
+        r64 = th.stack([o64.step(acts[t].double()).clone() for t in range(T)])
+        assert rel_l2(got, r32) < TRAJ_TOL
+        assert rel_l2(got, r64) < max(TRAJ_TOL, 2 * rel_l2(r32, r64))
+
+
+# -- adjoint ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("integ,dt,ctrl_dt", [("euler", 0.005, 0.02), ("rk4", 0.0025, 0.02), ("rk4", 0.0025, 0.03),
+                                              ("euler", 0.001, 0.04)])
+@pytest.mark.parametrize("at", ["bodyrate", "thrust"])
+@pytest.mark.parametrize("lag", [True, False])
+def test_backward_one_step_vs_autograd(integ, dt, ctrl_dt, at, lag):
+    n, S, wind = 777, int(round(ctrl_dt / dt)), (0.3, -0.2, 0.1)
+    P = vf_params(at, dt, wind=wind)
+    packed = pack(*random_flight_state(n, seed=8))
+    g = th.Generator().manual_seed(9)
+    action = th.rand(n, 4, generator=g) * 2 - 1
+    g_out, g_obs = th.randn(5, n, 4, generator=g), th.randn(n, 13, generator=g)
+    # (the oracle repeats the reference's float32 `ctrl_dt % dt` check, which rejects e.g. 0.04/0.001:
+    #  build it with one sub-step and set the count directly)
+    orc = make_oracle(n, at, integ, dt, ctrl_dt=dt, ctrl_delay=lag, wind=wind, dtype=th.float64)
+    orc.substeps = S
+    ref_gs, ref_ga = oracle_grads(orc, packed.double(), action.double(), g_out.double(), g_obs.double())
+    got_gs, got_ga = cuda_bwd(P, packed, action, g_out, g_obs, S, integ, at, lag)
+    assert rel_l2(got_gs, ref_gs) < GRAD_TOL and rel_l2(got_ga, ref_ga) < GRAD_TOL
+    for got, ref in zip(unpack(got_gs), unpack(ref_gs)):
+        assert rel_l2(got, ref) < GRAD_TOL
+    # NULL gradient inputs mean zeros
+    z_gs, z_ga = cuda_bwd(P, packed, action, None, None, S, integ, at, lag)
+    assert float(z_gs.abs().max()) == 0.0 and float(z_ga.abs().max()) == 0.0
+    o_gs, o_ga = cuda_bwd(P, packed, action, None, g_obs, S, integ, at, lag)
+    r_gs, r_ga = oracle_grads(orc, packed.double(), action.double(), None, g_obs.double())
+    assert rel_l2(o_gs, r_gs) < GRAD_TOL and rel_l2(o_ga, r_ga) < GRAD_TOL
+
+
+def _hover_loss(dyn, acts, gamma=0.99):
+    dev, dt = acts.device, acts.dtype
+    target = th.tensor([[1.0, 0.0, 1.5]], dtype=dt, device=dev)
+    one = th.tensor([1.0, 0, 0, 0], dtype=dt, device=dev)
+    total = 0.0
+    for t in range(acts.shape[0]):
+        dyn.step(acts[t])
+        r = 0.1 - (dyn.position - target).norm(dim=1) / 90 - (dyn.orientation - one).norm(dim=1) * 1e-5 \
+            - (dyn.velocity - 0).norm(dim=1) * 0.002 - (dyn.angular_velocity - 0).norm(dim=1) * 0.002
+        total = total + (gamma ** t) * r
+    return -total.mean()
+
+
+@pytest.mark.parametrize("cfg", list(CONFIGS))
+def test_rollout_gradients_vs_reference_autograd_golden(cfg):
+    """8-step BPTT through the drop-in Dynamics + autograd.Function against gradients recorded from
+    torch.autograd through the real reference (tests/golden/grad_*.npz)."""
+    from visfly_b200.dynamics import ControlStep
+    kw = CONFIGS[cfg]
+    z = np.load(os.path.join(GOLD, f"grad_{cfg}.npz"))
+    n = z["init_pos"].shape[0]
+    d = make_dynamics(n, **kw)
+    leaves = [th.from_numpy(z["init_" + k]).float().cuda().requires_grad_(True) for k in ("pos", "quat", "vel", "rate")]
+    acts = th.from_numpy(z["actions"]).cuda().requires_grad_(True)
+    d.reset()
+    zero = th.zeros((n, 1), device="cuda")
+    motor = d.motor_omega.detach()
+    d._state = th.stack([th.cat([leaves[0], zero], 1), leaves[1], th.cat([leaves[2], zero], 1),
+                         th.cat([leaves[3], zero], 1), motor])
+    loss = _hover_loss(d, acts)
+    grads = th.autograd.grad(loss, [acts] + leaves)
+    tag = "f64" if "grad_actions_f64" in z.files else "f32"
+    assert abs(loss.item() - float(z[f"loss_{tag}"])) < 1e-5
+    for k, g in zip(("actions", "pos", "quat", "vel", "rate"), grads):
+        assert rel_l2(g.cpu(), z[f"grad_{k}_{tag}"]) < GRAD_TOL, k
+        assert rel_l2(g.cpu(), z[f"grad_{k}_f32"]) < GRAD_TOL, k
+
+
+def test_apg_horizon_gradients_vs_oracle_autograd():
+    """Config 3 at a parity-sized batch: H=32 RK4 steps with the comm-delay FIFO, gradients of a discounted
+    return w.r.t. all actions and the initial state, vs torch.autograd through the oracle (float32 and float64)."""
+    n, H, dt = 512, 32, 0.0025
+    init = random_flight_state(n, seed=50, spread=0.3)
+    g = th.Generator().manual_seed(51)
+    acts = (th.rand(H, n, 4, generator=g) * 2 - 1) * 0.5
+    d = make_dynamics(n, action_type="bodyrate", integrator="rk4", dt=dt, ctrl_dt=0.02)
+    d.reset(pos=init[0], ori=init[1], vel=init[2], ori_vel=init[3])
+    a_gpu = acts.cuda().requires_grad_(True)
+    s0 = d._state.detach().clone().requires_grad_(True)
+    d._state = s0
+    loss = _hover_loss(d, a_gpu)
+    g_a, g_s = th.autograd.grad(loss, [a_gpu, s0])
+    res = {}
+    for dtype in (th.float32, th.float64):
+        o = make_oracle(n, "bodyrate", "rk4", dt, comm_delay=0.06, dtype=dtype)
+        o.reset(pos=init[0], ori=init[1], vel=init[2], ori_vel=init[3])
+        a = acts.to(dtype).requires_grad_(True)
+        p0 = o.packed().clone().requires_grad_(True)
+        o.load_packed(p0)
+        lo = _hover_loss(o, a)
+        res[dtype] = th.autograd.grad(lo, [a, p0]) + (lo,)
+    assert abs(loss.item() - res[th.float64][2].item()) < 1e-5
+    # actions still in the FIFO at the end of the horizon get exactly zero gradient
+    assert float(g_a[-3:].abs().max()) == 0.0 and float(res[th.float64][0][-3:].abs().max()) == 0.0
+    assert rel_l2(g_a.cpu(), res[th.float64][0]) < GRAD_TOL
+    assert rel_l2(g_s.cpu(), res[th.float64][1]) < GRAD_TOL
+    assert rel_l2(g_a.cpu(), res[th.float32][0]) < GRAD_TOL
+
+
+# -- edge cases and size-independent properties --------------------------------------------------------------
+@pytest.mark.parametrize("n", [0, 1, 31, 33, 64, 65])
+def test_ragged_and_tiny_batches(n):
+    from visfly_b200 import _lib
+    P = vf_params("bodyrate", 0.0025)
+    if n == 0:
+        e = th.empty((5, 0, 4), device="cuda")
+        _lib.step_fwd(P, 8, 1, 1, 1, e, th.empty((0, 4), device="cuda"), th.empty((5, 0, 4), device="cuda"), None, None)
+        return
+    packed = pack(*random_flight_state(n, seed=n))
+    g = th.Generator().manual_seed(n)
+    action = th.rand(n, 4, generator=g) * 2 - 1
+    out, obs, _ = cuda_fwd(P, packed, action, 8, "rk4")
+    ref, robs = oracle_step_packed(make_oracle(n, "bodyrate", "rk4", 0.0025, dtype=th.float64), packed.double(), action.double())
+    assert rel_l2(out, ref) < 1e-6 and rel_l2(obs, robs) < 1e-6
+    g_obs = th.randn(n, 13, generator=g)
+    gs, ga = cuda_bwd(P, packed, action, None, g_obs, 8, "rk4")
+    rgs, rga = oracle_grads(make_oracle(n, "bodyrate", "rk4", 0.0025, dtype=th.float64), packed.double(),
+                            action.double(), None, g_obs.double())
+    assert rel_l2(gs, rgs) < GRAD_TOL and rel_l2(ga, rga) < GRAD_TOL
+
+
+def test_full_size_properties_and_shard_invariance():
+    """BASELINE config 2 size (65 536 agents, RK4 x8): unit quaternions, determinism, and bitwise identical
+    results whether the batch is stepped whole or as two shards (per-agent arithmetic only)."""
+    n, dt, S = 65536, 0.0025, 8
+    P = vf_params("bodyrate", dt)
+    packed = pack(*random_flight_state(n, seed=77))
+    g = th.Generator().manual_seed(78)
+    for _ in range(4):
+        action = th.rand(n, 4, generator=g) * 2 - 1
+        out, obs, _ = cuda_fwd(P, packed, action, S, "rk4")
+        out2, obs2, _ = cuda_fwd(P, packed, action, S, "rk4")
+        assert th.equal(out, out2) and th.equal(obs, obs2)
+        h = n // 2
+        lo, lo_obs, _ = cuda_fwd(P, packed[:, :h].contiguous(), action[:h], S, "rk4")
+        hi, hi_obs, _ = cuda_fwd(P, packed[:, h:].contiguous(), action[h:], S, "rk4")
+        assert th.equal(th.cat([lo, hi], 1), out) and th.equal(th.cat([lo_obs, hi_obs]), obs)
+        assert float((out[1].norm(dim=1) - 1).abs().max()) < 1e-6
+        assert bool(th.isfinite(out).all())
+        packed = out
+    # spot-check a slice of the big batch against the oracle
+    sl = slice(1000, 1256)
+    ref, _ = oracle_step_packed(make_oracle(256, "bodyrate", "rk4", dt, dtype=th.float64),
+                                packed[:, sl].double(), action[sl].double())
+    got, _, _ = cuda_fwd(P, packed, action, S, "rk4")
+    assert rel_l2(got[:, sl], ref) < 1e-6
+
+
+def test_post_step_clamps_and_gradient_gates():
+    n, dt, S = 64, 0.005, 4
+    P = vf_params("bodyrate", dt)
+    pos, quat, vel, rate, motor, alpha = random_flight_state(n, seed=4)
+    pos[:, 2], vel[:, 0], rate[:, 1] = 25.0, 30.0, -40.0
+    packed = pack(pos, quat, vel, rate, motor, alpha)
+    action = th.ones(n, 4)
+    out, obs, _ = cuda_fwd(P, packed, action, S, "euler")
+    assert float(out[0, :, 2].max()) <= 20.0 and float(out[2, :, 0].max()) <= 20.0 and float(out[3, :, 1].min()) >= -10.0
+    g_out = th.zeros(5, n, 4)
+    g_out[0, :, 2] = 1.0
+    g_out[2, :, 0] = 1.0
+    gs, ga = cuda_bwd(P, packed, action, g_out, None, S, "euler")
+    rgs, rga = oracle_grads(make_oracle(n, "bodyrate", "euler", dt, dtype=th.float64), packed.double(),
+                            action.double(), g_out.double(), None)
+    assert float(rgs.abs().max()) == 0.0 and float(gs.abs().max()) == 0.0 and float(ga.abs().max()) == 0.0
+
+
+def test_pack_unpack_roundtrip_and_scatter():
+    from visfly_b200 import _lib
+    n = 300
+    fields = [f.cuda().contiguous() for f in random_flight_state(n, seed=5)]
+    st = th.zeros((5, n, 4), device="cuda")
+    _lib.pack_state(n, st, None, *fields)
+    assert th.equal(st.cpu(), pack(*[f.cpu() for f in fields]))
+    outs = [th.empty_like(f) for f in fields]
+    _lib.unpack_state(n, st, *outs)
+    for a, b in zip(outs, fields):
+        assert th.equal(a, b)
+    idx = th.tensor([5, 17, 299, 0], device="cuda")
+    rows = [f[:4].contiguous() * 2 for f in fields]
+    _lib.pack_state(n, st, idx, *rows)
+    ref = pack(*[f.cpu() for f in fields])
+    ref[:, idx.cpu()] = pack(*[r.cpu() for r in rows])
+    assert th.equal(st.cpu(), ref)
+
+
+def test_cuda_graph_capture_replays_the_step():
+    from visfly_b200 import _lib
+    n, S = 4096, 8
+    P = vf_params("bodyrate", 0.0025)
+    st = pack(*random_flight_state(n, seed=6)).cuda()
+    ac = (th.rand(n, 4) * 2 - 1).cuda()
+    out, obs = th.empty_like(st), th.empty((n, 13), device="cuda")
+    _lib.step_fwd(P, S, 1, 1, 1, st, ac, out, obs, None)
+    eager = out.clone()
+    th.cuda.synchronize()
+    graph = th.cuda.CUDAGraph()
+    out.zero_()
+    with th.cuda.graph(graph):
+        _lib.step_fwd(P, S, 1, 1, 1, st, ac, out, obs, None)
+    graph.replay()
+    th.cuda.synchronize()
+    assert th.equal(out, eager)
+
+
+def test_host_buffer_entry_point():
+    from visfly_b200 import _lib
+    n, S = 5000, 8
+    P = vf_params("bodyrate", 0.0025)
+    st = pack(*random_flight_state(n, seed=7)).cuda()
+    a_host = (th.rand(n, 4) * 2 - 1).pin_memory()
+    o_host = th.empty((n, 13)).pin_memory()
+    a_dev, o_dev, out = th.empty((n, 4), device="cuda"), th.empty((n, 13), device="cuda"), th.empty_like(st)
+    _lib.step_fwd_host(P, S, 1, 1, 1, st, a_host, a_dev, out, o_dev, o_host)
+    ref_out, ref_obs, _ = cuda_fwd(P, st.cpu(), a_host, S, "rk4")
+    assert th.equal(out.cpu(), ref_out) and th.equal(o_host, ref_obs)
+
+
+# -- Dynamics surface -------------------------------------------------------------------------------------------
+def test_dynamics_surface_shapes_and_reset_semantics():
+    from visfly_b200.type import ACTION_TYPE
+    n = 128
+    d = make_dynamics(n, action_type="bodyrate", integrator="rk4", dt=0.0025, ctrl_dt=0.02)
+    assert d.action_type == ACTION_TYPE.BODYRATE and d.num == n and d.is_quat_output
+    assert d.state.shape == (n, 13) and d.full_state.shape == (n, 22) and d.extend_state.shape == (n, 28)
+    assert d.R.shape == (3, 3, n) and d.xz_axis.shape == (2, 3, n) and d.direction.shape == (n, 3)
+    assert d._orientation.toTensor().shape == (4, n)
+    o = make_oracle(n, "bodyrate", "rk4", 0.0025, comm_delay=0.06)
+    init = random_flight_state(n, seed=60, spread=0.3)
+    d.reset(pos=init[0], ori=init[1], vel=init[2], ori_vel=init[3])
+    o.reset(pos=init[0], ori=init[1], vel=init[2], ori_vel=init[3])
+    assert rel_l2(d.full_state.cpu(), o.full_state) < 1e-6
+    g = th.Generator().manual_seed(61)
+    for t in range(10):
+        a = th.rand(n, 4, generator=g) * 2 - 1
+        d.step(a.cuda()), o.step(a)
+        if t == 4:                      # partial reset in the middle (auto-reset path of the env wrapper)
+            idx = [3, 50, 127]
+            newp = th.tensor([[0.0, 0, 1], [1, 1, 1], [2, 2, 2.0]])
+            d.reset(pos=newp, indices=idx)
+            o.reset(pos=newp, indices=idx)
+            assert float(d.t[idx].abs().max()) == 0.0
+    assert rel_l2(d.full_state.cpu()[:, :21], o.full_state[:, :21]) < 1e-5
+    assert rel_l2(d.acceleration.cpu(), o.acceleration) < 1e-4
+    assert rel_l2(d.direction.cpu(), o.direction) < 1e-5
+    assert rel_l2(d.angular_acceleration.cpu(), o.angular_acceleration) < 1e-4
+    assert th.allclose(d.t.cpu(), o.t, atol=1e-6)
+    with pytest.raises(ValueError):
+        make_dynamics(4, dt=0.003, ctrl_dt=0.02)
+
+
+def test_partial_reset_cuts_the_gradient_like_the_reference():
+    n, H = 64, 6
+    d = make_dynamics(n, action_type="bodyrate", integrator="euler", dt=0.005, ctrl_dt=0.02, comm_delay=0.0)
+    o = make_oracle(n, "bodyrate", "euler", 0.005, comm_delay=0.0, dtype=th.float64)
+    init = random_flight_state(n, seed=70, spread=0.3)
+    d.reset(pos=init[0], ori=init[1], vel=init[2], ori_vel=init[3])
+    o.reset(pos=init[0], ori=init[1], vel=init[2], ori_vel=init[3])
+    g = th.Generator().manual_seed(71)
+    acts = th.rand(H, n, 4, generator=g) * 2 - 1
+    a_gpu, a_cpu = acts.cuda().requires_grad_(True), acts.double().requires_grad_(True)
+    idx = list(range(0, n, 2))
+    lg = lc = 0.0
+    for t in range(H):
+        d.step(a_gpu[t]), o.step(a_cpu[t])
+        lg = lg + d.position.norm(dim=1).sum() + d.angular_velocity.pow(2).sum()
+        lc = lc + o.position.norm(dim=1).sum() + o.angular_velocity.pow(2).sum()
+        if t == 2:
+            d.reset(indices=idx), o.reset(indices=idx)
+    gg, = th.autograd.grad(lg, a_gpu)
+    gc, = th.autograd.grad(lc, a_cpu)
+    assert rel_l2(gg.cpu(), gc) < GRAD_TOL
+    d.detach()
+    assert not d._state.requires_grad and all(not a.requires_grad for a in d._pre_action)

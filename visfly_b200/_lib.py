@@ -1,0 +1,157 @@
+"""ctypes binding of the C-ABI in include/visfly_b200.h (``libvisfly_b200.so``, built in-tree).
+
+There is exactly one compute path: the sm_100a kernels.  If the shared library is missing, or CUDA is not
+available, every entry point raises — there is no CPU fallback and no PyTorch re-implementation behind it.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Optional
+
+import torch as th
+
+from .params import VfParams
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvisfly_b200.so")
+ABI_VERSION = 3
+
+INTEGRATOR_ID = {"euler": 0, "rk4": 1}
+FLAG_CTRL_DELAY = 1
+MAX_SUBSTEPS_BWD = 64
+
+_P = ctypes.POINTER
+_vp = ctypes.c_void_p
+_i = ctypes.c_int
+_u = ctypes.c_uint
+
+# name -> (restype, argtypes); mirrors include/visfly_b200.h one to one
+SIGNATURES = {
+    "vf_abi_version": (_i, []),
+    "vf_last_error": (ctypes.c_char_p, []),
+    "vf_params_size": (_i, []),
+    "vf_device_sm_count": (_i, []),
+    "vf_step_fwd": (_i, [_P(VfParams), _i, _i, _i, _i, _u, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "vf_step_bwd": (_i, [_P(VfParams), _i, _i, _i, _i, _u, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "vf_step_fwd_host": (_i, [_P(VfParams), _i, _i, _i, _i, _u, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "vf_pack_state": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "vf_unpack_state": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+}
+
+_lib: Optional[ctypes.CDLL] = None
+
+
+class ExtensionMissing(RuntimeError):
+    pass
+
+
+def load(require_cuda: bool = False) -> ctypes.CDLL:
+    """Load (once) and type the shared library.  ``require_cuda`` additionally insists on a usable GPU."""
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise ExtensionMissing(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a). visfly_b200 has no CPU fallback.")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)          # AttributeError here = header / library mismatch
+            fn.restype, fn.argtypes = res, args
+        got = lib.vf_abi_version()
+        if got != ABI_VERSION:
+            raise ExtensionMissing(f"libvisfly_b200.so has ABI {got}, python side expects {ABI_VERSION}: rebuild")
+        if lib.vf_params_size() != ctypes.sizeof(VfParams):
+            raise ExtensionMissing("struct VfParams differs between libvisfly_b200.so and visfly_b200/params.py")
+        _lib = lib
+    if require_cuda and not th.cuda.is_available():
+        raise RuntimeError("visfly_b200 needs a CUDA device (sm_100a): torch.cuda.is_available() is False "
+                           "and there is no CPU fallback")
+    return _lib
+
+
+def _check(rc: int):
+    if rc != 0:
+        raise RuntimeError("visfly_b200: " + load().vf_last_error().decode())
+
+
+def _dev_ptr(t: Optional[th.Tensor], what: str) -> Optional[int]:
+    if t is None:
+        return None
+    if not t.is_cuda or t.dtype != th.float32 or not t.is_contiguous():
+        raise ValueError(f"{what} must be a contiguous float32 CUDA tensor (got {t.dtype}, {t.device}, "
+                         f"contiguous={t.is_contiguous()})")
+    return t.data_ptr()
+
+
+def _stream(device) -> int:
+    return th.cuda.current_stream(device).cuda_stream
+
+
+def step_fwd(params: VfParams, substeps: int, integrator: int, action_type: int, flags: int,
+             state_in: th.Tensor, action: th.Tensor, state_out: th.Tensor, obs_out: Optional[th.Tensor],
+             ext_out: Optional[th.Tensor]) -> None:
+    lib = load(require_cuda=True)
+    n = state_in.shape[1]
+    with th.cuda.device(state_in.device):
+        _check(lib.vf_step_fwd(ctypes.byref(params), n, substeps, integrator, action_type, flags,
+                               _dev_ptr(state_in, "state_in"), _dev_ptr(action, "action"),
+                               _dev_ptr(state_out, "state_out"), _dev_ptr(obs_out, "obs_out"),
+                               _dev_ptr(ext_out, "ext_out"), _stream(state_in.device)))
+
+
+def step_bwd(params: VfParams, substeps: int, integrator: int, action_type: int, flags: int,
+             state_in: th.Tensor, action: th.Tensor, g_state_out: Optional[th.Tensor],
+             g_obs: Optional[th.Tensor], g_state_in: th.Tensor, g_action: th.Tensor) -> None:
+    lib = load(require_cuda=True)
+    n = state_in.shape[1]
+    with th.cuda.device(state_in.device):
+        _check(lib.vf_step_bwd(ctypes.byref(params), n, substeps, integrator, action_type, flags,
+                               _dev_ptr(state_in, "state_in"), _dev_ptr(action, "action"),
+                               _dev_ptr(g_state_out, "grad_state_out"), _dev_ptr(g_obs, "grad_obs"),
+                               _dev_ptr(g_state_in, "grad_state_in"), _dev_ptr(g_action, "grad_action"),
+                               _stream(state_in.device)))
+
+
+def step_fwd_host(params: VfParams, substeps: int, integrator: int, action_type: int, flags: int,
+                  state_in: th.Tensor, action_host: th.Tensor, action_dev: th.Tensor, state_out: th.Tensor,
+                  obs_dev: Optional[th.Tensor], obs_host: Optional[th.Tensor]) -> None:
+    lib = load(require_cuda=True)
+    n = state_in.shape[1]
+    for t, what in ((action_host, "action_host"), (obs_host, "obs_host")):
+        if t is not None and (t.is_cuda or t.dtype != th.float32 or not t.is_contiguous()):
+            raise ValueError(f"{what} must be a contiguous float32 host tensor")
+    with th.cuda.device(state_in.device):
+        _check(lib.vf_step_fwd_host(ctypes.byref(params), n, substeps, integrator, action_type, flags,
+                                    _dev_ptr(state_in, "state_in"), action_host.data_ptr(),
+                                    _dev_ptr(action_dev, "action_dev"), _dev_ptr(state_out, "state_out"),
+                                    _dev_ptr(obs_dev, "obs_dev"),
+                                    None if obs_host is None else obs_host.data_ptr(),
+                                    _stream(state_in.device)))
+
+
+def pack_state(n: int, state: th.Tensor, index: Optional[th.Tensor] = None, pos=None, quat=None, vel=None,
+               rate=None, motor=None, alpha=None) -> None:
+    lib = load(require_cuda=True)
+    fields = [pos, quat, vel, rate, motor, alpha]
+    m = n
+    for f in fields:
+        if f is not None:
+            m = f.shape[0]
+    if index is not None:
+        if index.dtype != th.int64 or not index.is_cuda or not index.is_contiguous():
+            raise ValueError("index must be a contiguous int64 CUDA tensor")
+        m = index.numel()
+    with th.cuda.device(state.device):
+        _check(lib.vf_pack_state(n, m, None if index is None else index.data_ptr(),
+                                 *[_dev_ptr(f, "field") for f in fields], _dev_ptr(state, "state"),
+                                 _stream(state.device)))
+
+
+def unpack_state(n: int, state: th.Tensor, pos=None, quat=None, vel=None, rate=None, motor=None,
+                 alpha=None) -> None:
+    lib = load(require_cuda=True)
+    with th.cuda.device(state.device):
+        _check(lib.vf_unpack_state(n, _dev_ptr(state, "state"),
+                                   *[_dev_ptr(f, "field") for f in (pos, quat, vel, rate, motor, alpha)],
+                                   _stream(state.device)))

@@ -1,0 +1,409 @@
+// vf_kernels.cu — sm_100a kernels and the C-ABI of include/visfly_b200.h.
+//
+// Design (B200): the control step is ~1-4 kFLOP of dependent fp32 arithmetic per agent on 24 input floats,
+// no reuse across agents and no contraction, so there is nothing for tensor cores / TMA tiles to do; the
+// levers that matter are (i) one HBM round trip per control step — all sub-steps run in registers,
+// (ii) 128-bit coalesced accesses on an SoA-of-float4 state (a warp touches 512 contiguous bytes per plane),
+// (iii) enough independent warps per SM sub-partition to cover the fp32 dependency chains (one agent per
+// thread, small CTAs so that 65 536 agents spread evenly over 148 SMs), and (iv) no forward intermediates in
+// HBM for the backward pass: the adjoint kernel re-runs the sub-steps and keeps its tape in thread-local
+// memory (L1-resident).  The AoS observation (n,13) the reference returns is transposed through shared
+// memory so its global stores/loads are 128-bit and coalesced as well.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+
+#include "vf_math.cuh"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(const char* what, cudaError_t err = cudaSuccess) {
+    g_last_error = what;
+    if (err != cudaSuccess) {
+        g_last_error += ": ";
+        g_last_error += cudaGetErrorString(err);
+    }
+    return 1;
+}
+
+constexpr int kObs = VF_OBS_FLOATS;       // 13
+constexpr int kWarpObs = 32 * kObs;       // floats one warp's observations occupy (416 = 104 float4)
+
+__device__ __forceinline__ float4 ldg4(const float* base, size_t idx4) {
+    return __ldg(reinterpret_cast<const float4*>(base) + idx4);
+}
+__device__ __forceinline__ void stg4(float* base, size_t idx4, float4 v) {
+    reinterpret_cast<float4*>(base)[idx4] = v;
+}
+
+__device__ __forceinline__ void load_state(const float* __restrict__ st, int n, int i, vf::State<float>& s) {
+    const float4 a = ldg4(st, size_t(i));
+    const float4 b = ldg4(st, size_t(n) + i);
+    const float4 c = ldg4(st, size_t(2) * n + i);
+    const float4 d = ldg4(st, size_t(3) * n + i);
+    const float4 e = ldg4(st, size_t(4) * n + i);
+    s.p[0] = a.x; s.p[1] = a.y; s.p[2] = a.z; s.al[0] = a.w;
+    s.q[0] = b.x; s.q[1] = b.y; s.q[2] = b.z; s.q[3] = b.w;
+    s.v[0] = c.x; s.v[1] = c.y; s.v[2] = c.z; s.al[1] = c.w;
+    s.w[0] = d.x; s.w[1] = d.y; s.w[2] = d.z; s.al[2] = d.w;
+    s.mot[0] = e.x; s.mot[1] = e.y; s.mot[2] = e.z; s.mot[3] = e.w;
+}
+
+__device__ __forceinline__ void store_state(float* __restrict__ st, int n, int i, const vf::State<float>& s) {
+    stg4(st, size_t(i), make_float4(s.p[0], s.p[1], s.p[2], s.al[0]));
+    stg4(st, size_t(n) + i, make_float4(s.q[0], s.q[1], s.q[2], s.q[3]));
+    stg4(st, size_t(2) * n + i, make_float4(s.v[0], s.v[1], s.v[2], s.al[1]));
+    stg4(st, size_t(3) * n + i, make_float4(s.w[0], s.w[1], s.w[2], s.al[2]));
+    stg4(st, size_t(4) * n + i, make_float4(s.mot[0], s.mot[1], s.mot[2], s.mot[3]));
+}
+
+// Warp-cooperative transpose of 32 agents x 13 floats between registers and the row-major (n,13) array.
+// `smem` is this warp's 416-float slice.  lane*13+j is conflict-free (13 is odd).
+__device__ __forceinline__ void warp_store_obs(float* __restrict__ obs, float* smem, int n, int warp_first,
+                                               int lane, const float o[kObs]) {
+    if (warp_first + 32 <= n) {
+#pragma unroll
+        for (int j = 0; j < kObs; ++j) smem[lane * kObs + j] = o[j];
+        __syncwarp();
+        float4* dst = reinterpret_cast<float4*>(obs + size_t(warp_first) * kObs);
+        const float4* src = reinterpret_cast<const float4*>(smem);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int idx = lane + 32 * k;
+            if (idx < kWarpObs / 4) dst[idx] = src[idx];
+        }
+        __syncwarp();
+    } else if (warp_first + lane < n) {
+        float* dst = obs + size_t(warp_first + lane) * kObs;
+#pragma unroll
+        for (int j = 0; j < kObs; ++j) dst[j] = o[j];
+    }
+}
+
+__device__ __forceinline__ void warp_load_obs(const float* __restrict__ obs, float* smem, int n, int warp_first,
+                                              int lane, float o[kObs]) {
+    if (warp_first + 32 <= n) {
+        const float4* src = reinterpret_cast<const float4*>(obs + size_t(warp_first) * kObs);
+        float4* dst = reinterpret_cast<float4*>(smem);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int idx = lane + 32 * k;
+            if (idx < kWarpObs / 4) dst[idx] = __ldg(src + idx);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < kObs; ++j) o[j] = smem[lane * kObs + j];
+        __syncwarp();
+    } else if (warp_first + lane < n) {
+        const float* src = obs + size_t(warp_first + lane) * kObs;
+#pragma unroll
+        for (int j = 0; j < kObs; ++j) o[j] = __ldg(src + j);
+    } else {
+#pragma unroll
+        for (int j = 0; j < kObs; ++j) o[j] = 0.f;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward control step
+// ---------------------------------------------------------------------------------------------
+template <int INTEG, int ACT, bool LAG, int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+vf_step_fwd_kernel(const __grid_constant__ VfParams params, int n, int substeps,
+                   const float* __restrict__ state_in, const float* __restrict__ action,
+                   float* __restrict__ state_out, float* __restrict__ obs_out, float* __restrict__ ext_out) {
+    __shared__ __align__(16) float s_obs[(BLOCK / 32) * kWarpObs];
+    const vf::Params<float>& P = reinterpret_cast<const vf::Params<float>&>(params);
+    const int i = blockIdx.x * BLOCK + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int warp_first = i - lane;
+    const bool live = i < n;
+
+    vf::State<float> s;
+    vf::Wrench<float> k;
+    if (live) {
+        load_state(state_in, n, i, s);
+        const float4 a4 = ldg4(action, size_t(i));
+        const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+        vf::step_fwd<float>(P, substeps, INTEG, ACT, LAG, a, s, k);
+        store_state(state_out, n, i, s);
+        if (ext_out) {
+            stg4(ext_out, size_t(2) * i, make_float4(k.acc[0], k.acc[1], k.acc[2], 0.f));
+            stg4(ext_out, size_t(2) * i + 1, make_float4(k.thr[0], k.thr[1], k.thr[2], k.thr[3]));
+        }
+    }
+    if (obs_out) {
+        float o[kObs];
+        if (live) {
+            o[0] = s.p[0]; o[1] = s.p[1]; o[2] = s.p[2];
+            o[3] = s.q[0]; o[4] = s.q[1]; o[5] = s.q[2]; o[6] = s.q[3];
+            o[7] = s.v[0] + P.wind[0]; o[8] = s.v[1] + P.wind[1]; o[9] = s.v[2] + P.wind[2];
+            o[10] = s.w[0]; o[11] = s.w[1]; o[12] = s.w[2];
+        }
+        warp_store_obs(obs_out, s_obs + warp * kWarpObs, n, warp_first, lane, o);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// reverse control step
+// ---------------------------------------------------------------------------------------------
+template <int INTEG, int ACT, bool LAG, int SMAX, int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+vf_step_bwd_kernel(const __grid_constant__ VfParams params, int n, int substeps,
+                   const float* __restrict__ state_in, const float* __restrict__ action,
+                   const float* __restrict__ g_state_out, const float* __restrict__ g_obs,
+                   float* __restrict__ g_state_in, float* __restrict__ g_action) {
+    __shared__ __align__(16) float s_obs[(BLOCK / 32) * kWarpObs];
+    const vf::Params<float>& P = reinterpret_cast<const vf::Params<float>&>(params);
+    const int i = blockIdx.x * BLOCK + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int warp_first = i - lane;
+    const bool live = i < n;
+
+    vf::State<float> g;
+    if (g_state_out && live) {
+        load_state(g_state_out, n, i, g);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) g.p[j] = g.v[j] = g.w[j] = g.al[j] = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) g.q[j] = g.mot[j] = 0.f;
+    }
+    if (g_obs) {
+        float o[kObs];
+        warp_load_obs(g_obs, s_obs + warp * kWarpObs, n, warp_first, lane, o);
+        g.p[0] += o[0]; g.p[1] += o[1]; g.p[2] += o[2];
+        g.q[0] += o[3]; g.q[1] += o[4]; g.q[2] += o[5]; g.q[3] += o[6];
+        g.v[0] += o[7]; g.v[1] += o[8]; g.v[2] += o[9];
+        g.w[0] += o[10]; g.w[1] += o[11]; g.w[2] += o[12];
+    }
+    if (!live) return;
+
+    vf::State<float> s0;
+    load_state(state_in, n, i, s0);
+    const float4 a4 = ldg4(action, size_t(i));
+    const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+    vf::Tape<float> tape[SMAX];
+    float ga[4];
+    vf::step_bwd<float>(P, substeps, INTEG, ACT, LAG, a, s0, g, ga, tape);
+    store_state(g_state_in, n, i, g);
+    stg4(g_action, size_t(i), make_float4(ga[0], ga[1], ga[2], ga[3]));
+}
+
+// ---------------------------------------------------------------------------------------------
+// layout conversion (reset / property views)
+// ---------------------------------------------------------------------------------------------
+__global__ void vf_pack_kernel(int n, int m, const long long* __restrict__ index,
+                               const float* __restrict__ pos, const float* __restrict__ quat,
+                               const float* __restrict__ vel, const float* __restrict__ rate,
+                               const float* __restrict__ motor, const float* __restrict__ alpha,
+                               float* __restrict__ st) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= m) return;
+    const long long i = index ? index[r] : r;
+    if (i < 0 || i >= n) return;
+    vf::State<float> s;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        s.p[j] = pos ? pos[size_t(r) * 3 + j] : 0.f;
+        s.v[j] = vel ? vel[size_t(r) * 3 + j] : 0.f;
+        s.w[j] = rate ? rate[size_t(r) * 3 + j] : 0.f;
+        s.al[j] = alpha ? alpha[size_t(r) * 3 + j] : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        s.q[j] = quat ? quat[size_t(r) * 4 + j] : (j == 0 ? 1.f : 0.f);
+        s.mot[j] = motor ? motor[size_t(r) * 4 + j] : 0.f;
+    }
+    store_state(st, n, int(i), s);
+}
+
+__global__ void vf_unpack_kernel(int n, const float* __restrict__ st, float* __restrict__ pos,
+                                 float* __restrict__ quat, float* __restrict__ vel, float* __restrict__ rate,
+                                 float* __restrict__ motor, float* __restrict__ alpha) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    vf::State<float> s;
+    load_state(st, n, i, s);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        if (pos) pos[size_t(i) * 3 + j] = s.p[j];
+        if (vel) vel[size_t(i) * 3 + j] = s.v[j];
+        if (rate) rate[size_t(i) * 3 + j] = s.w[j];
+        if (alpha) alpha[size_t(i) * 3 + j] = s.al[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (quat) quat[size_t(i) * 4 + j] = s.q[j];
+        if (motor) motor[size_t(i) * 4 + j] = s.mot[j];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// dispatch
+// ---------------------------------------------------------------------------------------------
+constexpr int kBlock = 64;   // 65 536 agents -> 1024 CTAs -> 6.9 per SM: <= 14 warps on the fullest SM
+
+bool aligned16(const void* p) { return (reinterpret_cast<size_t>(p) & 15u) == 0; }
+
+int check_common(const VfParams* params, int n, int substeps, int integrator, int action_type) {
+    if (!params) return fail("params is NULL");
+    if (n < 0) return fail("n must be >= 0");
+    if (substeps < 1) return fail("substeps must be >= 1");
+    if (integrator != VF_INTEGRATOR_EULER && integrator != VF_INTEGRATOR_RK4)
+        return fail("integrator must be VF_INTEGRATOR_EULER or VF_INTEGRATOR_RK4");
+    if (action_type != VF_ACTION_THRUST && action_type != VF_ACTION_BODYRATE)
+        return fail("action_type must be VF_ACTION_THRUST or VF_ACTION_BODYRATE");
+    return 0;
+}
+
+template <int INTEG, int ACT, bool LAG>
+void launch_fwd(const VfParams& p, int n, int substeps, const float* si, const float* a, float* so, float* obs,
+                float* ext, cudaStream_t st) {
+    const int grid = (n + kBlock - 1) / kBlock;
+    vf_step_fwd_kernel<INTEG, ACT, LAG, kBlock><<<grid, kBlock, 0, st>>>(p, n, substeps, si, a, so, obs, ext);
+}
+
+template <int INTEG, int ACT, bool LAG>
+void launch_bwd(const VfParams& p, int n, int substeps, const float* si, const float* a, const float* gso,
+                const float* gobs, float* gsi, float* ga, cudaStream_t st) {
+    const int grid = (n + kBlock - 1) / kBlock;
+    if (substeps <= 8)
+        vf_step_bwd_kernel<INTEG, ACT, LAG, 8, kBlock><<<grid, kBlock, 0, st>>>(p, n, substeps, si, a, gso, gobs, gsi, ga);
+    else if (substeps <= 16)
+        vf_step_bwd_kernel<INTEG, ACT, LAG, 16, kBlock><<<grid, kBlock, 0, st>>>(p, n, substeps, si, a, gso, gobs, gsi, ga);
+    else
+        vf_step_bwd_kernel<INTEG, ACT, LAG, VF_MAX_SUBSTEPS_BWD, kBlock><<<grid, kBlock, 0, st>>>(p, n, substeps, si, a, gso, gobs, gsi, ga);
+}
+
+#define VF_DISPATCH(FN, ...)                                                                  \
+    do {                                                                                      \
+        const bool lag = (flags & VF_FLAG_CTRL_DELAY) != 0;                                   \
+        if (integrator == VF_INTEGRATOR_RK4) {                                                \
+            if (action_type == VF_ACTION_BODYRATE) {                                          \
+                if (lag) FN<VF_INTEGRATOR_RK4, VF_ACTION_BODYRATE, true>(__VA_ARGS__);        \
+                else     FN<VF_INTEGRATOR_RK4, VF_ACTION_BODYRATE, false>(__VA_ARGS__);       \
+            } else {                                                                          \
+                if (lag) FN<VF_INTEGRATOR_RK4, VF_ACTION_THRUST, true>(__VA_ARGS__);          \
+                else     FN<VF_INTEGRATOR_RK4, VF_ACTION_THRUST, false>(__VA_ARGS__);         \
+            }                                                                                 \
+        } else {                                                                              \
+            if (action_type == VF_ACTION_BODYRATE) {                                          \
+                if (lag) FN<VF_INTEGRATOR_EULER, VF_ACTION_BODYRATE, true>(__VA_ARGS__);      \
+                else     FN<VF_INTEGRATOR_EULER, VF_ACTION_BODYRATE, false>(__VA_ARGS__);     \
+            } else {                                                                          \
+                if (lag) FN<VF_INTEGRATOR_EULER, VF_ACTION_THRUST, true>(__VA_ARGS__);        \
+                else     FN<VF_INTEGRATOR_EULER, VF_ACTION_THRUST, false>(__VA_ARGS__);       \
+            }                                                                                 \
+        }                                                                                     \
+    } while (0)
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// C-ABI
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+int vf_abi_version(void) { return VF_ABI_VERSION; }
+
+const char* vf_last_error(void) { return g_last_error.c_str(); }
+
+int vf_params_size(void) { return int(sizeof(VfParams)); }
+
+int vf_device_sm_count(void) {
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
+    return sms;
+}
+
+int vf_step_fwd(const VfParams* params, int n, int substeps, int integrator, int action_type, unsigned flags,
+                const float* state_in, const float* action, float* state_out, float* obs_out, float* ext_out,
+                void* stream) {
+    if (check_common(params, n, substeps, integrator, action_type)) return 1;
+    if (n == 0) return 0;
+    if (!state_in || !action || !state_out) return fail("state_in, action and state_out must not be NULL");
+    if (state_in == state_out) return fail("state_out must not alias state_in");
+    if (!aligned16(state_in) || !aligned16(action) || !aligned16(state_out) || !aligned16(obs_out) ||
+        !aligned16(ext_out))
+        return fail("all buffers must be 16-byte aligned");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    VF_DISPATCH(launch_fwd, *params, n, substeps, state_in, action, state_out, obs_out, ext_out, st);
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return fail("vf_step_fwd launch failed", err);
+    return 0;
+}
+
+int vf_step_bwd(const VfParams* params, int n, int substeps, int integrator, int action_type, unsigned flags,
+                const float* state_in, const float* action, const float* grad_state_out, const float* grad_obs,
+                float* grad_state_in, float* grad_action, void* stream) {
+    if (check_common(params, n, substeps, integrator, action_type)) return 1;
+    if (substeps > VF_MAX_SUBSTEPS_BWD) return fail("substeps exceeds VF_MAX_SUBSTEPS_BWD for the reverse sweep");
+    if (n == 0) return 0;
+    if (!state_in || !action || !grad_state_in || !grad_action)
+        return fail("state_in, action, grad_state_in and grad_action must not be NULL");
+    if (!aligned16(state_in) || !aligned16(action) || !aligned16(grad_state_out) || !aligned16(grad_obs) ||
+        !aligned16(grad_state_in) || !aligned16(grad_action))
+        return fail("all buffers must be 16-byte aligned");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    VF_DISPATCH(launch_bwd, *params, n, substeps, state_in, action, grad_state_out, grad_obs, grad_state_in,
+                grad_action, st);
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return fail("vf_step_bwd launch failed", err);
+    return 0;
+}
+
+int vf_step_fwd_host(const VfParams* params, int n, int substeps, int integrator, int action_type,
+                     unsigned flags, const float* state_in, const float* action_host, float* action_dev,
+                     float* state_out, float* obs_dev, float* obs_host, void* stream) {
+    if (!action_host || !action_dev) return fail("action_host and action_dev must not be NULL");
+    if ((obs_host == nullptr) != (obs_dev == nullptr)) return fail("obs_host and obs_dev must be given together");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaError_t err = cudaMemcpyAsync(action_dev, action_host, sizeof(float) * 4 * size_t(n),
+                                      cudaMemcpyHostToDevice, st);
+    if (err != cudaSuccess) return fail("vf_step_fwd_host: H2D copy of the actions failed", err);
+    if (vf_step_fwd(params, n, substeps, integrator, action_type, flags, state_in, action_dev, state_out, obs_dev,
+                    nullptr, stream))
+        return 1;
+    if (obs_host) {
+        err = cudaMemcpyAsync(obs_host, obs_dev, sizeof(float) * VF_OBS_FLOATS * size_t(n),
+                              cudaMemcpyDeviceToHost, st);
+        if (err != cudaSuccess) return fail("vf_step_fwd_host: D2H copy of the observation failed", err);
+    }
+    err = cudaStreamSynchronize(st);
+    if (err != cudaSuccess) return fail("vf_step_fwd_host: stream synchronise failed", err);
+    return 0;
+}
+
+int vf_pack_state(int n, int m, const long long* index, const float* pos, const float* quat, const float* vel,
+                  const float* rate, const float* motor, const float* alpha, float* state, void* stream) {
+    if (n < 0 || m < 0) return fail("n and m must be >= 0");
+    if (m == 0) return 0;
+    if (!state || !aligned16(state)) return fail("state must be a 16-byte aligned device pointer");
+    vf_pack_kernel<<<(m + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(n, m, index, pos, quat, vel,
+                                                                                   rate, motor, alpha, state);
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return fail("vf_pack_state launch failed", err);
+    return 0;
+}
+
+int vf_unpack_state(int n, const float* state, float* pos, float* quat, float* vel, float* rate, float* motor,
+                    float* alpha, void* stream) {
+    if (n < 0) return fail("n must be >= 0");
+    if (n == 0) return 0;
+    if (!state || !aligned16(state)) return fail("state must be a 16-byte aligned device pointer");
+    vf_unpack_kernel<<<(n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(n, state, pos, quat, vel,
+                                                                                     rate, motor, alpha);
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return fail("vf_unpack_state launch failed", err);
+    return 0;
+}
+
+}  // extern "C"

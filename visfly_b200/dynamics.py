@@ -1,0 +1,383 @@
+"""Drop-in ``Dynamics`` (reference envs/base/dynamics.py:19-826) on top of the fused sm_100a control-step kernel.
+
+Same constructor keywords, methods and properties as the reference class, so ``DroneEnvsBase`` and task code
+keep working; what is different is where the work happens:
+
+* the whole control step (command de-normalisation, body-rate PID, thrust clamp, ``ctrl_dt/dt`` sub-steps of
+  rotor lag / allocation / drag / Euler-or-RK4 / renormalisation, post-step clamps, the ``state`` view) is ONE
+  kernel launch (``vf_step_fwd``) instead of ~2 000 (Euler x4) to ~8 000 (RK4 x8) aten ops;
+* its gradient is ONE launch of the hand-derived adjoint kernel (``vf_step_bwd``) behind a
+  ``torch.autograd.Function``; nothing but the step's inputs is kept for the backward pass (the reference's
+  autograd graph keeps ~7.9 KB per agent per control step);
+* the agent state lives in HBM as five planes of float4 (see include/visfly_b200.h); the (N,k) tensors the
+  reference's properties return are views of the kernel's outputs;
+* there is no CPU implementation: without the CUDA extension every call raises.
+
+Deliberate deviations from the reference (documented in DESIGN.md): inputs of ``reset`` are copied (the
+reference aliases and later mutates them); the two per-step device synchronising asserts
+(dynamics.py:333, droneGymEnv.py:144) are opt-in via ``debug_checks``; ``t`` after a partial reset is 0 unless
+``random_reset_time=True`` (reference draws U(0, 2*pi), C9); action types ``velocity`` / ``position``,
+string wind functions and ``drag_random`` are not fused yet and raise ``NotImplementedError``.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+import torch as th
+
+from . import _lib
+from .maths import Quaternion
+from .params import action_scaling, build_vf_params, load_drone_model
+from .type import ACTION_TYPE
+
+_ALIAS = {"thrust": ACTION_TYPE.THRUST, "bodyrate": ACTION_TYPE.BODYRATE,
+          "velocity": ACTION_TYPE.VELOCITY, "position": ACTION_TYPE.POSITION}
+
+
+class StepConfig:
+    """Everything ``vf_step_fwd`` / ``vf_step_bwd`` need besides tensors (immutable per Dynamics object)."""
+
+    __slots__ = ("params", "substeps", "integrator", "action_type", "flags")
+
+    def __init__(self, params, substeps, integrator, action_type, flags):
+        self.params, self.substeps, self.integrator = params, substeps, integrator
+        self.action_type, self.flags = action_type, flags
+
+
+class ControlStep(th.autograd.Function):
+    """``(state[5,N,4], action[N,4]) -> (state'[5,N,4], obs[N,13])`` — one kernel each way."""
+
+    @staticmethod
+    def forward(ctx, state: th.Tensor, action: th.Tensor, cfg: StepConfig):
+        state_out = th.empty_like(state)
+        obs = th.empty((state.shape[1], 13), dtype=th.float32, device=state.device)
+        _lib.step_fwd(cfg.params, cfg.substeps, cfg.integrator, cfg.action_type, cfg.flags,
+                      state, action, state_out, obs, None)
+        ctx.cfg = cfg
+        ctx.save_for_backward(state, action)
+        ctx.set_materialize_grads(False)
+        return state_out, obs
+
+    @staticmethod
+    @th.autograd.function.once_differentiable
+    def backward(ctx, g_state_out, g_obs):
+        state, action = ctx.saved_tensors
+        cfg = ctx.cfg
+        g_state = th.empty_like(state)
+        g_action = th.empty_like(action)
+        if g_state_out is not None:
+            g_state_out = g_state_out.contiguous()
+        if g_obs is not None:
+            g_obs = g_obs.contiguous()
+        _lib.step_bwd(cfg.params, cfg.substeps, cfg.integrator, cfg.action_type, cfg.flags,
+                      state, action, g_state_out, g_obs, g_state, g_action)
+        return g_state, g_action, None
+
+
+class Dynamics:
+    action_type_alias: Dict = _ALIAS
+
+    def __init__(
+            self,
+            num: int = 1,
+            action_type: str = "bodyrate",
+            ori_output_type: str = "quaternion",
+            seed: int = 42,
+            dt: float = 0.005,
+            ctrl_dt: float = 0.03,
+            ctrl_delay: bool = True,
+            comm_delay: float = 0.06,
+            action_space: Tuple[float, float] = (-1, 1),
+            device: Union[str, th.device] = "cuda",
+            integrator: str = "euler",
+            drag_random: float = 0,
+            cfg: str = "drone_state",
+            wind_settings: Optional[List] = (0, 0, 0),
+            rotor_sim: bool = True,
+            debug_checks: bool = False,
+            random_reset_time: bool = False,
+    ):
+        assert action_type in ["bodyrate", "thrust", "velocity", "position"]
+        assert ori_output_type in ["quaternion", "euler"]
+        if integrator not in ("euler", "rk4"):
+            raise ValueError("type should be one of ['euler', 'rk4']")
+        self.device = th.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError(
+                "visfly_b200.Dynamics computes on a CUDA device only (sm_100a kernels, no CPU fallback); "
+                f"got device={device!r}")
+        if self.device.index is None:
+            self.device = th.device("cuda", th.cuda.current_device() if th.cuda.is_available() else 0)
+        _lib.load(require_cuda=True)
+
+        self.num = num
+        self.action_type = _ALIAS[action_type]
+        self.angular_output_type = ori_output_type
+        self._is_quat_output = ori_output_type == "quaternion"
+        self.dt, self.ctrl_dt = dt, ctrl_dt
+        if not th.as_tensor(ctrl_dt) % th.as_tensor(dt) == 0:
+            raise ValueError("ctrl_dt should be a multiple of dt")
+        self._interval_steps = int(ctrl_dt / dt)
+        self._comm_delay_steps = int(comm_delay / ctrl_dt)
+        self._integrator = integrator
+        self._ctrl_delay = ctrl_delay
+        self._rotor_sim = rotor_sim
+        self._debug_checks = debug_checks
+        self._random_reset_time = random_reset_time
+        if drag_random:
+            raise NotImplementedError("drag_random (per-agent drag coefficients) is not fused yet")
+        self._drag_random = drag_random
+
+        self.set_seed(seed)
+        self._model = load_drone_model(cfg, dt)
+        self.m = self._model.m.to(self.device)
+        self.name = self._model.name
+        self._normal_params = action_scaling(self._model, self.action_type, action_space)
+        self._wind = self._parse_wind(wind_settings)
+        self._params = build_vf_params(self._model, self.action_type, self._normal_params, self._wind)
+        for v in self._normal_params.values():
+            v.to(self.device)
+        self._bd_thrust = self._model.bd_thrust
+        self._init_thrust = self._model.init_thrust.to(self.device)
+        self._init_motor_omega = self._model.init_motor_omega.to(self.device)
+        self.wind_velocity = th.tensor(self._wind, dtype=th.float32, device=self.device).reshape(3, 1)
+        self._cfg = StepConfig(self._params, self._interval_steps, _lib.INTEGRATOR_ID[integrator],
+                               self.action_type.value, _lib.FLAG_CTRL_DELAY if ctrl_delay else 0)
+        self._ext = None
+        self._prev = None
+        self.reset()
+
+    # ------------------------------------------------------------------------------------------
+    @staticmethod
+    def _parse_wind(wind_settings) -> Tuple[float, float, float]:
+        if wind_settings is None:
+            return (0.0, 0.0, 0.0)
+        if isinstance(wind_settings, (list, tuple)) and len(wind_settings) == 3 and \
+                all(isinstance(w, (int, float)) for w in wind_settings):
+            return tuple(float(w) for w in wind_settings)
+        raise NotImplementedError("only constant wind [wx, wy, wz] is fused; string wind functions "
+                                  "(reference dynamics.py:136-165) are out of scope for now")
+
+    def set_seed(self, seed=42):
+        th.manual_seed(seed)
+
+    def close(self):
+        pass
+
+    def _f(self, x, cols):
+        """(n,cols) float32 contiguous copy on the engine's device."""
+        t = x.detach() if isinstance(x, th.Tensor) else th.as_tensor(x)
+        return t.to(device=self.device, dtype=th.float32, copy=True).reshape(-1, cols).contiguous()
+
+    def _assemble(self, n, pos, ori, vel, ori_vel, motor_omega):
+        """Rows of packed state (5,n,4) and observation (n,13) for freshly (re)initialised agents."""
+        dev = self.device
+        pos = th.zeros((n, 3), device=dev) if pos is None else self._f(pos, 3)
+        vel = th.zeros((n, 3), device=dev) if vel is None else self._f(vel, 3)
+        rate = th.zeros((n, 3), device=dev) if ori_vel is None else self._f(ori_vel, 3)
+        if ori is None:
+            quat = th.zeros((n, 4), device=dev)
+            quat[:, 0] = 1
+        else:
+            quat = self._f(ori, 4)
+        motor = self._init_motor_omega.expand(n, 4) if motor_omega is None else self._f(motor_omega, 4)
+        zero = th.zeros((n, 1), device=dev)       # angular acceleration restarts at 0 (dynamics.py:239,258)
+        packed = th.stack([th.cat([pos, zero], 1), quat, th.cat([vel, zero], 1), th.cat([rate, zero], 1),
+                           motor.to(th.float32)])
+        obs = th.cat([pos, quat, vel + self.wind_velocity.T, rate], 1)
+        return packed.contiguous(), obs.contiguous()
+
+    def reset(self, pos=None, ori=None, vel=None, ori_vel=None, motor_omega=None, thrusts=None, t=None,
+              indices=None):
+        """Reference ``Dynamics.reset`` (dynamics.py:218-269); inputs are (n,k) row-major and are copied."""
+        dev = self.device
+        if indices is None:
+            n = self.num
+            self._state, self._obs = self._assemble(n, pos, ori, vel, ori_vel, motor_omega)
+            self._thrusts_override = None if thrusts is None else self._f(thrusts, 4)
+            self._t_base = th.zeros((n,), device=dev) if t is None else \
+                th.as_tensor(t, dtype=th.float32, device=dev).reshape(n).clone()
+            self._n_steps = 0
+            self._acc = th.zeros((n, 3), device=dev)
+            self._pre_action = [th.zeros((n, 4), device=dev) for _ in range(self._comm_delay_steps)]
+        else:
+            idx = th.as_tensor(indices, device=dev, dtype=th.int64).reshape(-1)
+            m = idx.numel()
+            rows, obs_rows = self._assemble(m, pos, ori, vel, ori_vel, motor_omega)
+            # functional masked overwrite: the reset agents' upstream gradient is cut, the fresh state is a
+            # constant — the reference's in-place index_put gives exactly this (dynamics.py:249-263, App. F)
+            self._state = self._state.index_copy(1, idx, rows)
+            self._obs = self._obs.index_copy(0, idx, obs_rows)
+            if t is None:
+                t_new = th.rand((m,), device=dev) * 3.14 * 2 if self._random_reset_time else th.zeros((m,), device=dev)
+            else:
+                t_new = th.as_tensor(t, dtype=th.float32, device=dev).reshape(m)
+            self._t_base = self._t_base.index_copy(0, idx, t_new - self._n_steps * self.ctrl_dt)
+            self._acc = self._acc.index_fill(0, idx, 0.0)
+            self._pre_action = [a.index_fill(0, idx, 0.0) for a in self._pre_action]
+            if thrusts is not None or self._thrusts_override is not None:
+                base = self.thrusts.detach().clone()
+                base[idx] = self._init_thrust if thrusts is None else self._f(thrusts, 4)
+                self._thrusts_override = base
+        self._ext, self._prev = None, None
+        return self.state
+
+    def detach(self):
+        """Cut the autograd graph at the current state (reference dynamics.py:176-190)."""
+        self._state = self._state.detach()
+        self._obs = self._obs.detach()
+        self._acc = self._acc.detach()
+        self._pre_action = [a.detach() for a in self._pre_action]
+
+    # ------------------------------------------------------------------------------------------
+    def step(self, action) -> th.Tensor:
+        """One control step; ``action`` is (N,4) in ``action_space``; returns ``state`` (reference :319-372)."""
+        if not isinstance(action, th.Tensor):
+            action = th.from_numpy(np.asarray(action))
+        action = action.to(device=self.device, dtype=th.float32)
+        if action.shape != (self.num, 4):
+            raise ValueError(f"action must have shape ({self.num}, 4), got {tuple(action.shape)}")
+        if self._comm_delay_steps:                                   # dynamics.py:323-326
+            self._pre_action.append(action)
+            action = self._pre_action.pop(0)
+        action = action.contiguous()
+        self._prev = (self._state.detach(), action.detach())
+        self._state, self._obs = ControlStep.apply(self._state, action, self._cfg)
+        self._n_steps += 1
+        self._ext = None
+        self._thrusts_override = None
+        if self._debug_checks:                                       # dynamics.py:333 (device sync!)
+            assert bool(th.isfinite(self._obs).all()), "non-finite state after step"
+        return self.state
+
+    def _extras(self) -> th.Tensor:
+        """(N,8) [acc, 0, thrusts] of the last sub-step; produced on demand by re-running the step kernel on
+        the saved inputs (the hot loop never pays for diagnostics nobody reads)."""
+        if self._ext is None:
+            ext = th.empty((self.num, 8), dtype=th.float32, device=self.device)
+            if self._prev is None:
+                ext.zero_()
+                ext[:, 4:] = self._model.thrust_from_rotor_omega(self._state[4].detach()) \
+                    if self._thrusts_override is None else self._thrusts_override
+            else:
+                scratch = th.empty_like(self._prev[0])
+                _lib.step_fwd(self._cfg.params, self._cfg.substeps, self._cfg.integrator, self._cfg.action_type,
+                              self._cfg.flags, self._prev[0], self._prev[1], scratch, None, ext)
+            self._ext = ext
+        return self._ext
+
+    # ------------------------------------------------------------------------------------------
+    def _normalize(self, action):
+        """real units -> [-1,1] (reference dynamics.py:271-317; used by deployment code only)."""
+        if not isinstance(action, th.Tensor):
+            action = th.from_numpy(np.asarray(action))
+        action = action.to(self.device)
+        p = self._normal_params
+        if self.action_type == ACTION_TYPE.BODYRATE:
+            return th.hstack([(action[:, :1] - p["acc"].mean) / p["acc"].half,
+                              (action[:, 1:] - p["bodyrate"].mean) / p["bodyrate"].half])
+        if self.action_type == ACTION_TYPE.THRUST:
+            return (action - p["acc"].mean) / p["acc"].half
+        return th.hstack([(action[:, :1] - p["yaw"].mean) / p["yaw"].half,
+                          (action[:, 1:] - p["velocity"].mean) / p["velocity"].half])
+
+    def _de_normalize(self, command):
+        """[-1,1] -> real units, same return layout as the reference (dynamics.py:692-733)."""
+        if not isinstance(command, th.Tensor):
+            command = th.from_numpy(np.asarray(command))
+        command = command.to(self.device)
+        p = self._normal_params
+        if self.action_type == ACTION_TYPE.BODYRATE:
+            return th.hstack([(command[:, :1] * p["acc"].half + p["acc"].mean) * self.m,
+                              command[:, 1:] * p["bodyrate"].half + p["bodyrate"].mean]).T
+        if self.action_type == ACTION_TYPE.THRUST:
+            return self.m * (command * p["acc"].half + p["acc"].mean).T
+        return th.hstack([command[:, :1] * p["yaw"].half + p["yaw"].mean,
+                          command[:, 1:] * p["velocity"].half + p["velocity"].mean])
+
+    # -- views (reference dynamics.py:735-826) -----------------------------------------------------
+    @property
+    def _orientation(self) -> Quaternion:
+        return Quaternion.from_tensor(self._obs[:, 3:7].T)
+
+    @property
+    def position(self):
+        return self._obs[:, 0:3]
+
+    @property
+    def orientation(self):
+        if self._is_quat_output:
+            return self._obs[:, 3:7]
+        return self._orientation.toEuler().T
+
+    @property
+    def direction(self):
+        return self._orientation.x_axis.T
+
+    @property
+    def velocity(self):
+        return self._obs[:, 7:10]
+
+    @property
+    def angular_velocity(self):
+        return self._obs[:, 10:13]
+
+    @property
+    def acceleration(self):
+        return self._extras()[:, 0:3]
+
+    @property
+    def angular_acceleration(self):
+        s = self._state
+        return th.stack([s[0, :, 3], s[2, :, 3], s[3, :, 3]], 1)
+
+    @property
+    def t(self):
+        return self._t_base + self._n_steps * self.ctrl_dt
+
+    @property
+    def motor_omega(self):
+        return self._state[4]
+
+    @property
+    def thrusts(self):
+        if self._thrusts_override is not None:
+            return self._thrusts_override
+        if self._ctrl_delay:
+            return self._model.thrust_from_rotor_omega(self._state[4])   # dynamics.py:516, differentiable
+        return self._extras()[:, 4:8]
+
+    @property
+    def state(self):
+        if self._is_quat_output:
+            return self._obs
+        return th.hstack([self.position, self.orientation, self.velocity, self.angular_velocity])
+
+    @property
+    def is_quat_output(self):
+        return self._is_quat_output
+
+    @property
+    def full_state(self):
+        return th.hstack([self.position, self.orientation, self.velocity, self.angular_velocity,
+                          self.motor_omega, self.thrusts, self.t.unsqueeze(1)])
+
+    @property
+    def extend_state(self):
+        return th.hstack([self.position, self.orientation, self.velocity, self.angular_velocity,
+                          self.acceleration, self.angular_acceleration, self.motor_omega, self.thrusts,
+                          self.t.unsqueeze(1)])
+
+    @property
+    def R(self):
+        return self._orientation.R
+
+    @property
+    def xz_axis(self):
+        return self._orientation.xz_axis
+
+    @property
+    def packed_state(self) -> th.Tensor:
+        """The HBM-resident (5,N,4) state (see include/visfly_b200.h)."""
+        return self._state
