@@ -91,8 +91,8 @@ def test_forward_one_step_vs_reference_golden(cfg):
     out, obs, ext = cuda_fwd(P, pack(*before), th.from_numpy(z["action"]), S, kw["integrator"], kw["action_type"],
                              kw["ctrl_delay"], ext=True)
     assert rel_l2(obs, z["obs_f32"]) < 1e-6
-    tag = "f64" if "obs_f64" in z.files else "f32"
-    assert rel_l2(obs, z[f"obs_{tag}"]) < max(2e-7, 3 * rel_l2(z["obs_f32"], z[f"obs_{tag}"]))
+    if "obs_f64" in z.files:      # float64 reference as arbiter: as close to it as the float32 reference is
+        assert rel_l2(obs, z["obs_f64"]) < max(2e-7, 3 * rel_l2(z["obs_f32"], z["obs_f64"]))
     for k, got in zip(("pos", "quat", "vel", "rate", "motor", "alpha"), unpack(out)):
         assert rel_l2(got, z[f"after_{k}_f32"]) < 2e-6, k
     assert rel_l2(ext[:, :3], z["acc_f32"]) < 1e-5 and rel_l2(ext[:, 4:], z["thrusts_f32"]) < 1e-6
