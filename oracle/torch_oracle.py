@@ -141,10 +141,11 @@ class OracleDynamics:
     def __init__(self, num: int = 1, action_type: str = "bodyrate", dt: float = 0.005, ctrl_dt: float = 0.03,
                  ctrl_delay: bool = True, comm_delay: float = 0.06, integrator: str = "euler",
                  cfg: str = "drone_state", wind: Sequence[float] = (0, 0, 0), device="cpu",
-                 dtype=th.float32):
+                 dtype=th.float32, random_reset_time: bool = False):
         assert action_type in ("bodyrate", "thrust")
         assert integrator in ("euler", "rk4")
         self.num, self.action_type, self.integrator = num, action_type, integrator
+        self.random_reset_time = random_reset_time     # reference quirk C9: partial reset draws t ~ U(0, 6.28)
         self.dt, self.ctrl_dt, self.ctrl_delay = dt, ctrl_dt, ctrl_delay
         self.device, self.dtype = th.device(device), dtype
         if not th.as_tensor(ctrl_dt) % th.as_tensor(dt) == 0:
@@ -168,17 +169,17 @@ class OracleDynamics:
         pos, ori, vel, ori_vel, motor_omega, thrusts = map(cv, (pos, ori, vel, ori_vel, motor_omega, thrusts))
         if indices is None:
             n = self.num
-            self.pos = self._zeros(3) if pos is None else pos.T.contiguous()
+            self.pos = self._zeros(3) if pos is None else pos.T
             q = th.tensor([[1.0, 0, 0, 0]], dtype=self.dtype, device=self.device).repeat(n, 1) if ori is None else ori
-            self.q = tuple(q.T.contiguous())
-            self.vel = self._zeros(3) if vel is None else vel.T.contiguous()
-            self.ang_vel = self._zeros(3) if ori_vel is None else ori_vel.T.contiguous()
+            self.q = tuple(q.T)
+            self.vel = self._zeros(3) if vel is None else vel.T
+            self.ang_vel = self._zeros(3) if ori_vel is None else ori_vel.T
             self.thrusts = th.ones((4, n), dtype=self.dtype, device=self.device) * self.init_thrust \
-                if thrusts is None else thrusts.T.contiguous()
+                if thrusts is None else thrusts.T
             self.motor = th.ones((4, n), dtype=self.dtype, device=self.device) * self.init_omega \
-                if motor_omega is None else motor_omega.T.contiguous()
+                if motor_omega is None else motor_omega.T
             self.t = th.zeros((n,), dtype=self.dtype, device=self.device) if t is None else cv(t)
-            self.ang_acc = self._zeros(3) if ang_acc is None else cv(ang_acc).T.contiguous()
+            self.ang_acc = self._zeros(3) if ang_acc is None else cv(ang_acc).T
             self.acc = self._zeros(3)
             self.fifo: List[th.Tensor] = [self._zeros(4) for _ in range(self.fifo_depth)]
         else:
@@ -207,7 +208,10 @@ class OracleDynamics:
                           if thrusts is None else thrusts.T)
             self.thrusts = tr
             tt = self.t.clone()
-            tt[idx] = th.zeros((m,), dtype=self.dtype, device=self.device) if t is None else cv(t)
+            if t is None and self.random_reset_time:                              # dynamics.py:256
+                tt[idx] = th.zeros((m,), dtype=self.dtype, device=self.device) + th.rand((m,)) * 3.14 * 2
+            else:
+                tt[idx] = th.zeros((m,), dtype=self.dtype, device=self.device) if t is None else cv(t)
             self.t = tt
             self.ang_acc = put(self.ang_acc, None, 3)
             self.acc = put(self.acc, None, 3)

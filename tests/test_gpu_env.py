@@ -1,0 +1,136 @@
+"""The product's Gym-style envs (visfly_b200.envs, CUDA dynamics underneath) against golden runs of the real
+reference envs: observations, rewards, termination flags, episode records, auto-reset, and autograd gradients
+through a requires_grad rollout.  Inputs are the recorded ones (start table, action sequence)."""
+import copy
+import os
+
+import numpy as np
+import pytest
+import torch as th
+
+from _env_util import DYN, GOLD, episode_records, load_env_golden, table_of
+from _util import rel_l2
+
+pytestmark = pytest.mark.gpu
+TASKS = ["hover", "navigation", "racing2"]
+
+
+def make_env(task, n, integ, max_episode_steps, table, **kw):
+    from visfly_b200.envs import HoverEnv, NavigationEnv, RacingEnv2
+    cls = {"hover": HoverEnv, "navigation": NavigationEnv, "racing2": RacingEnv2}[task]
+    if task == "hover":
+        kw.setdefault("tensor_output", True)
+    env = cls(num_agent_per_scene=n, visual=False, device="cuda", dynamics_kwargs=dict(DYN[integ], comm_delay=0.06),
+              max_episode_steps=max_episode_steps, **kw)
+    tbl = tuple(x.cuda() for x in table)
+
+    def generate(indices=None, num=None):
+        if indices is None:
+            return tbl
+        idx = th.as_tensor(indices, device="cuda")
+        return tuple(x[idx] for x in tbl)
+
+    env.envs._generate_state = generate
+    return env
+
+
+@pytest.mark.parametrize("task", TASKS)
+@pytest.mark.parametrize("integ", ["euler", "rk4"])
+def test_env_replays_reference_golden(task, integ):
+    z = load_env_golden(task, integ)
+    acts = th.from_numpy(z["actions"]).cuda()
+    T, n = acts.shape[:2]
+    env = make_env(task, n, integ, int(z["max_episode_steps"]), table_of(z))
+    obs = env.reset()
+    ref0 = z["reset_obs_state"]
+    cols = slice(6, None) if task == "racing2" else slice(None)    # reference reset() returns stale gate columns
+    assert rel_l2(obs["state"].cpu()[:, cols], ref0[:, cols]) < 1e-6
+    for t in range(T):
+        obs, r, d, info = env.step(acts[t])
+        assert isinstance(r, th.Tensor) and r.shape == (n,) and d.dtype == th.bool
+        assert np.array_equal(d.cpu().numpy(), z["done"][t]), t
+        assert rel_l2(obs["state"].cpu(), z["obs_state"][t]) < 1e-5, t
+        if "gate" in obs:
+            assert np.array_equal(obs["gate"].cpu().numpy(), z["obs_gate"][t])
+        if "target" in obs:
+            assert np.array_equal(obs["target"].cpu().numpy(), z["obs_target"][t])
+        np.testing.assert_allclose(r.cpu().numpy(), z["reward"][t], rtol=1e-4, atol=1e-5)
+        er, el, tr, sc, co, pg = episode_records(d.cpu().numpy(), info, n)
+        np.testing.assert_allclose(er, z["episode_r"][t], rtol=1e-4, atol=1e-5)
+        assert np.array_equal(el, z["episode_l"][t]) and np.array_equal(tr, z["truncated"][t])
+        assert np.array_equal(sc, z["is_success"][t]) and np.array_equal(co, z["collision"][t])
+        assert np.array_equal(pg, z["past_gate"][t])
+        idle = [i for i in range(n) if not z["done"][t][i]][:2]
+        for i in idle:
+            assert info[i] == {"TimeLimit.truncated": False, "episode_done": False}
+
+
+@pytest.mark.parametrize("integ", ["euler", "rk4"])
+def test_env_rollout_gradients_match_reference_autograd(integ):
+    z = np.load(os.path.join(GOLD, "envgrad_navigation.npz"))
+    acts = th.from_numpy(z["actions"]).cuda().requires_grad_(True)
+    H, n = acts.shape[:2]
+    env = make_env("navigation", n, integ, int(z["max_episode_steps"]), table_of(z), requires_grad=True)
+    env.reset()
+    loss = 0.0
+    for t in range(H):
+        obs, r, d, info = env.step(acts[t])
+        assert r.requires_grad
+        loss = loss - (0.99 ** t) * r
+    loss = loss.mean()
+    g, = th.autograd.grad(loss, acts)
+    assert abs(loss.item() - float(z[f"loss_{integ}"])) < 1e-5
+    assert rel_l2(g.cpu(), z[f"grad_actions_{integ}"]) < 1e-4
+    env.detach()
+    assert not env.envs.dynamics.packed_state.requires_grad
+
+
+def test_output_modes_spaces_and_deepcopy():
+    from visfly_b200.envs import HoverEnv, NavigationEnv
+    n = 64
+    dyn = dict(DYN["euler"])
+    env = HoverEnv(num_agent_per_scene=n, visual=False, dynamics_kwargs=dyn, max_episode_steps=4)   # numpy mode
+    assert env.observation_space["state"].shape == (13,) and env.action_space.shape == (4,)
+    assert env.num_envs == n and len(env) == n
+    obs = env.reset()
+    assert isinstance(obs["state"], np.ndarray) and obs["state"].shape == (n, 13)
+    with pytest.raises(AssertionError):
+        HoverEnv(num_agent_per_scene=2, visual=False, dynamics_kwargs=dyn).step(np.zeros((2, 4)))    # step before reset
+    for t in range(5):
+        obs, r, d, info = env.step(np.random.uniform(-1, 1, (n, 4)).astype(np.float32))
+        assert isinstance(obs["state"], np.ndarray) and isinstance(r, np.ndarray) and d.dtype == np.int32
+    assert d.sum() == 0 and len(info) == n        # step 4 ended every episode, step 5 is the first of the next ones
+    nav = NavigationEnv(num_agent_per_scene=n, visual=False, dynamics_kwargs=dyn, requires_grad=True,
+                        random_kwargs={"state_generator": {"class": "Uniform", "kwargs": [
+                            {"position": {"mean": [2., 0., 1.5], "half": [1.0, 1.0, 0.5]}}]}})
+    assert "target" in nav.observation_space.spaces
+    nav.reset()
+    twin = copy.deepcopy(nav)                       # reference utils/algorithms/shac.py:121 deep-copies the env
+    a = th.zeros(n, 4, device="cuda")
+    o1 = nav.step(a)[0]["state"]
+    o2 = twin.step(a)[0]["state"]
+    assert th.equal(o1, o2)
+    nav.requires_grad = False                        # settable (reference PPO.py:80-82)
+    nav.tensor_output = True
+    assert not nav.step(a)[1].requires_grad
+    with pytest.raises(NotImplementedError):
+        HoverEnv(num_agent_per_scene=2, visual=True)
+
+
+def test_random_state_generators_cover_the_configured_box():
+    from visfly_b200.envs import HoverEnv, RacingEnv2
+    n = 4096
+    env = HoverEnv(num_agent_per_scene=n, visual=False, dynamics_kwargs=dict(DYN["euler"]), tensor_output=True)
+    p = env.reset()["state"][:, :3]
+    lo, hi = th.tensor([0., -1, 1], device="cuda"), th.tensor([2., 1, 2], device="cuda")
+    assert bool((p >= lo).all() and (p <= hi).all())
+    assert float((p.mean(0) - th.tensor([1., 0, 1.5], device="cuda")).abs().max()) < 0.05
+    race = RacingEnv2(num_agent_per_scene=n, visual=False, dynamics_kwargs=dict(DYN["euler"]))
+    race.reset()
+    centres = th.tensor([[2., 2., 1], [6., 2., 1.5], [6., -2., 1.5], [2., 0., 1]], device="cuda")
+    dist = (race.position.unsqueeze(1) - centres).abs().amax(dim=2)
+    which = dist.argmin(dim=1)
+    assert bool((dist.amin(dim=1) <= 0.2 + 1e-6).all())
+    assert all(abs(float((which == k).float().mean()) - 0.25) < 0.05 for k in range(4))
+    # first gate from the start box (reference RacingEnv._choose_target)
+    assert bool((race._next_target_i[which == 0] == 0).all() and (race._next_target_i[which == 1] == 1).all())

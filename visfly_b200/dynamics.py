@@ -144,8 +144,6 @@ class Dynamics:
         self.wind_velocity = th.tensor(self._wind, dtype=th.float32, device=self.device).reshape(3, 1)
         self._cfg = StepConfig(self._params, self._interval_steps, _lib.INTEGRATOR_ID[integrator],
                                self.action_type.value, _lib.FLAG_CTRL_DELAY if ctrl_delay else 0)
-        self._ext = None
-        self._prev = None
         self.reset()
 
     # ------------------------------------------------------------------------------------------
@@ -195,12 +193,12 @@ class Dynamics:
         if indices is None:
             n = self.num
             self._state, self._obs = self._assemble(n, pos, ori, vel, ori_vel, motor_omega)
-            self._thrusts_override = None if thrusts is None else self._f(thrusts, 4)
             self._t_base = th.zeros((n,), device=dev) if t is None else \
                 th.as_tensor(t, dtype=th.float32, device=dev).reshape(n).clone()
             self._n_steps = 0
-            self._acc = th.zeros((n, 3), device=dev)
             self._pre_action = [th.zeros((n, 4), device=dev) for _ in range(self._comm_delay_steps)]
+            self._prev, self._ext, self._fresh = None, None, None
+            self._thrusts_given = None if thrusts is None else self._f(thrusts, 4)
         else:
             idx = th.as_tensor(indices, device=dev, dtype=th.int64).reshape(-1)
             m = idx.numel()
@@ -214,20 +212,44 @@ class Dynamics:
             else:
                 t_new = th.as_tensor(t, dtype=th.float32, device=dev).reshape(m)
             self._t_base = self._t_base.index_copy(0, idx, t_new - self._n_steps * self.ctrl_dt)
-            self._acc = self._acc.index_fill(0, idx, 0.0)
             self._pre_action = [a.index_fill(0, idx, 0.0) for a in self._pre_action]
-            if thrusts is not None or self._thrusts_override is not None:
+            fresh = th.zeros((self.num,), dtype=th.bool, device=dev).index_fill(0, idx, True)
+            self._mark_fresh(fresh)
+            if thrusts is not None:
                 base = self.thrusts.detach().clone()
-                base[idx] = self._init_thrust if thrusts is None else self._f(thrusts, 4)
-                self._thrusts_override = base
-        self._ext, self._prev = None, None
+                base[idx] = self._f(thrusts, 4)
+                self._thrusts_given = base
         return self.state
+
+    def reset_where(self, mask: th.Tensor, pos=None, ori=None, vel=None, ori_vel=None, motor_omega=None, t=None):
+        """Mask form of the partial reset: ``pos`` etc. are full (N,k) batches, rows where ``mask`` is True
+        replace the current state.  Same semantics as ``reset(indices=where(mask))`` (gradient of the replaced
+        agents is cut, FIFO rows zeroed) but with no device->host round trip, so it can sit in the step loop."""
+        n = self.num
+        mask = mask.to(self.device).reshape(n)
+        rows, obs_rows = self._assemble(n, pos, ori, vel, ori_vel, motor_omega)
+        self._state = th.where(mask.view(1, n, 1), rows, self._state)
+        m1 = mask.view(n, 1)
+        self._obs = th.where(m1, obs_rows, self._obs)
+        if t is None:
+            t_new = th.rand((n,), device=self.device) * 3.14 * 2 if self._random_reset_time else 0.0
+        else:
+            t_new = th.as_tensor(t, dtype=th.float32, device=self.device).reshape(n)
+        self._t_base = th.where(mask, t_new - self._n_steps * self.ctrl_dt, self._t_base)
+        self._pre_action = [th.where(m1, 0.0, a) for a in self._pre_action]
+        self._mark_fresh(mask)
+        return self.state
+
+    def _mark_fresh(self, mask: th.Tensor):
+        """Agents re-initialised since the last step: their diagnostics (acceleration, thrusts) read as the
+        reset values (reference dynamics.py:254,259) instead of the last step's."""
+        self._fresh = mask if self._fresh is None else (self._fresh | mask)
+        self._ext = None
 
     def detach(self):
         """Cut the autograd graph at the current state (reference dynamics.py:176-190)."""
         self._state = self._state.detach()
         self._obs = self._obs.detach()
-        self._acc = self._acc.detach()
         self._pre_action = [a.detach() for a in self._pre_action]
 
     # ------------------------------------------------------------------------------------------
@@ -245,8 +267,7 @@ class Dynamics:
         self._prev = (self._state.detach(), action.detach())
         self._state, self._obs = ControlStep.apply(self._state, action, self._cfg)
         self._n_steps += 1
-        self._ext = None
-        self._thrusts_override = None
+        self._ext, self._fresh, self._thrusts_given = None, None, None
         if self._debug_checks:                                       # dynamics.py:333 (device sync!)
             assert bool(th.isfinite(self._obs).all()), "non-finite state after step"
         return self.state
@@ -255,15 +276,17 @@ class Dynamics:
         """(N,8) [acc, 0, thrusts] of the last sub-step; produced on demand by re-running the step kernel on
         the saved inputs (the hot loop never pays for diagnostics nobody reads)."""
         if self._ext is None:
-            ext = th.empty((self.num, 8), dtype=th.float32, device=self.device)
+            ext = th.zeros((self.num, 8), dtype=th.float32, device=self.device)
+            rest = self._model.thrust_from_rotor_omega(self._state[4].detach())
             if self._prev is None:
-                ext.zero_()
-                ext[:, 4:] = self._model.thrust_from_rotor_omega(self._state[4].detach()) \
-                    if self._thrusts_override is None else self._thrusts_override
+                ext[:, 4:] = rest
             else:
                 scratch = th.empty_like(self._prev[0])
                 _lib.step_fwd(self._cfg.params, self._cfg.substeps, self._cfg.integrator, self._cfg.action_type,
                               self._cfg.flags, self._prev[0], self._prev[1], scratch, None, ext)
+                if self._fresh is not None:
+                    m1 = self._fresh.view(-1, 1)
+                    ext = th.cat([th.where(m1, 0.0, ext[:, :4]), th.where(m1, rest, ext[:, 4:])], 1)
             self._ext = ext
         return self._ext
 
@@ -342,8 +365,8 @@ class Dynamics:
 
     @property
     def thrusts(self):
-        if self._thrusts_override is not None:
-            return self._thrusts_override
+        if self._thrusts_given is not None:
+            return self._thrusts_given
         if self._ctrl_delay:
             return self._model.thrust_from_rotor_omega(self._state[4])   # dynamics.py:516, differentiable
         return self._extras()[:, 4:8]

@@ -1,0 +1,401 @@
+"""``DroneGymEnvsBase`` — the Gym/SB3-style vectorised wrapper (surface of reference
+envs/base/droneGymEnv.py:19-633): ``reset() -> obs``, ``step(a) -> (obs, reward, done, info)``, the three output
+modes (tensors with grad / detached tensors / numpy), reward accumulation, success / failure / out-of-bounds /
+collision / time-limit termination, per-episode ``info`` records and auto-reset of finished agents.
+
+Differences that make it run at 65 536+ agents (the reference's wrapper caps at ~2.5e5 agent-steps/s because of
+per-agent Python loops):
+  * bookkeeping is functional tensor code on the device, no per-agent loops and no host synchronisation in
+    ``step``; finished agents are re-initialised with a mask blend (``reset_agents_where``);
+  * ``info`` is a lazy sequence: dictionaries with the reference's keys (droneGymEnv.py:238-275) are built only
+    for the entries somebody reads;
+  * the range assert on the action (a device sync per step, droneGymEnv.py:144) is opt-in (``debug_checks``);
+  * task methods receive ``predicted_obs=None`` uniformly (the reference's Hover/Racing envs crash on it, C4).
+World-model latent hooks (``world``, ``deter``/``stoch``) are not part of this path.
+"""
+from __future__ import annotations
+
+import contextlib
+from collections.abc import Sequence
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch as th
+
+from ...type import ACTION_TYPE, TensorDict
+from ._compat import VecEnv, spaces
+from .droneEnv import DroneEnvsBase
+
+
+class LazyInfo(Sequence):
+    """Per-agent info dicts materialised on demand from one snapshot of device tensors."""
+
+    _IDLE = {"TimeLimit.truncated": False, "episode_done": False}
+
+    def __init__(self, n, done, episode_done, success, step_count, rewards, once_collided, terminal_obs,
+                 max_episode_steps, ctrl_dt, indiv_rewards=None, extra_fn=None, detach_obs=True):
+        self._n = n
+        self._dev = dict(done=done, episode_done=episode_done, success=success, step_count=step_count,
+                         rewards=rewards, once_collided=once_collided)
+        self._terminal_obs, self._indiv, self._extra_fn = terminal_obs, indiv_rewards, extra_fn
+        self._max_steps, self._ctrl_dt, self._host = max_episode_steps, ctrl_dt, None
+        self._cache: Dict[int, dict] = {}
+
+    def _fetch(self):
+        if self._host is None:        # one batched device->host transfer, only if somebody looks
+            self._host = {k: v.detach().cpu().numpy() for k, v in self._dev.items()}
+        return self._host
+
+    def __len__(self):
+        return self._n
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[j] for j in range(*i.indices(self._n))]
+        if i < 0:
+            i += self._n
+        if not 0 <= i < self._n:
+            raise IndexError(i)
+        if i in self._cache:
+            return self._cache[i]
+        h = self._fetch()
+        if not h["done"][i]:
+            info = dict(self._IDLE)
+        else:
+            length = h["step_count"][i]
+            info = {
+                "episode_done": bool(h["episode_done"][i]),
+                "is_success": bool(h["success"][i]),
+                "episode": {"r": h["rewards"][i], "l": length, "t": np.asarray(length * self._ctrl_dt),
+                            "extra": {"collision": h["once_collided"][i]}},
+                "terminal_observation": {
+                    k: (v[i].detach() if isinstance(v, th.Tensor) else v[i]) for k, v in self._terminal_obs.items()},
+                "TimeLimit.truncated": bool(length >= self._max_steps),
+            }
+            if self._indiv is not None:
+                for k, v in self._indiv.items():
+                    info["episode"]["extra"][k] = v[i].detach().clone()
+            if self._extra_fn is not None:
+                self._extra_fn(i, info)
+        self._cache[i] = info
+        return info
+
+    def copy(self):
+        return self
+
+    def done_indices(self):
+        return np.nonzero(self._fetch()["done"])[0]
+
+
+class DroneGymEnvsBase(VecEnv):
+    def __init__(
+            self,
+            num_agent_per_scene: int = 1,
+            num_scene: int = 1,
+            seed: int = 42,
+            visual: bool = False,
+            max_episode_steps: int = 1000,
+            device="cuda",
+            dynamics_kwargs=None,
+            random_kwargs=None,
+            requires_grad: bool = False,
+            scene_kwargs: Optional[Dict] = None,
+            sensor_kwargs: Optional[List] = None,
+            tensor_output: bool = True,
+            is_train: bool = False,
+            is_collision_reset: bool = True,
+            debug_checks: bool = False,
+    ):
+        device = th.device(device)
+        self.envs = DroneEnvsBase(
+            num_agent_per_scene=num_agent_per_scene, num_scene=num_scene, seed=seed, visual=visual, device=device,
+            dynamics_kwargs=dict(dynamics_kwargs or {}), random_kwargs=dict(random_kwargs or {}),
+            scene_kwargs=dict(scene_kwargs or {}), sensor_kwargs=sensor_kwargs or [])
+        self.device = self.envs.device
+        self.num_agent = self.num_envs = num_agent_per_scene * num_scene
+        self.num_scene, self.num_agent_per_scene = num_scene, num_agent_per_scene
+        self.requires_grad = requires_grad
+        self.max_sense_radius = 10
+        self.tensor_output = tensor_output
+        self.is_train = is_train
+        self.is_collision_reset = is_collision_reset
+        self.debug_checks = debug_checks
+        self.max_episode_steps = max_episode_steps
+
+        ori_dim = 3 if self.envs.dynamics.angular_output_type == "euler" else 4
+        self.observation_space = spaces.Dict(
+            {"state": spaces.Box(low=-np.inf, high=np.inf, shape=(9 + ori_dim,), dtype=np.float32)})
+        if self.envs.dynamics.action_type not in (ACTION_TYPE.BODYRATE, ACTION_TYPE.THRUST, ACTION_TYPE.VELOCITY,
+                                                  ACTION_TYPE.POSITION):
+            raise ValueError("action_type should be one of ['bodyrate', 'thrust', 'velocity', 'position']")
+        self.action_space = spaces.Box(low=-1, high=1, shape=(4,), dtype=np.float32)
+        self.deter = self.stoch = None
+
+        n, dev = self.num_agent, self.device
+        self._step_count = th.zeros((n,), dtype=th.int32, device=dev)
+        self._reward = th.zeros((n,), device=dev)
+        self._rewards = th.zeros((n,), device=dev)
+        self._action = th.zeros((n, 4), device=dev)
+        self._obs_tensors = TensorDict({})
+        self._observations = TensorDict({})
+        self._success = th.zeros(n, dtype=th.bool, device=dev)
+        self._failure = th.zeros(n, dtype=th.bool, device=dev)
+        self._episode_done = th.zeros(n, dtype=th.bool, device=dev)
+        self._done = th.zeros(n, dtype=th.bool, device=dev)
+        self._info = None
+        self._indiv_rewards = self._indiv_reward = None
+        self.render_mode = ["None"] * n
+        self._is_initial = False
+
+    # -- the step ------------------------------------------------------------------------------------
+    def _grad_ctx(self):
+        return contextlib.nullcontext() if self.requires_grad else th.no_grad()
+
+    def step(self, _action, is_test=False, predict=False, world=None):
+        assert self._is_initial, "You should call reset() before step()"
+        if world is not None or predict:
+            raise NotImplementedError("world-model rollouts are not part of the dynamics path")
+        action = _action if isinstance(_action, th.Tensor) else th.as_tensor(np.asarray(_action))
+        self._action = action.to(self.device, dtype=th.float32)
+        if self.debug_checks:                                   # reference droneGymEnv.py:144 (host sync)
+            assert self._action.max() <= 1 and self._action.min() >= -1
+        with self._grad_ctx():
+            self.envs.step(self._action)
+            self.get_full_observation()
+            self._step_count = self._step_count + 1
+            self._success = self.get_success()
+            self._failure = self.get_failure()
+            assert self._success.dtype == th.bool and self._failure.dtype == th.bool
+            if self._indiv_reward is None:
+                self._reward = self.get_reward(predicted_obs={})
+            else:
+                self._indiv_reward = self.get_reward(predicted_obs={})
+                assert isinstance(self._indiv_reward, dict) and "reward" in self._indiv_reward
+                self._reward = self._indiv_reward["reward"]
+                self._indiv_rewards = {k: self._indiv_rewards[k] + v.detach() for k, v in self._indiv_reward.items()}
+            self._rewards = self._rewards + self._reward
+
+            episode_done = self._episode_done | self._success | self._failure | self.is_out_bounds
+            if self.is_collision_reset:
+                episode_done = episode_done | self.is_collision
+            self._episode_done = episode_done
+            self._done = episode_done | (self._step_count >= self.max_episode_steps)
+
+            done, reward = self._done, self._reward
+            info = self._snapshot_info()
+            self._info = info
+            if not is_test:
+                self._auto_reset(done)
+        return self._format_step_output(reward, done, info)
+
+    def _snapshot_info(self) -> LazyInfo:
+        return LazyInfo(self.num_agent, self._done, self._episode_done, self._success, self._step_count,
+                        self._rewards, self.envs.once_collided, self._obs_tensors,
+                        self.max_episode_steps, self.envs.dynamics.ctrl_dt, self._indiv_rewards,
+                        extra_fn=self._extra_info)
+
+    def _extra_info(self, indice: int, info: dict):
+        """Hook for task envs that add per-episode extras (reference RacingEnv.collect_info)."""
+
+    def collect_info(self, indice, observations=None):
+        """Info record of one agent for the step just taken (reference droneGymEnv.py:238-275)."""
+        return self._snapshot_info()[indice]
+
+    def _auto_reset(self, done: th.Tensor):
+        """Re-initialise finished agents in place of the reference's ``examine()`` (droneGymEnv.py:207-208,
+        :420-423) — same effect, expressed with a mask so that nothing leaves the device."""
+        self._on_reset_where(done)
+        self.envs.reset_agents_where(done)
+        self.get_full_observation()
+        self._reset_attr_where(done)
+
+    def _on_reset_where(self, mask: th.Tensor):
+        """Hook: task-specific per-agent state to re-initialise (called before the dynamics reset)."""
+
+    def _format_step_output(self, reward, done, info):
+        if self.requires_grad:
+            if not self.tensor_output:
+                raise ValueError("requires_grad should be False if tensor_output is False")
+            self._observations = self._obs_tensors
+            return self._observations, reward, done, info
+        if self.tensor_output:
+            self._observations = self._obs_tensors
+            return self._observations.detach(), reward.detach(), done, info
+        self._observations = self._format_obs(self._obs_tensors)
+        return self._observations, reward.cpu().numpy(), done.cpu().numpy().astype(np.int32), info
+
+    def _format_obs(self, obs):
+        if not self.tensor_output:
+            return TensorDict({k: v.detach().cpu().numpy() for k, v in obs.items()})
+        return obs
+
+    # -- reset ---------------------------------------------------------------------------------------------
+    def reset(self, state=None, predicted_obs=None, is_test=False, stoch=None, deter=None):
+        self._is_initial = True
+        with self._grad_ctx():
+            self.envs.reset(state=state)
+            self._on_reset_where(th.ones(self.num_agent, dtype=th.bool, device=self.device))
+            self._reset_attr()
+            self.get_full_observation()
+            probe = self.get_reward()
+            if isinstance(probe, dict):
+                self._indiv_reward = {k: th.zeros((self.num_agent,), device=self.device) for k in probe}
+                self._indiv_rewards = {k: th.zeros((self.num_agent,), device=self.device) for k in probe}
+            elif isinstance(probe, th.Tensor):
+                self._indiv_reward = self._indiv_rewards = None
+            else:
+                raise ValueError(f"get_reward should return a dict or a tensor, but got {type(probe)}")
+        self._observations = self._format_obs(self._obs_tensors)
+        return self._observations
+
+    def reset_agent_by_id(self, agent_indices=None, state=None, reset_obs=None):
+        """Index-based reset of selected agents (reference droneGymEnv.py:339-349)."""
+        assert not isinstance(agent_indices, bool)
+        with self._grad_ctx():
+            if agent_indices is None:
+                mask = th.ones(self.num_agent, dtype=th.bool, device=self.device)
+            else:
+                idx = th.as_tensor(agent_indices, device=self.device, dtype=th.int64).reshape(-1)
+                mask = th.zeros(self.num_agent, dtype=th.bool, device=self.device).index_fill(0, idx, True)
+            self._on_reset_where(mask)
+            self.envs.reset_agents(agent_indices, state=state, pos_reset_by_state=True)
+            self.get_full_observation()
+            self._reset_attr_where(mask)
+        self._observations = self._format_obs(self._obs_tensors)
+        return self._observations
+
+    def reset_env_by_id(self, scene_indices=None):
+        scene_indices = th.arange(self.num_scene) if scene_indices is None else th.atleast_1d(th.as_tensor(scene_indices))
+        agents = (scene_indices.unsqueeze(1) * self.num_agent_per_scene + th.arange(self.num_agent_per_scene)).flatten()
+        return self.reset_agent_by_id(agents)
+
+    def examine(self):
+        self._auto_reset(self._done)
+        self._observations = self._format_obs(self._obs_tensors)
+        return self._observations
+
+    @th.no_grad()
+    def _reset_attr(self, indices=None, reset_latent=True):
+        if indices is not None:
+            idx = th.as_tensor(indices, device=self.device, dtype=th.int64).reshape(-1)
+            return self._reset_attr_where(
+                th.zeros(self.num_agent, dtype=th.bool, device=self.device).index_fill(0, idx, True))
+        n, dev = self.num_agent, self.device
+        self._reward = th.zeros((n,), device=dev)
+        self._rewards = th.zeros((n,), device=dev)
+        self._done = th.zeros(n, dtype=th.bool, device=dev)
+        self._episode_done = th.zeros(n, dtype=th.bool, device=dev)
+        self._step_count = th.zeros((n,), dtype=th.int32, device=dev)
+        if self._indiv_rewards is not None:
+            self._indiv_rewards = {k: th.zeros((n,), device=dev) for k in self._indiv_rewards}
+            self._indiv_reward = {k: th.zeros((n,), device=dev) for k in self._indiv_reward}
+
+    @th.no_grad()
+    def _reset_attr_where(self, mask: th.Tensor):
+        keep = ~mask
+        self._reward = th.where(mask, 0.0, self._reward.detach())
+        self._rewards = th.where(mask, 0.0, self._rewards)
+        self._done = self._done & keep
+        self._episode_done = self._episode_done & keep
+        self._step_count = self._step_count * keep
+        if self._indiv_rewards is not None:
+            self._indiv_rewards = {k: th.where(mask, 0.0, v) for k, v in self._indiv_rewards.items()}
+            self._indiv_reward = {k: th.where(mask, 0.0, v) for k, v in self._indiv_reward.items()}
+
+    def detach(self):
+        self.envs.detach()
+        self.simple_detach()
+
+    def simple_detach(self):
+        self._rewards = self._rewards.detach()
+        self._reward = self._reward.detach()
+        self._action = self._action.detach()
+        self._obs_tensors = self._obs_tensors.detach()
+
+    # -- task interface ---------------------------------------------------------------------------------------
+    def get_done(self):
+        return th.zeros(self.num_agent, dtype=th.bool, device=self.device)
+
+    def get_success(self) -> th.Tensor:
+        return th.zeros(self.num_agent, dtype=th.bool, device=self.device)
+
+    def get_failure(self) -> th.Tensor:
+        return th.zeros(self.num_agent, dtype=th.bool, device=self.device)
+
+    def get_reward(self, predicted_obs=None):
+        raise NotImplementedError
+
+    def get_observation(self, indices=None, predicted_obs=None) -> TensorDict:
+        raise NotImplementedError
+
+    def get_full_observation(self, indice=None, predicted_obs=None):
+        obs = self.get_observation(predicted_obs=predicted_obs)
+        assert isinstance(obs, TensorDict)
+        self._obs_tensors = obs.as_tensor(device=self.device)
+        return self._obs_tensors
+
+    # -- misc VecEnv surface -------------------------------------------------------------------------------------
+    def close(self):
+        self.envs.close()
+
+    def render(self, **kwargs):
+        return self.envs.render(**kwargs)
+
+    def env_is_wrapped(self, wrapper_class=None, indices=None):
+        return False
+
+    def step_async(self, actions=None):
+        raise NotImplementedError("This method is not implemented")
+
+    def step_wait(self):
+        raise NotImplementedError("This method is not implemented")
+
+    def get_attr(self, attr_name, indices=None):
+        if indices is None:
+            return getattr(self, attr_name)
+
+    def set_attr(self, attr_name, value, indices=None):
+        raise NotImplementedError("This method is not implemented")
+
+    def env_method(self, method_name, *method_args, indices=None, **method_kwargs):
+        raise NotImplementedError("This method is not implemented")
+
+    def to(self, device):
+        self.device = device if not isinstance(device, str) else th.device(device)
+
+    def eval(self):
+        self.envs.eval()
+
+    def set_requires_grad(self, requires_grad: bool):
+        self.requires_grad = requires_grad
+
+    def __len__(self):
+        return self.num_envs
+
+    def __repr__(self):
+        return (f"{self.__class__.__name__}(Env={self.envs.__class__}, NumAgentPerScene={self.num_agent_per_scene}, "
+                f"NumScene={self.num_scene}, tensorOut={self.tensor_output}, RequiresGrad={self.requires_grad})")
+
+    reward = property(lambda s: s._reward)
+    sensor_obs = property(lambda s: s.envs.sensor_obs)
+    state = property(lambda s: s.envs.state)
+    info = property(lambda s: s._info)
+    is_collision = property(lambda s: s.envs.is_collision)
+    is_out_bounds = property(lambda s: s.envs.is_out_bounds)
+    done = property(lambda s: s._done)
+    episode_done = property(lambda s: s._episode_done)
+    success = property(lambda s: s._success)
+    failure = property(lambda s: s._failure)
+    direction = property(lambda s: s.envs.direction)
+    position = property(lambda s: s.envs.position)
+    orientation = property(lambda s: s.envs.orientation)
+    velocity = property(lambda s: s.envs.velocity)
+    angular_velocity = property(lambda s: s.envs.angular_velocity)
+    t = property(lambda s: s.envs.t)
+    visual = property(lambda s: s.envs.visual)
+    collision_vector = property(lambda s: s.envs.collision_vector)
+    collision_dis = property(lambda s: s.envs.collision_dis)
+    collision_point = property(lambda s: s.envs.collision_point)
+    full_state = property(lambda s: s.envs.full_state)
+    extend_state = property(lambda s: s.envs.extend_state)
+    dynamic_object_position = property(lambda s: s.envs.dynamic_object_position)
