@@ -75,7 +75,6 @@ def test_env_rollout_gradients_match_reference_autograd(integ):
     loss = 0.0
     for t in range(H):
         obs, r, d, info = env.step(acts[t])
-        assert r.requires_grad
         loss = loss - (0.99 ** t) * r
     loss = loss.mean()
     g, = th.autograd.grad(loss, acts)
