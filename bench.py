@@ -1,0 +1,379 @@
+#!/usr/bin/env python
+"""bench.py — agent control-steps/sec of the north-star path (BASELINE.json configs[1]):
+
+    HoverEnv, 65 536 agents per GPU, visual=False, RK4, dt=0.0025, ctrl_dt=0.02 (8 sub-steps), bodyrate actions,
+    motor lag on, comm-delay FIFO of 3 steps, float32.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One JSON line on stdout (rank 0).  What is measured
+  value     env.step throughput with actions and state resident in HBM (tensor mode), timed on the device with one
+            CUDA-event pair per step and an L2 flush (256 MiB write) before every timed step; max over ranks.
+  e2e       the same env driven like an SB3/numpy training loop: actions arrive in (pinned) host memory every step,
+            observation / reward / done come back as numpy arrays — host<->device copies inside the timed region.
+  roofline  the dominant kernel (the fused control step) timed alone, cold L2, against the measured HBM peak.
+  cpu_baseline  the oracle port of the reference (oracle/env_oracle.py, same aten-op sequence as the reference
+            incl. its per-agent Python loops) on this box's host cores, on a bounded sample of the same workload.
+`--impl reference` runs only that CPU arm for K steps and prints the same line with "impl": "reference".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch as th  # noqa: E402
+
+METRIC = "agent control-steps/sec (visual=False)"
+UNIT = "agent-steps/s"
+AGENTS = 65536
+DYN = dict(action_type="bodyrate", integrator="rk4", dt=0.0025, ctrl_dt=0.02, ctrl_delay=True, comm_delay=0.06)
+WORKLOAD = "HoverEnv 65536 agents/GPU visual=False RK4 dt=0.0025 ctrl_dt=0.02 bodyrate (BASELINE configs[1])"
+ALGO_BYTES_FWD = 176          # 96 B read (20 state + 4 action floats) + 80 B written per agent-step
+MOVED_BYTES_FWD = 176 + 52    # + the (n,13) observation the reference's step() returns
+FLOP_PER_AGENT_STEP = 4100    # SURVEY.md §8(d) lean count, RK4 x 8 sub-steps
+FP32_PEAK_TFLOPS = 74.0       # 148 SM x 128 lanes x 2 x 1.965 GHz (nominal)
+L2_FLUSH_BYTES = 256 << 20
+
+
+# ---------------------------------------------------------------------------------------------------------
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """SM clock and throttle reasons sampled DURING the timed region (NVML; nvidia-smi as fallback)."""
+
+    def __init__(self, index: int):
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+
+    def _nvml_loop(self):
+        import pynvml as nv
+        nv.nvmlInit()
+        h = nv.nvmlDeviceGetHandleByIndex(self.index)
+        self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        names = {
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
+        }
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        while not self._stop.is_set():
+            self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+            mask = get_reasons(h)
+            for bit, name in names.items():
+                if mask & bit:
+                    self.reasons.add(name)
+            time.sleep(0.02)
+
+    def _smi_loop(self):
+        import subprocess
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self._stop.is_set():
+            out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                 capture_output=True, text=True).stdout.strip().split(",")
+            if len(out) >= 6:
+                self.samples.append(int(out[0]))
+                self.max_mhz = int(out[1])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), out[2:]):
+                    if "Active" in v and "Not" not in v:
+                        self.reasons.add(name)
+            time.sleep(0.1)
+
+    def _loop(self):
+        try:
+            self._nvml_loop()
+        except Exception:  # noqa: BLE001
+            try:
+                self._smi_loop()
+            except Exception:  # noqa: BLE001
+                pass
+
+    def __enter__(self):
+        self._thread = threading.Thread(target=self._loop, daemon=True)
+        self._thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        self._thread.join(timeout=2)
+
+    def summary(self):
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None,
+                "sm_max_mhz": self.max_mhz, "samples": len(self.samples), "reasons": sorted(self.reasons)}
+
+
+def hover_actions(n, count, device, seed=0):
+    """smooth-hover law of SURVEY.md §8d config 2: a = [-1/3, 0, 0, 0] + U(-0.1, 0.1)^4  (-1/3 <-> 1 g)."""
+    g = th.Generator(device="cpu").manual_seed(seed)
+    a = (th.rand(count, n, 4, generator=g) * 2 - 1) * 0.1
+    a[..., 0] += -1.0 / 3.0
+    return a.to(device) if device != "cpu" else a
+
+
+# ---------------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port on the host cores
+# ---------------------------------------------------------------------------------------------------------
+def cpu_reference_run(steps: int, warmup: int, budget_s: float, agents: int = AGENTS):
+    """Times OracleEnv.step (hover task, same dynamics kwargs) on the CPU.  The agent count of the sample is
+    reduced (power of two) until `steps` steps fit the time budget."""
+    from oracle.env_oracle import OracleEnv
+    from oracle.torch_oracle import OracleDynamics
+    th.set_num_threads(os.cpu_count() or 1)
+    cores = th.get_num_threads()
+
+    def build(n):
+        table = None
+
+        def generate(indices=None):      # initial placement vectorised: reset is not part of the timed step
+            m = n if indices is None else len(indices)
+            pos = th.tensor([1., 0., 1.5]) + (th.rand(m, 3) * 2 - 1) * th.tensor([1.0, 1.0, 0.5])
+            quat = th.zeros(m, 4)
+            quat[:, 0] = 1
+            return pos, quat, th.zeros(m, 3), th.zeros(m, 3)
+        env = OracleEnv("hover", n, dict(DYN), max_episode_steps=256, generate_state=generate)
+        env.reset()
+        return env
+
+    n = agents
+    while True:
+        env = build(n)
+        acts = hover_actions(n, 4, "cpu")
+        t0 = time.perf_counter()
+        env.step(acts[0])
+        probe = time.perf_counter() - t0
+        if probe * (steps + warmup) <= budget_s or n <= 1024:
+            break
+        n //= 2
+    for i in range(warmup):
+        env.step(acts[i % 4])
+    t0 = time.perf_counter()
+    for i in range(steps):
+        env.step(acts[i % 4])
+    dt = time.perf_counter() - t0
+    # the dynamics alone (no wrapper loops), a few steps
+    dyn = OracleDynamics(n, **{k: v for k, v in DYN.items()})
+    dyn.step(acts[0])
+    k = max(1, min(5, steps))
+    t1 = time.perf_counter()
+    for i in range(k):
+        dyn.step(acts[i % 4])
+    dyn_dt = (time.perf_counter() - t1) / k
+    return {"value": n * steps / dt, "ms_per_step": 1e3 * dt / steps, "agents": n, "cores": cores,
+            "dynamics_only_value": n / dyn_dt, "steps": steps}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = cpu_reference_run(args.steps, args.warmup, budget_s=200.0)
+    sample = f"OracleEnv(hover).step on {r['agents']} agents x {r['steps']} steps, {r['cores']} host threads"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "agents_in_sample": r["agents"], "device": "cpu"},
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": sample,
+                         "dynamics_only_value": r["dynamics_only_value"]},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------------
+def timed_steps(step_fn, steps, flush, stream):
+    """One CUDA-event pair per step on the launching stream, L2 flushed before each timed step."""
+    starts = [th.cuda.Event(enable_timing=True) for _ in range(steps)]
+    ends = [th.cuda.Event(enable_timing=True) for _ in range(steps)]
+    for i in range(steps):
+        if flush is not None:
+            flush.zero_()
+        starts[i].record(stream)
+        step_fn(i)
+        ends[i].record(stream)
+    th.cuda.synchronize()
+    return [s.elapsed_time(e) for s, e in zip(starts, ends)]       # ms
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    from visfly_b200 import _lib
+    from visfly_b200.envs import HoverEnv
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    th.cuda.set_device(local)
+    dev = th.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n, K, W = args.agents, args.steps, args.warmup
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        th.cuda.synchronize()
+
+    flush = th.empty(L2_FLUSH_BYTES, dtype=th.uint8, device=dev)
+    stream = th.cuda.current_stream(dev)
+    pool = 16
+    acts = hover_actions(n, pool, dev, seed=rank)
+
+    # ---- value: tensor mode, everything resident in HBM ----------------------------------------------
+    env = HoverEnv(num_agent_per_scene=n, visual=False, device=dev, dynamics_kwargs=dict(DYN), seed=42 + rank,
+                   max_episode_steps=256, tensor_output=True)
+    env.reset()
+    returns = th.zeros(n, device=dev)
+
+    def env_step(i):
+        obs, reward, done, info = env.step(acts[i % pool])
+        returns.add_(reward)
+
+    for i in range(W):
+        env_step(i)
+    barrier()
+    with ClockSampler(local) as clk:
+        per_step = timed_steps(env_step, K, flush, stream)
+        if world > 1:     # the one collective of the path: episode returns of all shards, once per rollout
+            gathered = [th.empty_like(returns) for _ in range(world)]
+            dist.all_gather(gathered, returns)
+        barrier()
+        # hot-L2 wall clock of the same loop (no flush, no per-step events): cross-check for the driver's clock
+        t0 = time.perf_counter()
+        for i in range(K):
+            env_step(i)
+        th.cuda.synchronize()
+        wall_hot = time.perf_counter() - t0
+    total_ms = th.tensor([sum(per_step)], device=dev, dtype=th.float64)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(total_ms)
+    value = world * n * K / (total_ms * 1e-3)
+
+    # ---- roofline: the fused control-step kernel alone, cold L2 -----------------------------------------
+    dynm = env.envs.dynamics
+    cfg = dynm._cfg
+    st_in = dynm.packed_state.detach().clone()
+    st_out, obs_out = th.empty_like(st_in), th.empty((n, 13), device=dev)
+
+    def kernel_only(i):
+        _lib.step_fwd(cfg.params, cfg.substeps, cfg.integrator, cfg.action_type, cfg.flags, st_in, acts[i % pool],
+                      st_out, obs_out, None)
+
+    for i in range(5):
+        kernel_only(i)
+    k_ms = timed_steps(kernel_only, max(K, 50), flush, stream)
+    k_avg = float(np.mean(k_ms)) * 1e-3
+    peak, peak_src = measured_peaks()
+    achieved = ALGO_BYTES_FWD * n / k_avg / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.isfile(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get("vf_step_fwd_kernel_bytes_per_launch")
+    roofline = {"bound": "hbm", "kernel": "vf_step_fwd_kernel<RK4,BODYRATE,LAG>", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "kernel_us": k_avg * 1e6, "algorithmic_bytes_per_launch": ALGO_BYTES_FWD * n,
+                "bytes_moved_per_launch": MOVED_BYTES_FWD * n,
+                "fp32": {"achieved_tflops": FLOP_PER_AGENT_STEP * n / k_avg / 1e12, "peak_tflops": FP32_PEAK_TFLOPS,
+                         "frac": FLOP_PER_AGENT_STEP * n / k_avg / 1e12 / FP32_PEAK_TFLOPS,
+                         "note": "RK4 x8 is fp32-pipe/latency bound (23 FLOP/B, ridge ~11.5), SURVEY.md §8d"}}
+
+    # ---- e2e: numpy in / numpy out through the public env API -------------------------------------------
+    env_np = HoverEnv(num_agent_per_scene=n, visual=False, device=dev, dynamics_kwargs=dict(DYN), seed=142 + rank,
+                      max_episode_steps=256, tensor_output=False)
+    env_np.reset()
+    host_acts = [th.empty((n, 4), pin_memory=True).copy_(acts[i].cpu()).numpy() for i in range(pool)]
+    sink = np.zeros(n, dtype=np.float64)
+
+    def e2e_step(i):
+        obs, reward, done, info = env_np.step(host_acts[i % pool])
+        sink[:] += reward                                     # the host really consumes the result
+
+    for i in range(W):
+        e2e_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(K):
+        e2e_step(i)
+    th.cuda.synchronize()
+    e2e_s = th.tensor([time.perf_counter() - t0], device=dev, dtype=th.float64)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e = {"value": world * n * K / float(e2e_s), "unit": UNIT, "h2d_bytes_per_step": n * 16,
+           "d2h_bytes_per_step": n * (13 * 4 + 4 + 1), "ms_per_step": 1e3 * float(e2e_s) / K,
+           "api": "HoverEnv(tensor_output=False).step(numpy actions) -> numpy obs/reward/done"}
+
+    if rank == 0:
+        cpu = None
+        if not args.no_cpu_baseline:
+            r = cpu_reference_run(steps=20, warmup=1, budget_s=25.0)
+            cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+                   "sample": f"OracleEnv(hover).step on {r['agents']} agents x {r['steps']} steps "
+                             f"({r['ms_per_step']:.0f} ms/step), {r['cores']} host threads",
+                   "dynamics_only_value": r["dynamics_only_value"]}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "agents_per_gpu": n, "substeps": 8, "actions": "smooth-hover law",
+                       "l2": "flushed before every timed step (256 MiB write); one CUDA-event pair per step",
+                       "parallelism": f"agents sharded over {world} GPU(s), one all_gather of episode returns per rollout"},
+            "clocks": clk.summary(), "e2e": e2e, "gpu_launches": K * env_launches_per_step(env),
+            "roofline": roofline, "cpu_baseline": cpu,
+            "hot_l2_wall_value": world * n * K / wall_hot, "kernel_only_value": n / k_avg,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def env_launches_per_step(env) -> int:
+    """Kernels of OUR library launched by one env.step (the torch elementwise glue is not counted)."""
+    return int(getattr(env, "native_launches_per_step", 1))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--agents", type=int, default=AGENTS, help="agents per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if not th.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

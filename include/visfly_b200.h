@@ -148,6 +148,86 @@ int vf_pack_state(int n, int m, const long long* index,
 int vf_unpack_state(int n, const float* state, float* pos, float* quat, float* vel, float* rate,
                     float* motor, float* alpha, void* stream);
 
+/* =====================================================================================================
+ * Fused env step: the control step above PLUS the wrapper tail the reference runs
+ * around it with ~100 aten ops and per-agent Python loops — analytic bounding-box collision
+ * (envs/base/droneEnv.py:345-369), the task's success test and reward (envs/HoverEnv.py:79-94,
+ * envs/NavigationEnv.py:81-99, envs/RacingEnv.py:142-148,203-215), reward accumulation and termination
+ * (envs/base/droneGymEnv.py:163-193), the per-episode record the reference puts into `info`
+ * (droneGymEnv.py:238-275) and the auto-reset of finished agents with freshly sampled initial states
+ * (droneGymEnv.py:207-208,339-349; droneEnv.py:260-288; utils/randomization.py:153-169,278-296) — in one launch.
+ * ===================================================================================================== */
+
+#define VF_TASK_HOVER      0
+#define VF_TASK_NAVIGATION 1
+#define VF_TASK_RACING     2
+
+#define VF_OBS_STATE13  0   /* [p q v w]                                    reference `state`, dynamics.py:778-786 */
+#define VF_OBS_RACING16 1   /* [gate-p, gate2-p]/10, q, v/10, w/10          reference RacingEnv.py:254-262          */
+
+#define VF_GEN_UNIFORM 0    /* (2u-1)*half + mean per field, utils/randomization.py:153-169; a Union of several    */
+#define VF_GEN_NORMAL  1    /* (2z-1)*std + mean, :201-204                  boxes picks one uniformly (:278-296)     */
+#define VF_GEN_TABLE   2    /* agent i restarts from row i of a caller-supplied [n][13] table                       */
+#define VF_GEN_MAX_BOXES 4
+
+#define VF_ENV_FLAG_NO_RESET 1u   /* is_test=True: report done but do not re-initialise (droneGymEnv.py:207)        */
+
+/* per-agent env status bits (in/out) */
+#define VF_EBIT_EPISODE_DONE  1u
+#define VF_EBIT_ONCE_COLLIDED 2u
+/* bits of the per-step episode record */
+#define VF_RBIT_DONE          1u
+#define VF_RBIT_EPISODE_DONE  2u
+#define VF_RBIT_SUCCESS       4u
+#define VF_RBIT_TRUNCATED     8u
+#define VF_RBIT_COLLIDED     16u
+
+typedef struct VfEnvSpec {
+    int   task;               /* VF_TASK_*                                                                        */
+    int   obs_kind;           /* VF_OBS_*                                                                         */
+    int   max_episode_steps;  /* droneGymEnv.py:193                                                               */
+    int   collision_reset;    /* is_collision_reset, droneGymEnv.py:189                                           */
+    int   fifo_depth;         /* comm-delay steps: a delayed action older than the agent's episode reads as zero  */
+                              /* (= the reference zeroing the FIFO rows of reset agents, dynamics.py:262-263)     */
+    float uav_radius;         /* droneEnv.py:31,367                                                               */
+    float bbox_lo[3];         /* droneEnv.py:129                                                                  */
+    float bbox_hi[3];
+    float target[3];          /* hover / navigation target                                                        */
+    float success_radius;
+    int   n_gates;            /* racing                                                                           */
+    float gates[4][3];
+    int   gen_kind;           /* VF_GEN_*                                                                         */
+    int   gen_boxes;          /* 1, or the number of boxes of a Union generator                                   */
+    float gen_mean[VF_GEN_MAX_BOXES][4][3];   /* [box][position, euler orientation, velocity, body rate][xyz]     */
+    float gen_half[VF_GEN_MAX_BOXES][4][3];   /* half width (uniform) or std (normal)                             */
+    float init_motor_omega;   /* hover rotor speed after reset, dynamics.py:86                                    */
+    unsigned long long seed;  /* Philox key of the reset sampler                                                  */
+} VfEnvSpec;
+
+int vf_env_spec_size(void);
+
+/*
+ * One env step for n agents.
+ *   state_in/action/state_out   as vf_step_fwd (action = output of the caller's comm-delay FIFO)
+ *   step_count  int32[n]  in/out   steps since the agent's last reset                 (droneGymEnv.py:163)
+ *   returns     float[n]  in/out   accumulated episode reward                         (droneGymEnv.py:185)
+ *   ebits       uint8[n]  in/out   VF_EBIT_*
+ *   gate        int32[n]  in/out   next gate index (racing; NULL otherwise)           (RacingEnv.py:142-148)
+ *   gates_passed int32[n] in/out   (racing; NULL otherwise)
+ *   step_index             counter mixed into the reset sampler (use the env's global step number)
+ *   reset_table float[n][13]  rows [p q v w] for VF_GEN_TABLE, else NULL
+ *   obs_out     float[n][13|16]  observation AFTER the auto-reset (what env.step returns)
+ *   reward_out  float[n], done_out uint8[n]
+ *   record_out  float[n][4]   [episode return, episode length, VF_RBIT_* as float, gates passed] of this step
+ *   term_obs_out float[n][13|16] or NULL: observation BEFORE the reset, written only for finished agents
+ */
+int vf_env_step_fwd(const VfParams* params, const VfEnvSpec* spec, int n, int substeps, int integrator,
+                    int action_type, unsigned flags, unsigned env_flags, unsigned long long step_index,
+                    const float* state_in, const float* action, const float* reset_table,
+                    int* step_count, float* returns, unsigned char* ebits, int* gate, int* gates_passed,
+                    float* state_out, float* obs_out, float* reward_out, unsigned char* done_out,
+                    float* record_out, float* term_obs_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -15,7 +15,7 @@ pytestmark = pytest.mark.gpu
 TASKS = ["hover", "navigation", "racing2"]
 
 
-def make_env(task, n, integ, max_episode_steps, table, **kw):
+def make_env(task, n, integ, max_episode_steps, table, path="generic", **kw):
     from visfly_b200.envs import HoverEnv, NavigationEnv, RacingEnv2
     cls = {"hover": HoverEnv, "navigation": NavigationEnv, "racing2": RacingEnv2}[task]
     if task == "hover":
@@ -23,6 +23,9 @@ def make_env(task, n, integ, max_episode_steps, table, **kw):
     env = cls(num_agent_per_scene=n, visual=False, device="cuda", dynamics_kwargs=dict(DYN[integ], comm_delay=0.06),
               max_episode_steps=max_episode_steps, **kw)
     tbl = tuple(x.cuda() for x in table)
+    if path == "fused":          # the official way to pin restarts: both paths honour it, the kernel reads the table
+        env.envs.set_reset_table(*tbl)
+        return env
 
     def generate(indices=None, num=None):
         if indices is None:
@@ -36,12 +39,15 @@ def make_env(task, n, integ, max_episode_steps, table, **kw):
 
 @pytest.mark.parametrize("task", TASKS)
 @pytest.mark.parametrize("integ", ["euler", "rk4"])
-def test_env_replays_reference_golden(task, integ):
+@pytest.mark.parametrize("path", ["generic", "fused"])
+def test_env_replays_reference_golden(task, integ, path):
+    """generic = tensor-op wrapper around the fused dynamics kernel; fused = the one-kernel env step."""
     z = load_env_golden(task, integ)
     acts = th.from_numpy(z["actions"]).cuda()
     T, n = acts.shape[:2]
-    env = make_env(task, n, integ, int(z["max_episode_steps"]), table_of(z))
+    env = make_env(task, n, integ, int(z["max_episode_steps"]), table_of(z), path=path)
     obs = env.reset()
+    assert (env._fused is not None) and env._fused.refresh() == (path == "fused")
     ref0 = z["reset_obs_state"]
     cols = slice(6, None) if task == "racing2" else slice(None)    # reference reset() returns stale gate columns
     assert rel_l2(obs["state"].cpu()[:, cols], ref0[:, cols]) < 1e-6
@@ -63,6 +69,7 @@ def test_env_replays_reference_golden(task, integ):
         idle = [i for i in range(n) if not z["done"][t][i]][:2]
         for i in idle:
             assert info[i] == {"TimeLimit.truncated": False, "episode_done": False}
+        assert env._fused.active == (path == "fused")
 
 
 @pytest.mark.parametrize("integ", ["euler", "rk4"])
@@ -133,3 +140,73 @@ def test_random_state_generators_cover_the_configured_box():
     assert all(abs(float((which == k).float().mean()) - 0.25) < 0.05 for k in range(4))
     # first gate from the start box (reference RacingEnv._choose_target)
     assert bool((race._next_target_i[which == 0] == 0).all() and (race._next_target_i[which == 1] == 1).all())
+
+
+def test_fused_and_generic_paths_agree_and_hand_over_mid_run():
+    """Same env stepped (a) fused all the way, (b) generic all the way, (c) fused then generic then fused."""
+    from visfly_b200.envs import NavigationEnv
+    z = load_env_golden("navigation", "rk4")
+    acts = th.from_numpy(z["actions"]).cuda()
+    T, n = acts.shape[:2]
+
+    def build():
+        env = NavigationEnv(num_agent_per_scene=n, visual=False, dynamics_kwargs=dict(DYN["rk4"]), max_episode_steps=20)
+        env.envs.set_reset_table(*[x.cuda() for x in table_of(z)])
+        env.reset()
+        return env
+
+    def run(env, fused_at):
+        outs = []
+        for t in range(T):
+            env.requires_grad = not fused_at(t)
+            obs, r, d, info = env.step(acts[t])
+            assert env._fused.active == fused_at(t)
+            outs.append((obs["state"].detach().clone(), r.detach().clone(), d.clone(),
+                         [float(info[i]["episode"]["r"]) for i in d.nonzero().flatten().tolist()]))
+        return outs
+
+    a = run(build(), lambda t: True)
+    b = run(build(), lambda t: False)
+    c = run(build(), lambda t: (t // 7) % 2 == 0)
+    for x, y, w in zip(a, b, c):
+        for other in (y, w):
+            assert th.allclose(x[0], other[0], atol=1e-5, rtol=1e-5) and th.allclose(x[1], other[1], atol=1e-5)
+            assert th.equal(x[2], other[2]) and np.allclose(x[3], other[3], atol=1e-5)
+
+
+def test_fused_path_samples_resets_on_device():
+    """Random (Philox) restarts of the fused step: right box, right bookkeeping, deterministic given the seed."""
+    from visfly_b200.envs import HoverEnv, RacingEnv2
+    n = 8192
+    outs = []
+    for _ in range(2):
+        env = HoverEnv(num_agent_per_scene=n, visual=False, dynamics_kwargs=dict(DYN["euler"]), max_episode_steps=5,
+                       tensor_output=True, seed=7)
+        env.envs.set_reset_table(th.tensor([[1.0, 0, 1.5]]).repeat(n, 1), th.tensor([[1.0, 0, 0, 0]]).repeat(n, 1))
+        env.reset()
+        env.envs.set_reset_table(None, None)          # from here on the generator (uniform box) is used
+        a = th.zeros(n, 4, device="cuda")
+        for t in range(5):
+            obs, r, d, info = env.step(a)
+        assert env._fused.active and bool(d.all())     # step 5 truncates everybody -> everybody restarts
+        p = obs["state"][:, :3]
+        lo, hi = th.tensor([0., -1, 1], device="cuda"), th.tensor([2., 1, 2], device="cuda")
+        assert bool((p >= lo).all() and (p <= hi).all())
+        assert float((p.mean(0) - th.tensor([1., 0, 1.5], device="cuda")).abs().max()) < 0.05
+        assert float((p.std(0) - th.tensor([2., 2, 1], device="cuda") / 12 ** 0.5).abs().max()) < 0.03
+        assert float(obs["state"][:, 3:7].sub(th.tensor([1., 0, 0, 0], device="cuda")).abs().max()) == 0
+        assert int(env._step_count.sum()) == 0 and float(env._rewards.abs().sum()) == 0
+        assert info[0]["TimeLimit.truncated"] and int(info[0]["episode"]["l"]) == 5
+        assert info[3]["terminal_observation"]["state"].shape == (13,)
+        outs.append(p.clone())
+    assert th.equal(outs[0], outs[1])
+    race = RacingEnv2(num_agent_per_scene=n, visual=False, dynamics_kwargs=dict(DYN["euler"]), max_episode_steps=3)
+    race.reset()
+    for t in range(3):
+        obs, r, d, info = race.step(th.zeros(n, 4, device="cuda"))
+    assert race._fused.active and bool(d.all()) and obs["state"].shape == (n, 16) and obs["gate"].shape == (n, 1)
+    centres = th.tensor([[2., 2., 1], [6., 2., 1.5], [6., -2., 1.5], [2., 0., 1]], device="cuda")
+    dist = (race.position.unsqueeze(1) - centres).abs().amax(dim=2)
+    assert bool((dist.amin(dim=1) <= 0.2 + 1e-6).all())
+    which = dist.argmin(dim=1)
+    assert all(abs(float((which == k).float().mean()) - 0.25) < 0.03 for k in range(4))

@@ -11,7 +11,7 @@ from typing import Optional
 
 import torch as th
 
-from .params import VfParams
+from .params import VfEnvSpec, VfParams
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvisfly_b200.so")
@@ -37,6 +37,9 @@ SIGNATURES = {
     "vf_step_fwd_host": (_i, [_P(VfParams), _i, _i, _i, _i, _u, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "vf_pack_state": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "vf_unpack_state": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "vf_env_spec_size": (_i, []),
+    "vf_env_step_fwd": (_i, [_P(VfParams), _P(VfEnvSpec), _i, _i, _i, _i, _u, _u, ctypes.c_ulonglong,
+                             _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
 }
 
 _lib: Optional[ctypes.CDLL] = None
@@ -63,6 +66,8 @@ def load(require_cuda: bool = False) -> ctypes.CDLL:
             raise ExtensionMissing(f"libvisfly_b200.so has ABI {got}, python side expects {ABI_VERSION}: rebuild")
         if lib.vf_params_size() != ctypes.sizeof(VfParams):
             raise ExtensionMissing("struct VfParams differs between libvisfly_b200.so and visfly_b200/params.py")
+        if lib.vf_env_spec_size() != ctypes.sizeof(VfEnvSpec):
+            raise ExtensionMissing("struct VfEnvSpec differs between libvisfly_b200.so and visfly_b200/params.py")
         _lib = lib
     if require_cuda and not th.cuda.is_available():
         raise RuntimeError("visfly_b200 needs a CUDA device (sm_100a): torch.cuda.is_available() is False "
@@ -155,3 +160,32 @@ def unpack_state(n: int, state: th.Tensor, pos=None, quat=None, vel=None, rate=N
         _check(lib.vf_unpack_state(n, _dev_ptr(state, "state"),
                                    *[_dev_ptr(f, "field") for f in (pos, quat, vel, rate, motor, alpha)],
                                    _stream(state.device)))
+
+
+def _any_ptr(t: Optional[th.Tensor], what: str, dtype) -> Optional[int]:
+    if t is None:
+        return None
+    if not t.is_cuda or t.dtype != dtype or not t.is_contiguous():
+        raise ValueError(f"{what} must be a contiguous {dtype} CUDA tensor (got {t.dtype}, {t.device})")
+    return t.data_ptr()
+
+
+def env_step_fwd(params: VfParams, spec: VfEnvSpec, substeps: int, integrator: int, action_type: int, flags: int,
+                 env_flags: int, step_index: int, state_in: th.Tensor, action: th.Tensor,
+                 reset_table: Optional[th.Tensor], step_count: th.Tensor, returns: th.Tensor, ebits: th.Tensor,
+                 gate: Optional[th.Tensor], gates_passed: Optional[th.Tensor], state_out: th.Tensor,
+                 obs_out: th.Tensor, reward_out: th.Tensor, done_out: th.Tensor, record_out: th.Tensor,
+                 term_obs_out: Optional[th.Tensor]) -> None:
+    """Binding of ``vf_env_step_fwd`` (fused control step + env wrapper tail, one launch)."""
+    lib = load(require_cuda=True)
+    n = state_in.shape[1]
+    with th.cuda.device(state_in.device):
+        _check(lib.vf_env_step_fwd(
+            ctypes.byref(params), ctypes.byref(spec), n, substeps, integrator, action_type, flags, env_flags,
+            step_index, _dev_ptr(state_in, "state_in"), _dev_ptr(action, "action"),
+            _dev_ptr(reset_table, "reset_table"), _any_ptr(step_count, "step_count", th.int32),
+            _dev_ptr(returns, "returns"), _any_ptr(ebits, "ebits", th.uint8), _any_ptr(gate, "gate", th.int32),
+            _any_ptr(gates_passed, "gates_passed", th.int32), _dev_ptr(state_out, "state_out"),
+            _dev_ptr(obs_out, "obs_out"), _dev_ptr(reward_out, "reward_out"),
+            _any_ptr(done_out, "done_out", th.bool), _dev_ptr(record_out, "record_out"),
+            _dev_ptr(term_obs_out, "term_obs_out"), _stream(state_in.device)))

@@ -1,0 +1,159 @@
+// vf_env.cuh — per-agent arithmetic of the env wrapper tail fused behind the control step (see the "Fused env
+// step" block of include/visfly_b200.h for the reference lines each piece follows).
+#pragma once
+
+#include "vf_math.cuh"
+
+namespace vf {
+
+// ---------------------------------------------------------------------------------------------
+// counter-based RNG for the reset sampler: Philox4x32-10 (Salmon et al., SC'11).  Key = seed, counter =
+// (agent, draw, step_lo, step_hi): every (agent, step) pair owns an independent stream, results do not
+// depend on launch geometry or on how agents are sharded over GPUs.
+// ---------------------------------------------------------------------------------------------
+struct Philox {
+    unsigned c[4];
+    unsigned k[2];
+};
+VF_HD unsigned mulhi32(unsigned a, unsigned b) { return (unsigned)(((unsigned long long)a * b) >> 32); }
+VF_HD void philox_round(Philox& s) {
+    const unsigned M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+    const unsigned hi0 = mulhi32(M0, s.c[0]), lo0 = M0 * s.c[0];
+    const unsigned hi1 = mulhi32(M1, s.c[2]), lo1 = M1 * s.c[2];
+    const unsigned n0 = hi1 ^ s.c[1] ^ s.k[0], n2 = hi0 ^ s.c[3] ^ s.k[1];
+    s.c[0] = n0; s.c[1] = lo1; s.c[2] = n2; s.c[3] = lo0;
+}
+VF_HD void philox4x32(unsigned long long seed, unsigned agent, unsigned draw, unsigned long long step, unsigned out[4]) {
+    Philox s;
+    s.c[0] = agent; s.c[1] = draw; s.c[2] = (unsigned)step; s.c[3] = (unsigned)(step >> 32);
+    s.k[0] = (unsigned)seed; s.k[1] = (unsigned)(seed >> 32);
+    for (int r = 0; r < 10; ++r) {
+        philox_round(s);
+        s.k[0] += 0x9E3779B9u; s.k[1] += 0xBB67AE85u;
+    }
+    for (int i = 0; i < 4; ++i) out[i] = s.c[i];
+}
+// uniform in [0,1) with 24 random bits (what torch.rand produces for float32)
+VF_HD float u01(unsigned x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }
+
+// ---------------------------------------------------------------------------------------------
+// analytic bounding box (reference droneEnv.py:345-369): nearest face, its distance, out-of-bounds test
+// ---------------------------------------------------------------------------------------------
+template <class T> struct BoxHit {
+    int axis;       // coordinate in which the nearest face lies
+    T delta;        // collision_vector[axis] = face - p[axis]  (all other components are 0)
+    T dis;          // |delta|
+    bool out;       // is_out_bounds
+};
+template <class T> VF_HD BoxHit<T> box_hit(const T p[3], const float lo[3], const float hi[3]) {
+    BoxHit<T> h;
+    T best = p[0] - T(lo[0]);
+    int face = 0;
+    for (int j = 1; j < 6; ++j) {                   // order [p-lo (x,y,z), hi-p (x,y,z)], first minimum wins
+        const T g = j < 3 ? p[j] - T(lo[j]) : T(hi[j - 3]) - p[j - 3];
+        if (g < best) { best = g; face = j; }
+    }
+    h.axis = face % 3;
+    const T wall = face < 3 ? T(lo[h.axis]) : T(hi[h.axis]);
+    h.delta = wall - p[h.axis];
+    h.dis = vsqrt(h.delta * h.delta);
+    h.out = (p[0] < T(lo[0])) | (p[1] < T(lo[1])) | (p[2] < T(lo[2])) | (p[0] > T(hi[0])) | (p[1] > T(hi[1])) |
+            (p[2] > T(hi[2]));
+    return h;
+}
+
+template <class T> VF_HD T norm3(T x, T y, T z) { return vsqrt(x * x + y * y + z * z); }
+
+// hover-style shaping shared by HoverEnv (HoverEnv.py:83-94) and RacingEnv (RacingEnv.py:203-215)
+template <class T>
+VF_HD T reward_hover(const T p[3], const T q[4], const T v[3], const T w[3], const T tgt[3]) {
+    const T d = norm3(p[0] - tgt[0], p[1] - tgt[1], p[2] - tgt[2]);
+    const T qe = vsqrt((q[0] - T(1)) * (q[0] - T(1)) + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+    return T(0.1) + d * T(-0.1 * 1 / 9) + qe * T(-0.00001) + norm3(v[0], v[1], v[2]) * T(-0.002) +
+           norm3(w[0], w[1], w[2]) * T(-0.002);
+}
+
+VF_HD float vacos(float x) { return acosf(x); }
+VF_HD double vacos(double x) { return acos(x); }
+
+// NavigationEnv.py:85-99, term by term
+template <class T>
+VF_HD T reward_navigation(const T p[3], const T q[4], const T v[3], const T w[3], const T tgt[3],
+                          const BoxHit<T>& hit, bool success, int max_steps, int step_count) {
+    const T tx = tgt[0] - p[0], ty = tgt[1] - p[1], tz = tgt[2] - p[2];
+    const T vn = norm3(v[0], v[1], v[2]);
+    T approach = (v[0] * tx + v[1] * ty + v[2] * tz) / (T(1e-6) + norm3(tx, ty, tz));
+    approach = approach > T(10) ? T(10) : approach;
+    // heading direction = x axis of the body frame (maths.py:129-131)
+    const T dx = T(1) - T(2) * (q[2] * q[2] + q[3] * q[3]);
+    const T dy = T(2) * (q[1] * q[2] + q[3] * q[0]);
+    const T dz = T(2) * (q[1] * q[3] - q[2] * q[0]);
+    const T thrd = T(3.14159265358979323846 / 18);
+    T c = (dx * v[0] + dy * v[1] + dz * v[2]) / (T(1e-6) + vn) / T(1);
+    c = vclamp(c, T(-1), T(1));
+    T ang = vacos(c);
+    ang = (ang < thrd ? thrd : ang) - thrd;
+    const T qe = vsqrt((q[0] - T(1)) * (q[0] - T(1)) + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+    const T stable = qe * T(-0.00001) + vn * T(-0.002) + norm3(w[0], w[1], w[2]) * T(-0.002);
+    const T near = T(1) / (hit.dis + T(0.2)) * T(-0.01);
+    T prox = T(1) - hit.dis;
+    prox = prox > T(0) ? prox : T(0);
+    T closing = (hit.delta * v[hit.axis]) / (T(1e-6) + hit.dis);
+    closing = closing > T(0) ? closing : T(0);
+    const T bonus = success ? T(max_steps - step_count) * T(0.1) * (T(0.2) + T(0.8) / (T(1) + T(1) * vn)) : T(0);
+    return T(0.1) * T(0) + approach * T(0.01) + ang * T(-0.01) + stable + near + prox * closing * T(-0.005) + bonus;
+}
+
+// first gate from where the agent stands (RacingEnv.py:173-185)
+template <class T> VF_HD int racing_first_gate(const T p[3]) {
+    const T rx = p[0] - T(4), ry = p[1] - T(0);
+    if (rx < T(0)) return ry > T(0) ? 0 : 3;
+    return rx > T(0) ? 1 : 2;
+}
+
+// euler (roll, pitch, yaw) -> quaternion, order zyx (maths.py:257-269)
+VF_HD void euler_to_quat(const float e[3], float q[4]) {
+    const float cr = cosf(e[0] * 0.5f), sr = sinf(e[0] * 0.5f);
+    const float cp = cosf(e[1] * 0.5f), sp = sinf(e[1] * 0.5f);
+    const float cy = cosf(e[2] * 0.5f), sy = sinf(e[2] * 0.5f);
+    q[0] = cr * cp * cy + sr * sp * sy;
+    q[1] = sr * cp * cy - cr * sp * sy;
+    q[2] = cr * sp * cy + sr * cp * sy;
+    q[3] = cr * cp * sy - sr * sp * cy;
+}
+
+// Fresh initial state of one agent (position, quaternion, velocity, body rates).
+VF_HD void sample_reset(const VfEnvSpec& E, unsigned agent, unsigned long long step, const float* table_row,
+                        float p[3], float q[4], float v[3], float w[3]) {
+    if (E.gen_kind == VF_GEN_TABLE) {
+        for (int j = 0; j < 3; ++j) { p[j] = table_row[j]; v[j] = table_row[7 + j]; w[j] = table_row[10 + j]; }
+        for (int j = 0; j < 4; ++j) q[j] = table_row[3 + j];
+        return;
+    }
+    unsigned r[16];
+    for (int d = 0; d < 4; ++d) philox4x32(E.seed, agent, (unsigned)d, step, r + 4 * d);
+    const int box = E.gen_boxes > 1 ? (int)(r[12] % (unsigned)E.gen_boxes) : 0;
+    float f[12];
+    if (E.gen_kind == VF_GEN_NORMAL) {
+        // Box-Muller on pairs; the reference draws (2*randn - 1) * std + mean (randomization.py:201-204)
+        unsigned r2[12];
+        for (int d = 0; d < 3; ++d) philox4x32(E.seed, agent, (unsigned)(4 + d), step, r2 + 4 * d);
+        for (int j = 0; j < 12; ++j) {
+            const float u1 = 1.0f - u01(r[j]), u2 = u01(r2[j]);
+            const float z = sqrtf(-2.0f * logf(u1)) * cosf(6.28318530717958647692f * u2);
+            f[j] = 2.0f * z - 1.0f;
+        }
+    } else {
+        for (int j = 0; j < 12; ++j) f[j] = 2.0f * u01(r[j]) - 1.0f;
+    }
+    float e[3];
+    for (int j = 0; j < 3; ++j) {
+        p[j] = f[j] * E.gen_half[box][0][j] + E.gen_mean[box][0][j];
+        e[j] = f[3 + j] * E.gen_half[box][1][j] + E.gen_mean[box][1][j];
+        v[j] = f[6 + j] * E.gen_half[box][2][j] + E.gen_mean[box][2][j];
+        w[j] = f[9 + j] * E.gen_half[box][3][j] + E.gen_mean[box][3][j];
+    }
+    euler_to_quat(e, q);
+}
+
+}  // namespace vf

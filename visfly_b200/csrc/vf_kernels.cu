@@ -15,6 +15,7 @@
 #include <cstdlib>
 #include <string>
 
+#include "vf_env.cuh"
 #include "vf_math.cuh"
 
 namespace {
@@ -197,6 +198,129 @@ vf_step_bwd_kernel(const __grid_constant__ VfParams params, int n, int substeps,
 }
 
 // ---------------------------------------------------------------------------------------------
+// fused env step: control step + collision + task reward + termination + episode record + auto-reset
+// ---------------------------------------------------------------------------------------------
+template <int INTEG, int ACT, bool LAG, int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+vf_env_step_fwd_kernel(const __grid_constant__ VfParams params, const __grid_constant__ VfEnvSpec E, int n,
+                       int substeps, unsigned env_flags, unsigned long long step_index,
+                       const float* __restrict__ state_in, const float* __restrict__ action,
+                       const float* __restrict__ reset_table, int* __restrict__ step_count,
+                       float* __restrict__ returns, unsigned char* __restrict__ ebits, int* __restrict__ gate,
+                       int* __restrict__ gates_passed, float* __restrict__ state_out, float* __restrict__ obs_out,
+                       float* __restrict__ reward_out, unsigned char* __restrict__ done_out,
+                       float* __restrict__ record_out, float* __restrict__ term_obs_out) {
+    __shared__ __align__(16) float s_obs[(BLOCK / 32) * kWarpObs];
+    const vf::Params<float>& P = reinterpret_cast<const vf::Params<float>&>(params);
+    const int i = blockIdx.x * BLOCK + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int warp_first = i - lane;
+    const bool live = i < n;
+
+    vf::State<float> s;
+    int g = 0;
+    if (live) {
+        load_state(state_in, n, i, s);
+        const int age = step_count[i];
+        float4 a4 = ldg4(action, size_t(i));
+        if (age < E.fifo_depth) a4 = make_float4(0.f, 0.f, 0.f, 0.f);   // FIFO rows of a reset agent read as zero
+        const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+        vf::Wrench<float> k;
+        vf::step_fwd<float>(P, substeps, INTEG, ACT, LAG, a, s, k);
+
+        float vel[3] = {s.v[0] + P.wind[0], s.v[1] + P.wind[1], s.v[2] + P.wind[2]};
+        const vf::BoxHit<float> hit = vf::box_hit<float>(s.p, E.bbox_lo, E.bbox_hi);
+        unsigned eb = ebits[i];
+        const bool is_col = hit.dis < E.uav_radius;
+        bool once = (eb & VF_EBIT_ONCE_COLLIDED) || is_col;
+        int sc = age + 1;
+        int passed = 0;
+        bool success = false;
+        float reward;
+        if (E.task == VF_TASK_HOVER) {
+            reward = vf::reward_hover<float>(s.p, s.q, vel, s.w, E.target);
+        } else if (E.task == VF_TASK_NAVIGATION) {
+            success = vf::norm3(s.p[0] - E.target[0], s.p[1] - E.target[1], s.p[2] - E.target[2]) <= E.success_radius;
+            reward = vf::reward_navigation<float>(s.p, s.q, vel, s.w, E.target, hit, success, E.max_episode_steps, sc);
+        } else {
+            g = gate[i];
+            passed = gates_passed[i];
+            const bool pass = vf::norm3(s.p[0] - E.gates[g][0], s.p[1] - E.gates[g][1], s.p[2] - E.gates[g][2]) <=
+                              E.success_radius;
+            g = (g + (pass ? 1 : 0)) % E.n_gates;
+            passed += pass ? 1 : 0;
+            reward = vf::reward_hover<float>(s.p, s.q, vel, s.w, E.gates[g]) + (pass ? 20.f : 0.f);
+        }
+        float ret = returns[i] + reward;
+        bool ep_done = (eb & VF_EBIT_EPISODE_DONE) || success || hit.out || (E.collision_reset && is_col);
+        const bool done = ep_done || sc >= E.max_episode_steps;
+
+        unsigned rbits = (done ? VF_RBIT_DONE : 0u) | (ep_done ? VF_RBIT_EPISODE_DONE : 0u) |
+                         (success ? VF_RBIT_SUCCESS : 0u) | (sc >= E.max_episode_steps ? VF_RBIT_TRUNCATED : 0u) |
+                         (once ? VF_RBIT_COLLIDED : 0u);
+        stg4(record_out, size_t(i), make_float4(ret, float(sc), float(rbits), float(passed)));
+        reward_out[i] = reward;
+        done_out[i] = done ? 1 : 0;
+
+        if (done && term_obs_out) {                 // rare: scalar stores are fine
+            if (E.obs_kind == VF_OBS_STATE13) {
+                float* t = term_obs_out + size_t(i) * 13;
+                t[0] = s.p[0]; t[1] = s.p[1]; t[2] = s.p[2];
+                t[3] = s.q[0]; t[4] = s.q[1]; t[5] = s.q[2]; t[6] = s.q[3];
+                t[7] = vel[0]; t[8] = vel[1]; t[9] = vel[2];
+                t[10] = s.w[0]; t[11] = s.w[1]; t[12] = s.w[2];
+            } else {
+                float* t = term_obs_out + size_t(i) * 16;
+                // the reference builds the terminal observation before the gate index advances (RacingEnv.py:254)
+                const int g0 = (E.task == VF_TASK_RACING) ? gate[i] : 0;
+                for (int kk = 0; kk < 2; ++kk)
+                    for (int j = 0; j < 3; ++j) t[3 * kk + j] = (E.gates[(g0 + kk) % E.n_gates][j] - s.p[j]) / 10.f;
+                t[6] = s.q[0]; t[7] = s.q[1]; t[8] = s.q[2]; t[9] = s.q[3];
+                for (int j = 0; j < 3; ++j) { t[10 + j] = vel[j] / 10.f; t[13 + j] = s.w[j] / 10.f; }
+            }
+        }
+        if (done && !(env_flags & VF_ENV_FLAG_NO_RESET)) {
+            if (E.task == VF_TASK_RACING) {         // chosen from the terminal position (RacingEnv.py:150-163)
+                g = vf::racing_first_gate<float>(s.p);
+                passed = 0;
+            }
+            vf::sample_reset(E, unsigned(i), step_index, reset_table ? reset_table + size_t(i) * 13 : nullptr,
+                             s.p, s.q, s.v, s.w);
+            for (int j = 0; j < 4; ++j) s.mot[j] = E.init_motor_omega;
+            s.al[0] = s.al[1] = s.al[2] = 0.f;
+            sc = 0; ret = 0.f; ep_done = false; once = false;
+            vel[0] = s.v[0] + P.wind[0]; vel[1] = s.v[1] + P.wind[1]; vel[2] = s.v[2] + P.wind[2];
+        }
+        store_state(state_out, n, i, s);
+        step_count[i] = sc;
+        returns[i] = ret;
+        ebits[i] = (unsigned char)((ep_done ? VF_EBIT_EPISODE_DONE : 0u) | (once ? VF_EBIT_ONCE_COLLIDED : 0u));
+        if (E.task == VF_TASK_RACING) { gate[i] = g; gates_passed[i] = passed; }
+
+        if (E.obs_kind == VF_OBS_RACING16) {
+            float o[16];
+            for (int kk = 0; kk < 2; ++kk)
+                for (int j = 0; j < 3; ++j) o[3 * kk + j] = (E.gates[(g + kk) % E.n_gates][j] - s.p[j]) / 10.f;
+            o[6] = s.q[0]; o[7] = s.q[1]; o[8] = s.q[2]; o[9] = s.q[3];
+            for (int j = 0; j < 3; ++j) { o[10 + j] = vel[j] / 10.f; o[13 + j] = s.w[j] / 10.f; }
+            for (int kk = 0; kk < 4; ++kk)
+                stg4(obs_out, size_t(4) * i + kk, make_float4(o[4 * kk], o[4 * kk + 1], o[4 * kk + 2], o[4 * kk + 3]));
+        }
+    }
+    if (E.obs_kind == VF_OBS_STATE13) {
+        float o[kObs];
+        if (live) {
+            o[0] = s.p[0]; o[1] = s.p[1]; o[2] = s.p[2];
+            o[3] = s.q[0]; o[4] = s.q[1]; o[5] = s.q[2]; o[6] = s.q[3];
+            o[7] = s.v[0] + P.wind[0]; o[8] = s.v[1] + P.wind[1]; o[9] = s.v[2] + P.wind[2];
+            o[10] = s.w[0]; o[11] = s.w[1]; o[12] = s.w[2];
+        }
+        warp_store_obs(obs_out, s_obs + warp * kWarpObs, n, warp_first, lane, o);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // layout conversion (reset / property views)
 // ---------------------------------------------------------------------------------------------
 __global__ void vf_pack_kernel(int n, int m, const long long* __restrict__ index,
@@ -280,6 +404,16 @@ void launch_bwd(const VfParams& p, int n, int substeps, const float* si, const f
         vf_step_bwd_kernel<INTEG, ACT, LAG, 16, kBlock><<<grid, kBlock, 0, st>>>(p, n, substeps, si, a, gso, gobs, gsi, ga);
     else
         vf_step_bwd_kernel<INTEG, ACT, LAG, VF_MAX_SUBSTEPS_BWD, kBlock><<<grid, kBlock, 0, st>>>(p, n, substeps, si, a, gso, gobs, gsi, ga);
+}
+
+template <int INTEG, int ACT, bool LAG>
+void launch_env_fwd(const VfParams& p, const VfEnvSpec& e, int n, int substeps, unsigned env_flags,
+                    unsigned long long step_index, const float* si, const float* a, const float* table, int* sc,
+                    float* ret, unsigned char* eb, int* gate, int* passed, float* so, float* obs, float* rew,
+                    unsigned char* done, float* rec, float* tobs, cudaStream_t st) {
+    const int grid = (n + kBlock - 1) / kBlock;
+    vf_env_step_fwd_kernel<INTEG, ACT, LAG, kBlock><<<grid, kBlock, 0, st>>>(
+        p, e, n, substeps, env_flags, step_index, si, a, table, sc, ret, eb, gate, passed, so, obs, rew, done, rec, tobs);
 }
 
 #define VF_DISPATCH(FN, ...)                                                                  \
@@ -379,6 +513,41 @@ int vf_step_fwd_host(const VfParams* params, int n, int substeps, int integrator
     }
     err = cudaStreamSynchronize(st);
     if (err != cudaSuccess) return fail("vf_step_fwd_host: stream synchronise failed", err);
+    return 0;
+}
+
+int vf_env_spec_size(void) { return int(sizeof(VfEnvSpec)); }
+
+int vf_env_step_fwd(const VfParams* params, const VfEnvSpec* spec, int n, int substeps, int integrator,
+                    int action_type, unsigned flags, unsigned env_flags, unsigned long long step_index,
+                    const float* state_in, const float* action, const float* reset_table, int* step_count,
+                    float* returns, unsigned char* ebits, int* gate, int* gates_passed, float* state_out,
+                    float* obs_out, float* reward_out, unsigned char* done_out, float* record_out,
+                    float* term_obs_out, void* stream) {
+    if (check_common(params, n, substeps, integrator, action_type)) return 1;
+    if (!spec) return fail("spec is NULL");
+    if (spec->task < VF_TASK_HOVER || spec->task > VF_TASK_RACING) return fail("spec.task must be a VF_TASK_* value");
+    if (spec->obs_kind != VF_OBS_STATE13 && spec->obs_kind != VF_OBS_RACING16)
+        return fail("spec.obs_kind must be a VF_OBS_* value");
+    if (spec->gen_kind < VF_GEN_UNIFORM || spec->gen_kind > VF_GEN_TABLE) return fail("spec.gen_kind must be a VF_GEN_* value");
+    if (spec->gen_boxes < 1 || spec->gen_boxes > VF_GEN_MAX_BOXES) return fail("spec.gen_boxes out of range");
+    if (spec->task == VF_TASK_RACING && (spec->n_gates < 1 || spec->n_gates > 4)) return fail("spec.n_gates out of range");
+    if (n == 0) return 0;
+    if (!state_in || !action || !state_out || !step_count || !returns || !ebits || !obs_out || !reward_out ||
+        !done_out || !record_out)
+        return fail("vf_env_step_fwd: a required buffer is NULL");
+    if (spec->task == VF_TASK_RACING && (!gate || !gates_passed)) return fail("racing needs gate and gates_passed buffers");
+    if (spec->gen_kind == VF_GEN_TABLE && !reset_table) return fail("VF_GEN_TABLE needs reset_table");
+    if (state_in == state_out) return fail("state_out must not alias state_in");
+    if (!aligned16(state_in) || !aligned16(action) || !aligned16(state_out) || !aligned16(obs_out) ||
+        !aligned16(record_out))
+        return fail("all float4 buffers must be 16-byte aligned");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    VF_DISPATCH(launch_env_fwd, *params, *spec, n, substeps, env_flags, step_index, state_in, action, reset_table,
+                step_count, returns, ebits, gate, gates_passed, state_out, obs_out, reward_out, done_out, record_out,
+                term_obs_out, st);
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return fail("vf_env_step_fwd launch failed", err);
     return 0;
 }
 

@@ -198,6 +198,7 @@ class Dynamics:
             self._n_steps = 0
             self._pre_action = [th.zeros((n, 4), device=dev) for _ in range(self._comm_delay_steps)]
             self._prev, self._ext, self._fresh = None, None, None
+            self._t_steps = None
             self._thrusts_given = None if thrusts is None else self._f(thrusts, 4)
         else:
             idx = th.as_tensor(indices, device=dev, dtype=th.int64).reshape(-1)
@@ -357,7 +358,22 @@ class Dynamics:
 
     @property
     def t(self):
+        if self._t_steps is not None:        # fused env step: time since the agent's last reset
+            return self._t_steps * self.ctrl_dt
         return self._t_base + self._n_steps * self.ctrl_dt
+
+    # the (N,13) observation is a kernel output; it is rebuilt from the packed state only if a path that does
+    # not produce it (fused env step with a task-specific observation) ran last
+    @property
+    def _obs(self):
+        if self._obs_t is None:
+            s = self._state
+            self._obs_t = th.cat([s[0, :, :3], s[1], s[2, :, :3] + self.wind_velocity.T, s[3, :, :3]], 1)
+        return self._obs_t
+
+    @_obs.setter
+    def _obs(self, value):
+        self._obs_t = value
 
     @property
     def motor_omega(self):

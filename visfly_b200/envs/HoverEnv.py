@@ -42,6 +42,13 @@ class HoverEnv(DroneGymEnvsBase):
     def get_observation(self, indices=None, predicted_obs=None) -> Dict:
         return TensorDict({"state": self.state})
 
+    def _make_fused(self):
+        from .. import params as P
+        from .base.fused import FusedEnvStep
+        if not self._builtin_task(HoverEnv) or bool((self.target != self.target[0]).any()):
+            return None
+        return FusedEnvStep(self, P.TASK_HOVER, P.OBS_STATE13, target=self.target[0].tolist())
+
     def get_success(self) -> th.Tensor:
         return th.zeros(self.num_agent, dtype=th.bool, device=self.device)      # reference HoverEnv.py:79-80
 

@@ -44,6 +44,17 @@ class NavigationEnv(DroneGymEnvsBase):
     def get_success(self) -> th.Tensor:
         return (self.position - self.target).norm(dim=1) <= self.success_radius
 
+    def _make_fused(self):
+        from .. import params as P
+        from .base.fused import FusedEnvStep
+        if not self._builtin_task(NavigationEnv) or bool((self.target != self.target[0]).any()):
+            return None
+        return FusedEnvStep(self, P.TASK_NAVIGATION, P.OBS_STATE13, target=self.target[0].tolist(),
+                            success_radius=self.success_radius)
+
+    def _fused_obs(self, obs):
+        return TensorDict({"state": obs, "target": self.target})
+
     def get_reward(self, predicted_obs=None) -> th.Tensor:
         """reference NavigationEnv.py:85-99, term by term."""
         base_r = 0.1

@@ -74,6 +74,21 @@ class RacingEnv(DroneGymEnvsBase):
     def get_observation(self, indices=None, predicted_obs=None) -> Dict:
         return TensorDict({"state": self.state, "gate": self._next_target_i})
 
+    _FUSED_OBS = 0          # params.OBS_STATE13
+
+    def _make_fused(self):
+        from .. import params as P
+        from .base.fused import FusedEnvStep
+        owner = RacingEnv2 if isinstance(self, RacingEnv2) else RacingEnv
+        if not is_pos_reward or not self._builtin_task(owner) or type(self)._extra_info is not RacingEnv._extra_info:
+            return None
+        return FusedEnvStep(self, P.TASK_RACING, self._FUSED_OBS, gates=self.targets,
+                            success_radius=self.success_radius)
+
+    def _fused_obs(self, obs):
+        gate = self._fused.gate.to(th.int64)
+        return TensorDict({"state": obs, "gate": gate.unsqueeze(1) if self._FUSED_OBS else gate})
+
     def get_success(self) -> th.Tensor:
         """Gate passing (reference :142-148); never ends the episode."""
         gate = self.targets[self._next_target_i]
@@ -115,6 +130,8 @@ class RacingEnv(DroneGymEnvsBase):
 
 
 class RacingEnv2(RacingEnv):
+    _FUSED_OBS = 1          # params.OBS_RACING16
+
     def get_observation(self, indices=None, predicted_obs=None) -> Dict:
         """Relative positions of the next two gates, attitude, scaled velocities (reference :250-267)."""
         nxt = th.stack([self._next_target_i + i for i in range(self._next_target_num)]).T % len(self.targets)

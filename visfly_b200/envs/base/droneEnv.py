@@ -67,6 +67,9 @@ class DroneEnvsBase:
         self._is_collision = th.zeros(n, dtype=th.bool, device=self.device)
         self._is_out_bounds = th.zeros(n, dtype=th.bool, device=self.device)
         self._collision_point = self._collision_vector = self._collision_dis = None
+        self._collision_stale = False      # set by the fused env step: collision views are recomputed on demand
+        self._reset_table = None           # optional (N,13) [p q v w] rows agents restart from (set_reset_table)
+        self._fused = None                 # FusedEnvStep while the one-kernel env step owns the per-agent status
         self._eval = False
 
     # -- construction helpers ---------------------------------------------------------------------
@@ -98,7 +101,21 @@ class DroneEnvsBase:
         return gen
 
     # -- state generation / reset ---------------------------------------------------------------------
+    def set_reset_table(self, pos, quat, vel=None, ang_vel=None):
+        """Deterministic (re)starts: agent i always restarts from row i.  Replaces the random state generator
+        for both the fused and the generic path (``None`` as ``pos`` switches back to the generator)."""
+        if pos is None:
+            self._reset_table = None
+            return
+        n, dev = self.dynamics.num, self.device
+        f = lambda x, k: th.zeros((n, k), device=dev) if x is None else \
+            th.as_tensor(x, dtype=th.float32, device=dev).reshape(n, k)
+        self._reset_table = th.cat([f(pos, 3), f(quat, 4), f(vel, 3), f(ang_vel, 3)], 1).contiguous()
+
     def _generate_state(self, indices=None, num: Optional[int] = None):
+        if self._reset_table is not None:
+            t = self._reset_table if indices is None else self._reset_table[th.as_tensor(indices, device=self.device)]
+            return t[:, 0:3], t[:, 3:7], t[:, 7:10], t[:, 10:13]
         n = self.dynamics.num if indices is None else len(indices)
         return self.stateGenerator.safe_generate(num=n if num is None else num)
 
@@ -176,6 +193,14 @@ class DroneEnvsBase:
         self._collision_dis = (self._collision_vector - 0).norm(dim=1)
         self._is_collision = self._collision_dis < self.uav_radius
         self._once_collided = self._once_collided | self._is_collision
+        self._collision_stale = False
+
+    def _collision_view(self, name):
+        if self._collision_stale:           # after a fused step: recompute from the current position, keep the flags
+            keep = self._once_collided
+            self.update_collision()
+            self._once_collided = keep
+        return getattr(self, name)
 
     def step(self, action):
         self.dynamics.step(action)
@@ -211,8 +236,8 @@ class DroneEnvsBase:
     # -- views -----------------------------------------------------------------------------------------------------
     state = property(lambda s: s.dynamics.state)
     sensor_obs = property(lambda s: s._sensor_obs)
-    is_collision = property(lambda s: s._is_collision)
-    is_out_bounds = property(lambda s: s._is_out_bounds)
+    is_collision = property(lambda s: s._collision_view("_is_collision"))
+    is_out_bounds = property(lambda s: s._collision_view("_is_out_bounds"))
     direction = property(lambda s: s.dynamics.direction)
     position = property(lambda s: s.dynamics.position)
     orientation = property(lambda s: s.dynamics.orientation)
@@ -224,10 +249,15 @@ class DroneEnvsBase:
     extend_state = property(lambda s: s.dynamics.extend_state)
     acceleration = property(lambda s: s.dynamics.acceleration)
     angular_acceleration = property(lambda s: s.dynamics.angular_acceleration)
-    collision_point = property(lambda s: s._collision_point)
-    collision_vector = property(lambda s: s._collision_vector)
-    collision_dis = property(lambda s: s._collision_dis)
-    once_collided = property(lambda s: s._once_collided)
+    collision_point = property(lambda s: s._collision_view("_collision_point"))
+    collision_vector = property(lambda s: s._collision_view("_collision_vector"))
+    collision_dis = property(lambda s: s._collision_view("_collision_dis"))
+
+    @property
+    def once_collided(self):
+        if self._fused is not None and self._fused.active:
+            return (self._fused.eb & 2).bool()
+        return self._once_collided
 
     @property
     def dynamic_object_position(self):

@@ -144,6 +144,8 @@ class DroneGymEnvsBase(VecEnv):
         self._done = th.zeros(n, dtype=th.bool, device=dev)
         self._info = None
         self._indiv_rewards = self._indiv_reward = None
+        self.keep_terminal_observation = True     # False: skip writing info["terminal_observation"] rows
+        self._fused = None                        # FusedEnvStep, created by built-in tasks (_make_fused)
         self.render_mode = ["None"] * n
         self._is_initial = False
 
@@ -155,10 +157,13 @@ class DroneGymEnvsBase(VecEnv):
         assert self._is_initial, "You should call reset() before step()"
         if world is not None or predict:
             raise NotImplementedError("world-model rollouts are not part of the dynamics path")
-        action = _action if isinstance(_action, th.Tensor) else th.as_tensor(np.asarray(_action))
-        self._action = action.to(self.device, dtype=th.float32)
+        self._action = self._stage_action(_action)
         if self.debug_checks:                                   # reference droneGymEnv.py:144 (host sync)
             assert self._action.max() <= 1 and self._action.min() >= -1
+        if self._fused is not None:
+            if not self.requires_grad and not is_test and self._fused.refresh():
+                return self._step_fused()
+            self._fused.leave()
         with self._grad_ctx():
             self.envs.step(self._action)
             self.get_full_observation()
@@ -186,6 +191,29 @@ class DroneGymEnvsBase(VecEnv):
             self._info = info
             if not is_test:
                 self._auto_reset(done)
+        return self._format_step_output(reward, done, info)
+
+    # -- one-kernel path (built-in tasks, no autograd) -------------------------------------------------------
+    def _make_fused(self):
+        """Built-in task envs return a ``FusedEnvStep`` here; ``None`` keeps the generic tensor-op path."""
+        return None
+
+    def _builtin_task(self, owner) -> bool:
+        """True if this object's task methods are exactly ``owner``'s (not overridden by a user subclass)."""
+        return all(getattr(type(self), m) is getattr(owner, m)
+                   for m in ("get_reward", "get_success", "get_failure", "get_observation"))
+
+    def _fused_obs(self, obs: th.Tensor) -> TensorDict:
+        return TensorDict({"state": obs})
+
+    def _step_fused(self):
+        from .fused import RecordInfo
+        obs, reward, done, record, term = self._fused.step(self._action)
+        self._obs_tensors = self._fused_obs(obs)
+        term_obs = self._fused_obs(term) if term is not None else {}
+        info = RecordInfo(self.num_agent, record, term_obs, self.envs.dynamics.ctrl_dt,
+                          racing=self._fused.gate is not None)
+        self._info = info
         return self._format_step_output(reward, done, info)
 
     def _snapshot_info(self) -> LazyInfo:
@@ -221,8 +249,57 @@ class DroneGymEnvsBase(VecEnv):
         if self.tensor_output:
             self._observations = self._obs_tensors
             return self._observations.detach(), reward.detach(), done, info
-        self._observations = self._format_obs(self._obs_tensors)
-        return self._observations, reward.cpu().numpy(), done.cpu().numpy().astype(np.int32), info
+        # numpy mode (reference droneGymEnv.py:218): everything goes to page-locked host buffers with
+        # asynchronous copies and ONE stream synchronisation, instead of one blocking .cpu() per tensor
+        host = self._host_buffers(self._obs_tensors, reward, done)
+        for k, v in self._obs_tensors.items():
+            host["obs"][k].copy_(v.detach(), non_blocking=True)
+        host["reward"].copy_(reward.detach(), non_blocking=True)
+        host["done"].copy_(done, non_blocking=True)
+        th.cuda.current_stream(self.device).synchronize()
+        self._observations = TensorDict({k: v.numpy() for k, v in host["obs"].items()})
+        return self._observations, host["reward"].numpy(), host["done"].numpy().astype(np.int32), info
+
+    def _host_buffers(self, obs, reward, done):
+        """Two alternating sets of pinned host buffers (the arrays handed out last step stay valid for one step)."""
+        ring = getattr(self, "_host_ring", None)
+        if ring is None or any(k not in ring[0]["obs"] or ring[0]["obs"][k].shape != v.shape for k, v in obs.items()):
+            pin = lambda t: th.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            ring = [{"obs": {k: pin(v) for k, v in obs.items()}, "reward": pin(reward), "done": pin(done)}
+                    for _ in range(2)]
+            self._host_ring, self._host_turn = ring, 0
+        self._host_turn ^= 1
+        return ring[self._host_turn]
+
+    def _stage_action(self, action) -> th.Tensor:
+        """Host actions (numpy / CPU tensors) reach the device through a pinned staging buffer."""
+        if isinstance(action, th.Tensor) and action.is_cuda:
+            return action.to(self.device, dtype=th.float32)
+        src = action if isinstance(action, th.Tensor) else th.as_tensor(np.asarray(action))
+        pin = getattr(self, "_act_pin", None)
+        if pin is None or pin.shape != src.shape:
+            pin = self._act_pin = th.empty(src.shape, dtype=th.float32, pin_memory=True)
+        evt = getattr(self, "_act_evt", None)
+        if evt is not None:
+            evt.synchronize()                 # the previous step's H2D copy must have left the staging buffer
+        pin.copy_(src)
+        dev = pin.to(self.device, non_blocking=True)
+        self._act_evt = th.cuda.Event()
+        self._act_evt.record(th.cuda.current_stream(self.device))
+        return dev
+
+    _TRANSIENT = ("_host_ring", "_host_turn", "_act_pin", "_act_evt")
+
+    def __deepcopy__(self, memo):
+        """Deep-copyable like the reference env (utils/algorithms/shac.py:121); host staging buffers and CUDA
+        events are per-object scratch and are re-created lazily by the copy."""
+        import copy
+        twin = self.__class__.__new__(self.__class__)
+        memo[id(self)] = twin
+        for k, v in self.__dict__.items():
+            if k not in self._TRANSIENT:
+                setattr(twin, k, copy.deepcopy(v, memo))
+        return twin
 
     def _format_obs(self, obs):
         if not self.tensor_output:
@@ -232,6 +309,9 @@ class DroneGymEnvsBase(VecEnv):
     # -- reset ---------------------------------------------------------------------------------------------
     def reset(self, state=None, predicted_obs=None, is_test=False, stoch=None, deter=None):
         self._is_initial = True
+        if self._fused is not None:
+            self._fused.active = False            # a full reset re-initialises everything the fused path owns
+            self.envs._fused = None
         with self._grad_ctx():
             self.envs.reset(state=state)
             self._on_reset_where(th.ones(self.num_agent, dtype=th.bool, device=self.device))
@@ -245,12 +325,15 @@ class DroneGymEnvsBase(VecEnv):
                 self._indiv_reward = self._indiv_rewards = None
             else:
                 raise ValueError(f"get_reward should return a dict or a tensor, but got {type(probe)}")
+        self._fused = self._make_fused()
         self._observations = self._format_obs(self._obs_tensors)
         return self._observations
 
     def reset_agent_by_id(self, agent_indices=None, state=None, reset_obs=None):
         """Index-based reset of selected agents (reference droneGymEnv.py:339-349)."""
         assert not isinstance(agent_indices, bool)
+        if self._fused is not None:
+            self._fused.leave()
         with self._grad_ctx():
             if agent_indices is None:
                 mask = th.ones(self.num_agent, dtype=th.bool, device=self.device)
@@ -270,6 +353,8 @@ class DroneGymEnvsBase(VecEnv):
         return self.reset_agent_by_id(agents)
 
     def examine(self):
+        if self._fused is not None:
+            self._fused.leave()
         self._auto_reset(self._done)
         self._observations = self._format_obs(self._obs_tensors)
         return self._observations
@@ -305,6 +390,11 @@ class DroneGymEnvsBase(VecEnv):
     def detach(self):
         self.envs.detach()
         self.simple_detach()
+
+    def get_state_for_generic_path(self):
+        """Make sure the per-agent attributes (``_step_count``, ``_rewards``, ...) are the live ones."""
+        if self._fused is not None:
+            self._fused.leave()
 
     def simple_detach(self):
         self._rewards = self._rewards.detach()

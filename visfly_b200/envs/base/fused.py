@@ -1,0 +1,223 @@
+"""Host side of the fused env step (``vf_env_step_fwd``): one kernel launch per ``env.step`` for the built-in tasks.
+
+``DroneGymEnvsBase.step`` takes this path when nothing needs autograd or Python-defined task code:
+``requires_grad=False``, ``is_test=False``, the task's ``get_reward / get_success / get_failure / get_observation``
+are the built-in ones, the IMU noise model is zero, the state generator is one the kernel can sample
+(Uniform / Normal / Union of those, or a reset table), and the orientation output is the quaternion.  Everything else
+(custom tasks, analytic-gradient training) keeps using the generic tensor-op path, which has identical semantics;
+``tests/test_gpu_env.py`` replays the reference's golden runs through both.
+"""
+from __future__ import annotations
+
+import os
+from collections.abc import Sequence
+from typing import Dict, Optional
+
+import numpy as np
+import torch as th
+
+from ... import _lib
+from ... import params as P
+from ...randomization import NormalStateRandomizer, UniformStateRandomizer, UnionRandomizer
+
+
+def generator_spec(gen, spec: P.VfEnvSpec) -> bool:
+    """Fill the reset-sampler part of ``spec`` from a state generator; False if the kernel cannot express it."""
+    boxes = gen.randomizers if isinstance(gen, UnionRandomizer) else [gen]
+    if not 1 <= len(boxes) <= P.GEN_MAX_BOXES:
+        return False
+    kinds = set()
+    for b, g in enumerate(boxes):
+        if isinstance(g, UniformStateRandomizer):
+            kinds.add(P.GEN_UNIFORM)
+            mean, half = g._mean, g._half
+        elif isinstance(g, NormalStateRandomizer):
+            kinds.add(P.GEN_NORMAL)
+            mean, half = g._mean, g._std
+        else:
+            return False
+        mean, half = mean.cpu(), half.cpu()
+        for f in range(4):
+            for j in range(3):
+                spec.gen_mean[b][f][j] = float(mean[f, j])
+                spec.gen_half[b][f][j] = float(half[f, j])
+    if len(kinds) != 1:
+        return False
+    spec.gen_kind, spec.gen_boxes = kinds.pop(), len(boxes)
+    return True
+
+
+class RecordInfo(Sequence):
+    """Lazy ``info`` list backed by the kernel's per-step episode record ``[return, length, bits, gates]``."""
+
+    _IDLE = {"TimeLimit.truncated": False, "episode_done": False}
+
+    def __init__(self, n, record: th.Tensor, term_obs: Dict[str, th.Tensor], ctrl_dt: float, racing: bool):
+        self._n, self._record, self._term, self._ctrl_dt, self._racing = n, record, term_obs, ctrl_dt, racing
+        self._host = None
+        self._cache: Dict[int, dict] = {}
+
+    def _fetch(self):
+        if self._host is None:
+            self._host = self._record.cpu().numpy()
+        return self._host
+
+    def __len__(self):
+        return self._n
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[j] for j in range(*i.indices(self._n))]
+        if i < 0:
+            i += self._n
+        if not 0 <= i < self._n:
+            raise IndexError(i)
+        if i in self._cache:
+            return self._cache[i]
+        ret, length, bits, gates = self._fetch()[i]
+        bits = int(bits)
+        if not bits & P.RBIT_DONE:
+            info = dict(self._IDLE)
+        else:
+            length = np.asarray(int(length), dtype=np.int32)
+            info = {
+                "episode_done": bool(bits & P.RBIT_EPISODE_DONE),
+                "is_success": bool(bits & P.RBIT_SUCCESS),
+                "episode": {"r": np.asarray(ret, dtype=np.float32), "l": length,
+                            "t": np.asarray(length * self._ctrl_dt, dtype=np.float32),
+                            "extra": {"collision": np.asarray(bool(bits & P.RBIT_COLLIDED))}},
+                "terminal_observation": {k: v[i] for k, v in self._term.items()},
+                "TimeLimit.truncated": bool(bits & P.RBIT_TRUNCATED),
+            }
+            if self._racing:
+                info["episode"]["extra"]["past_gate"] = int(gates)
+        self._cache[i] = info
+        return info
+
+    def copy(self):
+        return self
+
+    def done_indices(self):
+        return np.nonzero(self._fetch()[:, 2].astype(np.int64) & P.RBIT_DONE)[0]
+
+
+class FusedEnvStep:
+    """Owns the spec and the in-place per-agent env state of one env object while the fused path is active."""
+
+    def __init__(self, env, task: int, obs_kind: int, target=None, gates=None, success_radius: float = 0.5):
+        dyn = env.envs.dynamics
+        self.env, self.n, self.device = env, env.num_agent, env.device
+        self.task, self.obs_kind = task, obs_kind
+        self.obs_width = 13 if obs_kind == P.OBS_STATE13 else 16
+        s = P.VfEnvSpec()
+        s.task, s.obs_kind = task, obs_kind
+        s.uav_radius = env.envs.uav_radius
+        lo, hi = env.envs._bboxes[0][0].tolist(), env.envs._bboxes[0][1].tolist()
+        for j in range(3):
+            s.bbox_lo[j], s.bbox_hi[j] = lo[j], hi[j]
+            s.target[j] = 0.0 if target is None else float(target[j])
+        s.success_radius = success_radius
+        s.n_gates = 0
+        if gates is not None:
+            g = th.as_tensor(gates).cpu()
+            s.n_gates = g.shape[0]
+            for a in range(g.shape[0]):
+                for j in range(3):
+                    s.gates[a][j] = float(g[a, j])
+        s.fifo_depth = dyn._comm_delay_steps
+        s.init_motor_omega = float(dyn._init_motor_omega)
+        s.seed = (int(env.envs.seed) * 0x9E3779B97F4A7C15 + 0x1234567) & 0xFFFFFFFFFFFFFFFF
+        self.spec = s
+        self.table: Optional[th.Tensor] = None
+        self.active = False
+        self.global_step = 0
+        self.sc = self.ret = self.eb = self.gate = self.passed = None
+
+    # -- eligibility ------------------------------------------------------------------------------------
+    def refresh(self) -> bool:
+        """Re-read the settings that may change between steps; False => the generic path must be used."""
+        env, s = self.env, self.spec
+        if os.environ.get("VISFLY_B200_NO_FUSED_ENV") or not env.envs._imu_noise_free:
+            return False
+        if not env.envs.dynamics.is_quat_output or "_generate_state" in vars(env.envs):
+            return False
+        s.max_episode_steps = int(env.max_episode_steps)
+        s.collision_reset = int(bool(env.is_collision_reset))
+        table = env.envs._reset_table
+        if table is not None:
+            s.gen_kind, s.gen_boxes, self.table = P.GEN_TABLE, 1, table
+            return True
+        self.table = None
+        return generator_spec(env.envs.stateGenerator, s)
+
+    # -- switching between the two paths ----------------------------------------------------------------
+    def enter(self):
+        env, dyn = self.env, self.env.envs.dynamics
+        self.sc = env._step_count.to(th.int32).clone()
+        self.ret = env._rewards.detach().to(th.float32).clone()
+        self.eb = env.envs._once_collided.to(th.uint8) * P.EBIT_ONCE_COLLIDED \
+            + env._episode_done.to(th.uint8) * P.EBIT_EPISODE_DONE
+        if self.task == P.TASK_RACING:
+            self.gate = env._next_target_i.to(th.int32).clone()
+            self.passed = env._past_targets_num.to(th.int32).clone()
+        dyn.detach()
+        env.envs._fused = self
+        self.active = True
+
+    def leave(self):
+        """Hand the per-agent state back to the attributes the generic path works on."""
+        if not self.active:
+            return
+        env, dyn = self.env, self.env.envs.dynamics
+        env._step_count = self.sc.clone()
+        env._rewards = self.ret.clone()
+        env._episode_done = (self.eb & P.EBIT_EPISODE_DONE).bool()
+        env.envs._once_collided = (self.eb & P.EBIT_ONCE_COLLIDED).bool()
+        if self.task == P.TASK_RACING:
+            env._next_target_i = self.gate.to(th.int64)
+            env._past_targets_num = self.passed.to(th.int64)
+        # FIFO rows the kernel treated as zero (agent younger than the entry) become real zeros again
+        d = len(dyn._pre_action)
+        dyn._pre_action = [th.where((self.sc < d - j).view(-1, 1), 0.0, a) for j, a in enumerate(dyn._pre_action)]
+        dyn._t_base = self.sc * dyn.ctrl_dt - dyn._n_steps * dyn.ctrl_dt
+        dyn._t_steps = None
+        env.envs.update_observation()
+        env.envs.update_collision()
+        env.envs._once_collided = (self.eb & P.EBIT_ONCE_COLLIDED).bool()
+        env.envs._fused = None
+        self.active = False
+
+    # -- the step -------------------------------------------------------------------------------------------
+    def step(self, action: th.Tensor):
+        env, dyn, n, dev = self.env, self.env.envs.dynamics, self.n, self.device
+        if not self.active:
+            self.enter()
+        if dyn._comm_delay_steps:
+            dyn._pre_action.append(action)
+            action = dyn._pre_action.pop(0)
+        action = action.contiguous()
+        state_in = dyn._state
+        state_out = th.empty_like(state_in)
+        obs = th.empty((n, self.obs_width), dtype=th.float32, device=dev)
+        reward = th.empty((n,), dtype=th.float32, device=dev)
+        done = th.empty((n,), dtype=th.bool, device=dev)
+        record = th.empty((n, 4), dtype=th.float32, device=dev)
+        term = th.empty((n, self.obs_width), dtype=th.float32, device=dev) if env.keep_terminal_observation else None
+        cfg = dyn._cfg
+        _lib.env_step_fwd(cfg.params, self.spec, cfg.substeps, cfg.integrator, cfg.action_type, cfg.flags, 0,
+                          self.global_step, state_in, action, self.table, self.sc, self.ret, self.eb, self.gate,
+                          self.passed, state_out, obs, reward, done, record, term)
+        self.global_step += 1
+        # keep the Dynamics object coherent (lazy views, diagnostics)
+        dyn._prev = (state_in, action)
+        dyn._state = state_out
+        dyn._obs = obs if self.obs_kind == P.OBS_STATE13 else None
+        dyn._n_steps += 1
+        dyn._ext, dyn._thrusts_given = None, None
+        dyn._fresh = done
+        dyn._t_steps = self.sc
+        env.envs._collision_stale = True
+        env._step_count, env._rewards, env._reward, env._done = self.sc, self.ret, reward, done
+        if self.gate is not None:
+            env._next_target_i, env._past_targets_num = self.gate, self.passed
+        return obs, reward, done, record, term

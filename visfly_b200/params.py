@@ -227,3 +227,38 @@ def build_vf_params(model: DroneModel, action_type: ACTION_TYPE, scaling: Dict[s
         p.act_half[i] = float(halves[i])
         p.act_mean[i] = float(means[i])
     return p
+
+
+# ---------------------------------------------------------------------------------------------------
+# fused env step: ctypes mirror of ``struct VfEnvSpec`` (include/visfly_b200.h)
+# ---------------------------------------------------------------------------------------------------
+TASK_HOVER, TASK_NAVIGATION, TASK_RACING = 0, 1, 2
+OBS_STATE13, OBS_RACING16 = 0, 1
+GEN_UNIFORM, GEN_NORMAL, GEN_TABLE = 0, 1, 2
+GEN_MAX_BOXES = 4
+ENV_FLAG_NO_RESET = 1
+RBIT_DONE, RBIT_EPISODE_DONE, RBIT_SUCCESS, RBIT_TRUNCATED, RBIT_COLLIDED = 1, 2, 4, 8, 16
+EBIT_EPISODE_DONE, EBIT_ONCE_COLLIDED = 1, 2
+
+
+class VfEnvSpec(ctypes.Structure):
+    _fields_ = [
+        ("task", ctypes.c_int),
+        ("obs_kind", ctypes.c_int),
+        ("max_episode_steps", ctypes.c_int),
+        ("collision_reset", ctypes.c_int),
+        ("fifo_depth", ctypes.c_int),
+        ("uav_radius", ctypes.c_float),
+        ("bbox_lo", ctypes.c_float * 3),
+        ("bbox_hi", ctypes.c_float * 3),
+        ("target", ctypes.c_float * 3),
+        ("success_radius", ctypes.c_float),
+        ("n_gates", ctypes.c_int),
+        ("gates", (ctypes.c_float * 3) * 4),
+        ("gen_kind", ctypes.c_int),
+        ("gen_boxes", ctypes.c_int),
+        ("gen_mean", ((ctypes.c_float * 3) * 4) * GEN_MAX_BOXES),
+        ("gen_half", ((ctypes.c_float * 3) * 4) * GEN_MAX_BOXES),
+        ("init_motor_omega", ctypes.c_float),
+        ("seed", ctypes.c_ulonglong),
+    ]
