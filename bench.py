@@ -39,7 +39,7 @@ AGENTS = 65536
 DYN = dict(action_type="bodyrate", integrator="rk4", dt=0.0025, ctrl_dt=0.02, ctrl_delay=True, comm_delay=0.06)
 WORKLOAD = "HoverEnv 65536 agents/GPU visual=False RK4 dt=0.0025 ctrl_dt=0.02 bodyrate (BASELINE configs[1])"
 ALGO_BYTES_FWD = 176          # 96 B read (20 state + 4 action floats) + 80 B written per agent-step
-MOVED_BYTES_FWD = 176 + 52    # + the (n,13) observation the reference's step() returns
+MOVED_BYTES_FWD = 176 + 52 + 39   # + the (n,13) observation + reward/done/episode record/env status of the tail
 FLOP_PER_AGENT_STEP = 4100    # SURVEY.md §8(d) lean count, RK4 x 8 sub-steps
 FP32_PEAK_TFLOPS = 74.0       # 148 SM x 128 lanes x 2 x 1.965 GHz (nominal)
 L2_FLUSH_BYTES = 256 << 20
@@ -279,9 +279,17 @@ def run_ours(args):
     st_in = dynm.packed_state.detach().clone()
     st_out, obs_out = th.empty_like(st_in), th.empty((n, 13), device=dev)
 
+    # the kernel env.step launches: the fused env step (control step + wrapper tail) on a private copy of the
+    # per-agent env status, so that timing it does not disturb the env
+    fz = env._fused
+    sc, ret, eb = fz.sc.clone(), fz.ret.clone(), fz.eb.clone()
+    rew_o, done_o = th.empty(n, device=dev), th.empty(n, dtype=th.bool, device=dev)
+    rec_o = th.empty((n, 4), device=dev)
+
     def kernel_only(i):
-        _lib.step_fwd(cfg.params, cfg.substeps, cfg.integrator, cfg.action_type, cfg.flags, st_in, acts[i % pool],
-                      st_out, obs_out, None)
+        _lib.env_step_fwd(cfg.params, fz.spec, cfg.substeps, cfg.integrator, cfg.action_type, cfg.flags, 0, 10_000 + i,
+                          st_in, acts[i % pool], None, sc, ret, eb, None, None, st_out, obs_out, rew_o, done_o, rec_o,
+                          None)
 
     for i in range(5):
         kernel_only(i)
@@ -293,8 +301,8 @@ def run_ours(args):
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.isfile(tpath):
         with open(tpath) as f:
-            traffic = json.load(f).get("vf_step_fwd_kernel_bytes_per_launch")
-    roofline = {"bound": "hbm", "kernel": "vf_step_fwd_kernel<RK4,BODYRATE,LAG>", "achieved": achieved, "peak": peak,
+            traffic = json.load(f).get("vf_env_step_fwd_kernel_bytes_per_launch")
+    roofline = {"bound": "hbm", "kernel": "vf_env_step_fwd_kernel<RK4,BODYRATE,LAG>", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "kernel_us": k_avg * 1e6, "algorithmic_bytes_per_launch": ALGO_BYTES_FWD * n,
                 "bytes_moved_per_launch": MOVED_BYTES_FWD * n,

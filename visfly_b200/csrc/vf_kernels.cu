@@ -374,6 +374,17 @@ __global__ void vf_unpack_kernel(int n, const float* __restrict__ st, float* __r
 // ---------------------------------------------------------------------------------------------
 constexpr int kBlock = 64;   // 65 536 agents -> 1024 CTAs -> 6.9 per SM: <= 14 warps on the fullest SM
 
+// Tuning knob for experiments only (tools/run_kernels.py): VF_BLOCK=32|64|128|256 overrides the CTA size of the
+// forward kernels.  Unset in production.
+int block_override() {
+    static const int v = [] {
+        const char* e = std::getenv("VF_BLOCK");
+        const int b = e ? std::atoi(e) : 0;
+        return (b == 32 || b == 64 || b == 128 || b == 256) ? b : 0;
+    }();
+    return v;
+}
+
 bool aligned16(const void* p) { return (reinterpret_cast<size_t>(p) & 15u) == 0; }
 
 int check_common(const VfParams* params, int n, int substeps, int integrator, int action_type) {
@@ -390,6 +401,12 @@ int check_common(const VfParams* params, int n, int substeps, int integrator, in
 template <int INTEG, int ACT, bool LAG>
 void launch_fwd(const VfParams& p, int n, int substeps, const float* si, const float* a, float* so, float* obs,
                 float* ext, cudaStream_t st) {
+    switch (block_override()) {
+        case 32: vf_step_fwd_kernel<INTEG, ACT, LAG, 32><<<(n + 31) / 32, 32, 0, st>>>(p, n, substeps, si, a, so, obs, ext); return;
+        case 128: vf_step_fwd_kernel<INTEG, ACT, LAG, 128><<<(n + 127) / 128, 128, 0, st>>>(p, n, substeps, si, a, so, obs, ext); return;
+        case 256: vf_step_fwd_kernel<INTEG, ACT, LAG, 256><<<(n + 255) / 256, 256, 0, st>>>(p, n, substeps, si, a, so, obs, ext); return;
+        default: break;
+    }
     const int grid = (n + kBlock - 1) / kBlock;
     vf_step_fwd_kernel<INTEG, ACT, LAG, kBlock><<<grid, kBlock, 0, st>>>(p, n, substeps, si, a, so, obs, ext);
 }

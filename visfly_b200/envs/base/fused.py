@@ -9,6 +9,7 @@ are the built-in ones, the IMU noise model is zero, the state generator is one t
 """
 from __future__ import annotations
 
+import ctypes
 import os
 from collections.abc import Sequence
 from typing import Dict, Optional
@@ -132,10 +133,25 @@ class FusedEnvStep:
         self.active = False
         self.global_step = 0
         self.sc = self.ret = self.eb = self.gate = self.passed = None
+        self._key, self._ok = None, False
+        self._fn = _lib.load().vf_env_step_fwd
+        self._params_ref, self._spec_ref = ctypes.byref(dyn._cfg.params), ctypes.byref(s)
 
     # -- eligibility ------------------------------------------------------------------------------------
     def refresh(self) -> bool:
-        """Re-read the settings that may change between steps; False => the generic path must be used."""
+        """Re-read the settings that may change between steps; False => the generic path must be used.
+        The answer is cached on the identity of everything it depends on (this runs once per step)."""
+        env = self.env
+        envs = env.envs
+        key = (id(envs.stateGenerator), id(envs._reset_table), env.max_episode_steps, env.is_collision_reset,
+               "_generate_state" in envs.__dict__)
+        if key == self._key:
+            return self._ok
+        self._key = key
+        self._ok = self._refresh()
+        return self._ok
+
+    def _refresh(self) -> bool:
         env, s = self.env, self.spec
         if os.environ.get("VISFLY_B200_NO_FUSED_ENV") or not env.envs._imu_noise_free:
             return False
@@ -162,6 +178,11 @@ class FusedEnvStep:
             self.passed = env._past_targets_num.to(th.int32).clone()
         dyn.detach()
         env.envs._fused = self
+        for t, dt in ((self.sc, th.int32), (self.ret, th.float32), (self.eb, th.uint8)):
+            assert t.is_cuda and t.is_contiguous() and t.dtype == dt
+        self._p_sc, self._p_ret, self._p_eb = self.sc.data_ptr(), self.ret.data_ptr(), self.eb.data_ptr()
+        self._p_gate = None if self.gate is None else self.gate.data_ptr()
+        self._p_passed = None if self.passed is None else self.passed.data_ptr()
         self.active = True
 
     def leave(self):
@@ -195,7 +216,8 @@ class FusedEnvStep:
         if dyn._comm_delay_steps:
             dyn._pre_action.append(action)
             action = dyn._pre_action.pop(0)
-        action = action.contiguous()
+        if not action.is_contiguous():
+            action = action.contiguous()
         state_in = dyn._state
         state_out = th.empty_like(state_in)
         obs = th.empty((n, self.obs_width), dtype=th.float32, device=dev)
@@ -204,14 +226,23 @@ class FusedEnvStep:
         record = th.empty((n, 4), dtype=th.float32, device=dev)
         term = th.empty((n, self.obs_width), dtype=th.float32, device=dev) if env.keep_terminal_observation else None
         cfg = dyn._cfg
-        _lib.env_step_fwd(cfg.params, self.spec, cfg.substeps, cfg.integrator, cfg.action_type, cfg.flags, 0,
-                          self.global_step, state_in, action, self.table, self.sc, self.ret, self.eb, self.gate,
-                          self.passed, state_out, obs, reward, done, record, term)
+        # hot call: tensors created above / owned by this object are float32-contiguous-CUDA by construction, the
+        # action was normalised by the wrapper; the C side still validates NULLs and alignment
+        if th.cuda.current_device() != dev.index:
+            th.cuda.set_device(dev)
+        rc = self._fn(self._params_ref, self._spec_ref, n, cfg.substeps, cfg.integrator, cfg.action_type, cfg.flags,
+                      0, self.global_step, state_in.data_ptr(), action.data_ptr(),
+                      None if self.table is None else self.table.data_ptr(), self._p_sc, self._p_ret, self._p_eb,
+                      self._p_gate, self._p_passed, state_out.data_ptr(), obs.data_ptr(), reward.data_ptr(),
+                      done.data_ptr(), record.data_ptr(), None if term is None else term.data_ptr(),
+                      th.cuda.current_stream(dev).cuda_stream)
+        if rc != 0:
+            raise RuntimeError("visfly_b200: " + _lib.load().vf_last_error().decode())
         self.global_step += 1
         # keep the Dynamics object coherent (lazy views, diagnostics)
         dyn._prev = (state_in, action)
         dyn._state = state_out
-        dyn._obs = obs if self.obs_kind == P.OBS_STATE13 else None
+        dyn._obs_t = obs if self.obs_kind == P.OBS_STATE13 else None
         dyn._n_steps += 1
         dyn._ext, dyn._thrusts_given = None, None
         dyn._fresh = done
