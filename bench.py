@@ -221,6 +221,7 @@ def timed_steps(step_fn, steps, flush, stream):
 def run_ours(args):
     import torch.distributed as dist
     from visfly_b200 import _lib
+    from visfly_b200.distributed import gather_episode_returns
     from visfly_b200.envs import HoverEnv
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -246,32 +247,40 @@ def run_ours(args):
     env = HoverEnv(num_agent_per_scene=n, visual=False, device=dev, dynamics_kwargs=dict(DYN), seed=42 + rank,
                    max_episode_steps=256, tensor_output=True)
     env.reset()
-    returns = th.zeros(n, device=dev)
+    act_list = list(acts.unbind(0))
 
     def env_step(i):
-        obs, reward, done, info = env.step(acts[i % pool])
-        returns.add_(reward)
+        env.step(act_list[i % pool])
 
     for i in range(W):
         env_step(i)
     barrier()
     with ClockSampler(local) as clk:
+        # (A) cold L2: one CUDA-event pair per step, 256 MiB flush before every timed step
         per_step = timed_steps(env_step, K, flush, stream)
-        if world > 1:     # the one collective of the path: episode returns of all shards, once per rollout
-            gathered = [th.empty_like(returns) for _ in range(world)]
-            dist.all_gather(gathered, returns)
         barrier()
-        # hot-L2 wall clock of the same loop (no flush, no per-step events): cross-check for the driver's clock
+        # (B) hot L2, the contract's bracket: barrier + synchronize, K steps back to back, events at both ends;
+        #     includes every host-side microsecond between launches and the rollout's one collective
+        e0, e1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
+        e0.record(stream)
         for i in range(K):
             env_step(i)
-        th.cuda.synchronize()
+        # the one collective of the path: episode returns of all shards, once per rollout (no-op at world 1)
+        all_returns = gather_episode_returns(env._rewards)
+        e1.record(stream)
+        barrier()
         wall_hot = time.perf_counter() - t0
-    total_ms = th.tensor([sum(per_step)], device=dev, dtype=th.float64)
+        dev_hot_ms = e0.elapsed_time(e1)
+    tot = th.tensor([sum(per_step), max(dev_hot_ms, wall_hot * 1e3)], device=dev, dtype=th.float64)
     if world > 1:
-        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
-    total_ms = float(total_ms)
-    value = world * n * K / (total_ms * 1e-3)
+        dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+    cold_ms, hot_ms = float(tot[0]), float(tot[1])
+    cold_value = world * n * K / (cold_ms * 1e-3)
+    hot_value = world * n * K / (hot_ms * 1e-3)
+    # the reported value is the LOWER of the two: device-timed with a cold L2, or end-to-end bracketed with the
+    # (realistic, 12 MB working set) hot L2 but including all host overhead between steps
+    value, total_ms = (cold_value, cold_ms) if cold_value <= hot_value else (hot_value, hot_ms)
 
     # ---- roofline: the fused control-step kernel alone, cold L2 -----------------------------------------
     dynm = env.envs.dynamics
@@ -348,11 +357,12 @@ def run_ours(args):
             "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "agents_per_gpu": n, "substeps": 8, "actions": "smooth-hover law",
-                       "l2": "flushed before every timed step (256 MiB write); one CUDA-event pair per step",
+                       "l2": "value = min(cold: 256 MiB L2 flush before every timed step, one CUDA-event pair per step; "
+                             "hot: K steps back to back inside barrier+synchronize, host overhead included)",
                        "parallelism": f"agents sharded over {world} GPU(s), one all_gather of episode returns per rollout"},
             "clocks": clk.summary(), "e2e": e2e, "gpu_launches": K * env_launches_per_step(env),
             "roofline": roofline, "cpu_baseline": cpu,
-            "hot_l2_wall_value": world * n * K / wall_hot, "kernel_only_value": n / k_avg,
+            "cold_l2_device_value": cold_value, "hot_l2_bracketed_value": hot_value, "kernel_only_value": n / k_avg,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -1,0 +1,58 @@
+"""Host-side logic of the multi-GPU path on world_size-2 gloo (CPU tensors): sharding covers the agent range,
+the one collective of the path (all-gather of episode returns) works for equal and ragged shards."""
+import os
+import socket
+
+import pytest
+import torch as th
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from visfly_b200.distributed import gather_episode_returns, rollout_stats, shard_range, shard_seed
+
+
+def test_shard_range_partitions_exactly():
+    for n, world in [(65536, 8), (524288, 8), (10, 3), (7, 8), (1, 2), (0, 4)]:
+        spans = [shard_range(n, r, world) for r in range(world)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        sizes = [b - a for a, b in spans]
+        assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        shard_range(10, 3, 3)
+    assert len({shard_seed(42, r) for r in range(8)}) == 8
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, n_total, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        lo, hi = shard_range(n_total, rank, world)
+        local = th.arange(lo, hi, dtype=th.float32) * 0.5          # "episode return" of agent i is i/2
+        full = gather_episode_returns(local)
+        ok = th.equal(full, th.arange(n_total, dtype=th.float32) * 0.5)
+        mean_r, mean_l, cnt = rollout_stats(local.sum(), th.tensor(float(hi - lo) * 10), th.tensor(float(hi - lo)))
+        ok = ok and cnt == n_total and abs(mean_l - 10.0) < 1e-9 and abs(mean_r - 0.5 * (n_total - 1) / 2) < 1e-6
+        out[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_total", [64, 9])
+def test_gather_episode_returns_world2_gloo(n_total):
+    world = 2
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_worker, args=(world, _free_port(), n_total, out), nprocs=world, join=True)
+        assert dict(out) == {0: True, 1: True}
+
+
+def test_single_process_is_identity():
+    x = th.arange(5.0)
+    assert gather_episode_returns(x) is x

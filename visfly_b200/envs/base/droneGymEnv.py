@@ -214,6 +214,9 @@ class DroneGymEnvsBase(VecEnv):
         info = RecordInfo(self.num_agent, record, term_obs, self.envs.dynamics.ctrl_dt,
                           racing=self._fused.gate is not None)
         self._info = info
+        if self.tensor_output:                   # kernel outputs never carry autograd history: nothing to detach
+            self._observations = self._obs_tensors
+            return self._obs_tensors, reward, done, info
         return self._format_step_output(reward, done, info)
 
     def _snapshot_info(self) -> LazyInfo:

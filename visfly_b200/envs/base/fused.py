@@ -22,6 +22,10 @@ from ... import params as P
 from ...randomization import NormalStateRandomizer, UniformStateRandomizer, UnionRandomizer
 
 
+_raw_stream = getattr(th._C, "_cuda_getCurrentRawStream", None) or \
+    (lambda index: th.cuda.current_stream(index).cuda_stream)
+
+
 def generator_spec(gen, spec: P.VfEnvSpec) -> bool:
     """Fill the reset-sampler part of ``spec`` from a state generator; False if the kernel cannot express it."""
     boxes = gen.randomizers if isinstance(gen, UnionRandomizer) else [gen]
@@ -235,7 +239,7 @@ class FusedEnvStep:
                       None if self.table is None else self.table.data_ptr(), self._p_sc, self._p_ret, self._p_eb,
                       self._p_gate, self._p_passed, state_out.data_ptr(), obs.data_ptr(), reward.data_ptr(),
                       done.data_ptr(), record.data_ptr(), None if term is None else term.data_ptr(),
-                      th.cuda.current_stream(dev).cuda_stream)
+                      _raw_stream(dev.index))
         if rc != 0:
             raise RuntimeError("visfly_b200: " + _lib.load().vf_last_error().decode())
         self.global_step += 1
