@@ -116,6 +116,15 @@ def test_output_modes_spaces_and_deepcopy():
     o1 = nav.step(a)[0]["state"]
     o2 = twin.step(a)[0]["state"]
     assert th.equal(o1, o2)
+    hov = HoverEnv(num_agent_per_scene=n, visual=False, dynamics_kwargs=dyn, tensor_output=True, max_episode_steps=6)
+    hov.reset()
+    for _ in range(3):
+        hov.step(a)
+    assert hov._fused.active
+    twin2 = copy.deepcopy(hov)                      # mid-run copy while the one-kernel path owns the env status
+    for _ in range(5):                              # crosses an auto-reset: same seed + same step index => same draws
+        r1, r2 = hov.step(a), twin2.step(a)
+        assert th.equal(r1[0]["state"], r2[0]["state"]) and th.equal(r1[1], r2[1]) and th.equal(r1[2], r2[2])
     nav.requires_grad = False                        # settable (reference PPO.py:80-82)
     nav.tensor_output = True
     assert not nav.step(a)[1].requires_grad

@@ -138,8 +138,30 @@ class FusedEnvStep:
         self.global_step = 0
         self.sc = self.ret = self.eb = self.gate = self.passed = None
         self._key, self._ok = None, False
+        self._fn = None
+        self._bind()
+
+    _CTYPES_REFS = ("_fn", "_params_ref", "_spec_ref")
+
+    def __deepcopy__(self, memo):
+        """ctypes references are per-object handles: the copy re-creates them against its own env / spec."""
+        import copy
+        twin = self.__class__.__new__(self.__class__)
+        memo[id(self)] = twin
+        for k, v in self.__dict__.items():
+            if k not in self._CTYPES_REFS:
+                setattr(twin, k, copy.deepcopy(v, memo))
+        twin._fn = None            # re-bound on first use (the twin env may not be fully copied yet)
+        return twin
+
+    def _bind(self):
         self._fn = _lib.load().vf_env_step_fwd
-        self._params_ref, self._spec_ref = ctypes.byref(dyn._cfg.params), ctypes.byref(s)
+        self._params_ref = ctypes.byref(self.env.envs.dynamics._cfg.params)
+        self._spec_ref = ctypes.byref(self.spec)
+        if self.active:
+            self._p_sc, self._p_ret, self._p_eb = self.sc.data_ptr(), self.ret.data_ptr(), self.eb.data_ptr()
+            self._p_gate = None if self.gate is None else self.gate.data_ptr()
+            self._p_passed = None if self.passed is None else self.passed.data_ptr()
 
     # -- eligibility ------------------------------------------------------------------------------------
     def refresh(self) -> bool:
@@ -215,6 +237,8 @@ class FusedEnvStep:
     # -- the step -------------------------------------------------------------------------------------------
     def step(self, action: th.Tensor):
         env, dyn, n, dev = self.env, self.env.envs.dynamics, self.n, self.device
+        if self._fn is None:
+            self._bind()
         if not self.active:
             self.enter()
         if dyn._comm_delay_steps:
