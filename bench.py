@@ -298,7 +298,7 @@ def run_ours(args):
     def kernel_only(i):
         _lib.env_step_fwd(cfg.params, fz.spec, cfg.substeps, cfg.integrator, cfg.action_type, cfg.flags, 0, 10_000 + i,
                           st_in, acts[i % pool], None, sc, ret, eb, None, None, st_out, obs_out, rew_o, done_o, rec_o,
-                          None)
+                          None, None)
 
     for i in range(5):
         kernel_only(i)

@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define VF_ABI_VERSION 3
+#define VF_ABI_VERSION 4
 
 /* integrator: reference `integrator=` kwarg, utils/maths.py:331 (euler) and :353 (rk4, repaired R1-R3) */
 #define VF_INTEGRATOR_EULER 0
@@ -220,13 +220,29 @@ int vf_env_spec_size(void);
  *   reward_out  float[n], done_out uint8[n]
  *   record_out  float[n][4]   [episode return, episode length, VF_RBIT_* as float, gates passed] of this step
  *   term_obs_out float[n][13|16] or NULL: observation BEFORE the reset, written only for finished agents
+ *   saved_out   int32[n][2] or NULL: [step_count, gate] at the START of the step — what vf_env_step_bwd needs
  */
 int vf_env_step_fwd(const VfParams* params, const VfEnvSpec* spec, int n, int substeps, int integrator,
                     int action_type, unsigned flags, unsigned env_flags, unsigned long long step_index,
                     const float* state_in, const float* action, const float* reset_table,
                     int* step_count, float* returns, unsigned char* ebits, int* gate, int* gates_passed,
                     float* state_out, float* obs_out, float* reward_out, unsigned char* done_out,
-                    float* record_out, float* term_obs_out, void* stream);
+                    float* record_out, float* term_obs_out, int* saved_out, void* stream);
+
+/*
+ * Reverse mode of vf_env_step_fwd with respect to (state_in, action), given the gradients of its differentiable
+ * outputs: the packed state, the returned observation and the reward.  Re-runs the step from its inputs (nothing
+ * else was stored), folds in the adjoint of the task reward (torch.autograd conventions, see csrc/vf_env.cuh) and of
+ * the observation layout, then the adjoint of the control step.  An agent that finished in this step was
+ * re-initialised inside it: its returned state/observation are constants, only its reward carries gradient — the
+ * same graph the reference builds by overwriting rows in place (dynamics.py:249-263).
+ *   saved        int32[n][2]  from vf_env_step_fwd        grad_state_out [5][n][4] or NULL
+ *   grad_obs     float[n][13|16] or NULL                   grad_reward    float[n] or NULL
+ */
+int vf_env_step_bwd(const VfParams* params, const VfEnvSpec* spec, int n, int substeps, int integrator,
+                    int action_type, unsigned flags, unsigned env_flags, const float* state_in,
+                    const float* action, const int* saved, const float* grad_state_out, const float* grad_obs,
+                    const float* grad_reward, float* grad_state_in, float* grad_action, void* stream);
 
 #ifdef __cplusplus
 }

@@ -10,6 +10,7 @@
 #include <cstddef>
 #include <vector>
 
+#include "../visfly_b200/csrc/vf_env.cuh"
 #include "../visfly_b200/csrc/vf_math.cuh"
 
 namespace {
@@ -93,9 +94,78 @@ int bwd(const VfParams* params, int n, int substeps, int integrator, int action_
     return 0;
 }
 
+// One fused env step WITHOUT the reset (reward / flags of the step + the pre-reset state), and its adjoint.
+template <class T>
+void env_fwd(const VfParams* params, const VfEnvSpec* E, int n, int substeps, int integrator, int action_type,
+             unsigned flags, const T* state_in, const T* action, const int* saved, T* state_out, T* reward,
+             int* done, int* gate_out) {
+    const vf::Params<T> P(*params);
+    const bool lag = flags & VF_FLAG_CTRL_DELAY;
+    for (int i = 0; i < n; ++i) {
+        vf::State<T> s;
+        load_state(state_in, n, i, s);
+        T a[4];
+        for (int j = 0; j < 4; ++j) a[j] = saved[2 * i] < E->fifo_depth ? T(0) : action[size_t(i) * 4 + j];
+        vf::Wrench<T> k;
+        vf::step_fwd<T>(P, substeps, integrator, action_type, lag, a, s, k);
+        vf::EnvEval<T> ev;
+        vf::env_eval<T>(P, *E, s, saved[2 * i] + 1, saved[2 * i + 1], false, ev);
+        store_state(state_out, n, i, s);
+        reward[i] = ev.reward;
+        done[i] = ev.done ? 1 : 0;
+        gate_out[i] = ev.gate;
+    }
+}
+
+template <class T>
+void env_bwd(const VfParams* params, const VfEnvSpec* E, int n, int substeps, int integrator, int action_type,
+             unsigned flags, unsigned env_flags, const T* state_in, const T* action, const int* saved,
+             const T* g_state_out, const T* g_obs, const T* g_reward, T* g_state_in, T* g_action) {
+    const vf::Params<T> P(*params);
+    const bool lag = flags & VF_FLAG_CTRL_DELAY;
+    const int width = E->obs_kind == VF_OBS_STATE13 ? 13 : 16;
+    std::vector<vf::Tape<T>> tape(substeps);
+    for (int i = 0; i < n; ++i) {
+        vf::State<T> s0, g;
+        load_state(state_in, n, i, s0);
+        if (g_state_out) {
+            load_state(g_state_out, n, i, g);
+        } else {
+            for (int j = 0; j < 3; ++j) g.p[j] = g.v[j] = g.w[j] = g.al[j] = T(0);
+            for (int j = 0; j < 4; ++j) g.q[j] = g.mot[j] = T(0);
+        }
+        const bool masked = saved[2 * i] < E->fifo_depth;
+        T a[4], ga[4];
+        for (int j = 0; j < 4; ++j) a[j] = masked ? T(0) : action[size_t(i) * 4 + j];
+        vf::env_step_bwd_agent<T>(P, *E, substeps, integrator, action_type, lag,
+                                  (env_flags & VF_ENV_FLAG_NO_RESET) != 0, a, s0, saved[2 * i], saved[2 * i + 1],
+                                  g_obs ? g_obs + size_t(i) * width : nullptr, g_reward ? g_reward[i] : T(0), g, ga,
+                                  tape.data());
+        store_state(g_state_in, n, i, g);
+        for (int j = 0; j < 4; ++j) g_action[size_t(i) * 4 + j] = masked ? T(0) : ga[j];
+    }
+}
+
 }  // namespace
 
 extern "C" {
+
+void vfm_env_fwd_f64(const VfParams* p, const VfEnvSpec* e, int n, int s, int integ, int at, unsigned fl,
+                     const double* si, const double* a, const int* saved, double* so, double* rew, int* done,
+                     int* gate) {
+    env_fwd<double>(p, e, n, s, integ, at, fl, si, a, saved, so, rew, done, gate);
+}
+void vfm_env_bwd_f64(const VfParams* p, const VfEnvSpec* e, int n, int s, int integ, int at, unsigned fl, unsigned efl,
+                     const double* si, const double* a, const int* saved, const double* gso, const double* gobs,
+                     const double* gr, double* gsi, double* ga) {
+    env_bwd<double>(p, e, n, s, integ, at, fl, efl, si, a, saved, gso, gobs, gr, gsi, ga);
+}
+void vfm_env_bwd_f32(const VfParams* p, const VfEnvSpec* e, int n, int s, int integ, int at, unsigned fl, unsigned efl,
+                     const float* si, const float* a, const int* saved, const float* gso, const float* gobs,
+                     const float* gr, float* gsi, float* ga) {
+    env_bwd<float>(p, e, n, s, integ, at, fl, efl, si, a, saved, gso, gobs, gr, gsi, ga);
+}
+
 
 void vfm_step_fwd_f32(const VfParams* p, int n, int s, int integ, int at, unsigned fl, const float* si,
                       const float* a, float* so, float* obs, float* ext) {

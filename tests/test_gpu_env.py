@@ -73,11 +73,13 @@ def test_env_replays_reference_golden(task, integ, path):
 
 
 @pytest.mark.parametrize("integ", ["euler", "rk4"])
-def test_env_rollout_gradients_match_reference_autograd(integ):
+@pytest.mark.parametrize("path", ["generic", "fused"])
+def test_env_rollout_gradients_match_reference_autograd(integ, path):
+    """generic: autograd through tensor-op rewards + ControlStep; fused: EnvControlStep (vf_env_step_bwd)."""
     z = np.load(os.path.join(GOLD, "envgrad_navigation.npz"))
     acts = th.from_numpy(z["actions"]).cuda().requires_grad_(True)
     H, n = acts.shape[:2]
-    env = make_env("navigation", n, integ, int(z["max_episode_steps"]), table_of(z), requires_grad=True)
+    env = make_env("navigation", n, integ, int(z["max_episode_steps"]), table_of(z), path=path, requires_grad=True)
     env.reset()
     loss = 0.0
     for t in range(H):
@@ -87,6 +89,7 @@ def test_env_rollout_gradients_match_reference_autograd(integ):
     g, = th.autograd.grad(loss, acts)
     assert abs(loss.item() - float(z[f"loss_{integ}"])) < 1e-5
     assert rel_l2(g.cpu(), z[f"grad_actions_{integ}"]) < 1e-4
+    assert env._fused.active == (path == "fused")
     env.detach()
     assert not env.envs.dynamics.packed_state.requires_grad
 
@@ -167,7 +170,7 @@ def test_fused_and_generic_paths_agree_and_hand_over_mid_run():
     def run(env, fused_at):
         outs = []
         for t in range(T):
-            env.requires_grad = not fused_at(t)
+            env.use_fused_step = fused_at(t)
             obs, r, d, info = env.step(acts[t])
             assert env._fused.active == fused_at(t)
             outs.append((obs["state"].detach().clone(), r.detach().clone(), d.clone(),
@@ -219,3 +222,29 @@ def test_fused_path_samples_resets_on_device():
     assert bool((dist.amin(dim=1) <= 0.2 + 1e-6).all())
     which = dist.argmin(dim=1)
     assert all(abs(float((which == k).float().mean()) - 0.25) < 0.03 for k in range(4))
+
+
+@pytest.mark.parametrize("task", TASKS)
+def test_fused_env_gradients_match_generic_autograd(task):
+    """APG-style rollout (H=12, auto-resets inside the horizon) through all three tasks: gradients of the discounted
+    return w.r.t. every action and the initial state, fused adjoint kernel vs autograd through the generic path."""
+    z = load_env_golden(task, "rk4")
+    acts0 = th.from_numpy(z["actions"])[:12].cuda()
+    n = acts0.shape[1]
+    res = {}
+    for fused in (True, False):
+        env = make_env(task, n, "rk4", 7, table_of(z), path="fused", requires_grad=True)
+        env.use_fused_step = fused
+        env.reset()
+        s0 = env.envs.dynamics._state.detach().clone().requires_grad_(True)
+        env.envs.dynamics._state = s0
+        acts = acts0.clone().requires_grad_(True)
+        loss = 0.0
+        for t in range(acts.shape[0]):
+            obs, r, d, info = env.step(acts[t])
+            loss = loss - (0.99 ** t) * r.mean() + 1e-3 * obs["state"].pow(2).mean()
+        assert env._fused.active == fused
+        res[fused] = th.autograd.grad(loss, [acts, s0]) + (loss.detach(),)
+    assert abs(float(res[True][2] - res[False][2])) < 1e-5
+    assert rel_l2(res[True][0].cpu(), res[False][0].cpu()) < 1e-4
+    assert rel_l2(res[True][1].cpu(), res[False][1].cpu()) < 1e-4

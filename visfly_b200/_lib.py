@@ -15,7 +15,7 @@ from .params import VfEnvSpec, VfParams
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvisfly_b200.so")
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 INTEGRATOR_ID = {"euler": 0, "rk4": 1}
 FLAG_CTRL_DELAY = 1
@@ -39,7 +39,9 @@ SIGNATURES = {
     "vf_unpack_state": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "vf_env_spec_size": (_i, []),
     "vf_env_step_fwd": (_i, [_P(VfParams), _P(VfEnvSpec), _i, _i, _i, _i, _u, _u, ctypes.c_ulonglong,
-                             _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+                             _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "vf_env_step_bwd": (_i, [_P(VfParams), _P(VfEnvSpec), _i, _i, _i, _i, _u, _u,
+                             _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
 }
 
 _lib: Optional[ctypes.CDLL] = None
@@ -175,7 +177,7 @@ def env_step_fwd(params: VfParams, spec: VfEnvSpec, substeps: int, integrator: i
                  reset_table: Optional[th.Tensor], step_count: th.Tensor, returns: th.Tensor, ebits: th.Tensor,
                  gate: Optional[th.Tensor], gates_passed: Optional[th.Tensor], state_out: th.Tensor,
                  obs_out: th.Tensor, reward_out: th.Tensor, done_out: th.Tensor, record_out: th.Tensor,
-                 term_obs_out: Optional[th.Tensor]) -> None:
+                 term_obs_out: Optional[th.Tensor], saved_out: Optional[th.Tensor] = None) -> None:
     """Binding of ``vf_env_step_fwd`` (fused control step + env wrapper tail, one launch)."""
     lib = load(require_cuda=True)
     n = state_in.shape[1]
@@ -188,4 +190,20 @@ def env_step_fwd(params: VfParams, spec: VfEnvSpec, substeps: int, integrator: i
             _any_ptr(gates_passed, "gates_passed", th.int32), _dev_ptr(state_out, "state_out"),
             _dev_ptr(obs_out, "obs_out"), _dev_ptr(reward_out, "reward_out"),
             _any_ptr(done_out, "done_out", th.bool), _dev_ptr(record_out, "record_out"),
-            _dev_ptr(term_obs_out, "term_obs_out"), _stream(state_in.device)))
+            _dev_ptr(term_obs_out, "term_obs_out"), _any_ptr(saved_out, "saved_out", th.int32),
+            _stream(state_in.device)))
+
+
+def env_step_bwd(params: VfParams, spec: VfEnvSpec, substeps: int, integrator: int, action_type: int, flags: int,
+                 env_flags: int, state_in: th.Tensor, action: th.Tensor, saved: th.Tensor,
+                 g_state_out: Optional[th.Tensor], g_obs: Optional[th.Tensor], g_reward: Optional[th.Tensor],
+                 g_state_in: th.Tensor, g_action: th.Tensor) -> None:
+    """Binding of ``vf_env_step_bwd`` (adjoint of the fused env step, one launch)."""
+    lib = load(require_cuda=True)
+    n = state_in.shape[1]
+    with th.cuda.device(state_in.device):
+        _check(lib.vf_env_step_bwd(
+            ctypes.byref(params), ctypes.byref(spec), n, substeps, integrator, action_type, flags, env_flags,
+            _dev_ptr(state_in, "state_in"), _dev_ptr(action, "action"), _any_ptr(saved, "saved", th.int32),
+            _dev_ptr(g_state_out, "grad_state_out"), _dev_ptr(g_obs, "grad_obs"), _dev_ptr(g_reward, "grad_reward"),
+            _dev_ptr(g_state_in, "grad_state_in"), _dev_ptr(g_action, "grad_action"), _stream(state_in.device)))

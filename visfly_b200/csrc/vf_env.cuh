@@ -104,6 +104,201 @@ VF_HD T reward_navigation(const T p[3], const T q[4], const T v[3], const T w[3]
     return T(0.1) * T(0) + approach * T(0.01) + ang * T(-0.01) + stable + near + prox * closing * T(-0.005) + bonus;
 }
 
+// ---- adjoints of the rewards (torch.autograd conventions: ||x|| has gradient 0 at x = 0, clamp / clamp_max /
+// clamp_min pass the gradient on the closed side, relu'(0) = 0).  One deliberate deviation: where
+// the reference's heading term would produce acos'(+-1) = -inf times a zero mask (NaN), the gradient is 0 here. ----
+template <class T>
+VF_HD void reward_hover_adj(const T p[3], const T q[4], const T v[3], const T w[3], const T tgt[3], T gr,
+                            T gp[3], T gq[4], T gv[3], T gw[3]) {
+    const T dx = p[0] - tgt[0], dy = p[1] - tgt[1], dz = p[2] - tgt[2];
+    const T d = norm3(dx, dy, dz);
+    if (d > T(0)) {
+        const T k = gr * T(-0.1 * 1 / 9) / d;
+        gp[0] += k * dx; gp[1] += k * dy; gp[2] += k * dz;
+    }
+    const T qe = vsqrt((q[0] - T(1)) * (q[0] - T(1)) + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+    if (qe > T(0)) {
+        const T k = gr * T(-0.00001) / qe;
+        gq[0] += k * (q[0] - T(1)); gq[1] += k * q[1]; gq[2] += k * q[2]; gq[3] += k * q[3];
+    }
+    const T vn = norm3(v[0], v[1], v[2]);
+    if (vn > T(0)) {
+        const T k = gr * T(-0.002) / vn;
+        gv[0] += k * v[0]; gv[1] += k * v[1]; gv[2] += k * v[2];
+    }
+    const T wn = norm3(w[0], w[1], w[2]);
+    if (wn > T(0)) {
+        const T k = gr * T(-0.002) / wn;
+        gw[0] += k * w[0]; gw[1] += k * w[1]; gw[2] += k * w[2];
+    }
+}
+
+template <class T>
+VF_HD void reward_navigation_adj(const T p[3], const T q[4], const T v[3], const T w[3], const T tgt[3],
+                                 const BoxHit<T>& hit, bool success, int max_steps, int step_count, T gr,
+                                 T gp[3], T gq[4], T gv[3], T gw[3]) {
+    const T t[3] = {tgt[0] - p[0], tgt[1] - p[1], tgt[2] - p[2]};
+    const T tn = norm3(t[0], t[1], t[2]);
+    const T vn = norm3(v[0], v[1], v[2]);
+    // approach speed
+    {
+        const T den = T(1e-6) + tn, dot = v[0] * t[0] + v[1] * t[1] + v[2] * t[2];
+        if (dot / den <= T(10)) {
+            const T g = gr * T(0.01);
+            for (int i = 0; i < 3; ++i) {
+                gv[i] += g * t[i] / den;
+                T gt = g * v[i] / den;
+                if (tn > T(0)) gt -= g * dot / (den * den) * t[i] / tn;
+                gp[i] -= gt;
+            }
+        }
+    }
+    // heading alignment
+    {
+        const T d[3] = {T(1) - T(2) * (q[2] * q[2] + q[3] * q[3]), T(2) * (q[1] * q[2] + q[3] * q[0]),
+                        T(2) * (q[1] * q[3] - q[2] * q[0])};
+        const T thrd = T(3.14159265358979323846 / 18);
+        const T denv = T(1e-6) + vn, dv = d[0] * v[0] + d[1] * v[1] + d[2] * v[2];
+        const T c0 = dv / denv;
+        const T c = vclamp(c0, T(-1), T(1));
+        const T ang0 = vacos(c);
+        if (ang0 >= thrd && c0 >= T(-1) && c0 <= T(1) && c > T(-1) && c < T(1)) {
+            const T gc0 = gr * T(-0.01) * (T(-1) / vsqrt(T(1) - c * c));
+            T gd[3];
+            for (int i = 0; i < 3; ++i) {
+                gd[i] = gc0 * v[i] / denv;
+                T g = gc0 * d[i] / denv;
+                if (vn > T(0)) g -= gc0 * dv / (denv * denv) * v[i] / vn;
+                gv[i] += g;
+            }
+            // d = (1-2(y^2+z^2), 2(xy+zw), 2(xz-yw)) with q = (w,x,y,z)
+            gq[0] += gd[1] * T(2) * q[3] - gd[2] * T(2) * q[2];
+            gq[1] += gd[1] * T(2) * q[2] + gd[2] * T(2) * q[3];
+            gq[2] += -gd[0] * T(4) * q[2] + gd[1] * T(2) * q[1] - gd[2] * T(2) * q[0];
+            gq[3] += -gd[0] * T(4) * q[3] + gd[1] * T(2) * q[0] + gd[2] * T(2) * q[1];
+        }
+    }
+    // stability terms
+    {
+        const T qe = vsqrt((q[0] - T(1)) * (q[0] - T(1)) + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+        if (qe > T(0)) {
+            const T k = gr * T(-0.00001) / qe;
+            gq[0] += k * (q[0] - T(1)); gq[1] += k * q[1]; gq[2] += k * q[2]; gq[3] += k * q[3];
+        }
+        if (vn > T(0)) { const T k = gr * T(-0.002) / vn; for (int i = 0; i < 3; ++i) gv[i] += k * v[i]; }
+        const T wn = norm3(w[0], w[1], w[2]);
+        if (wn > T(0)) { const T k = gr * T(-0.002) / wn; for (int i = 0; i < 3; ++i) gw[i] += k * w[i]; }
+    }
+    // obstacle proximity and closing speed.  collision_vector = point.detach() - p: value (0,..,delta,..,0) but
+    // d(vector_j)/dp_j = -1 for every j (droneEnv.py:351-365)
+    {
+        const int ax = hit.axis;
+        const T dis = hit.dis, delta = hit.delta;
+        T g_dis = gr * T(0.01) / ((dis + T(0.2)) * (dis + T(0.2)));
+        const T den = T(1e-6) + dis;
+        const T num = delta * v[ax];
+        const T cl0 = num / den;
+        const T A = T(1) - dis > T(0) ? T(1) - dis : T(0);
+        const T Bc = cl0 > T(0) ? cl0 : T(0);
+        if (T(1) - dis > T(0)) g_dis -= gr * T(-0.005) * Bc;
+        if (cl0 > T(0)) {
+            const T g_cl0 = gr * T(-0.005) * A;
+            for (int j = 0; j < 3; ++j) gp[j] -= g_cl0 * v[j] / den;      // d num / d p_j = -v_j
+            gv[ax] += g_cl0 * delta / den;                               // d num / d v_ax = delta
+            g_dis -= g_cl0 * num / (den * den);
+        }
+        if (dis > T(0)) gp[ax] -= g_dis * delta / dis;                   // dis = |delta|, d delta / d p_ax = -1
+    }
+    // success bonus
+    if (success && vn > T(0)) {
+        const T k = gr * T(max_steps - step_count) * T(0.1) * (T(-0.8) / ((T(1) + vn) * (T(1) + vn))) / vn;
+        for (int i = 0; i < 3; ++i) gv[i] += k * v[i];
+    }
+}
+
+// ---- everything the wrapper decides from the state after the control step (shared by forward, backward, mirror) ----
+template <class T> struct EnvEval {
+    T vel[3];            // reported velocity = v + wind
+    BoxHit<T> hit;
+    bool is_col, success, pass, ep_done, done;
+    int gate;            // next gate index after this step's gate test (racing)
+    T reward;
+};
+
+template <class T>
+VF_HD void env_eval(const Params<T>& P, const VfEnvSpec& E, const State<T>& s, int sc, int gate_in, bool ep_done_in,
+                    EnvEval<T>& ev) {
+    for (int j = 0; j < 3; ++j) ev.vel[j] = s.v[j] + P.wind[j];
+    ev.hit = box_hit<T>(s.p, E.bbox_lo, E.bbox_hi);
+    ev.is_col = ev.hit.dis < T(E.uav_radius);
+    ev.success = false;
+    ev.pass = false;
+    ev.gate = gate_in;
+    T tgt[3];
+    if (E.task == VF_TASK_HOVER) {
+        for (int j = 0; j < 3; ++j) tgt[j] = T(E.target[j]);
+        ev.reward = reward_hover<T>(s.p, s.q, ev.vel, s.w, tgt);
+    } else if (E.task == VF_TASK_NAVIGATION) {
+        for (int j = 0; j < 3; ++j) tgt[j] = T(E.target[j]);
+        ev.success = norm3(s.p[0] - tgt[0], s.p[1] - tgt[1], s.p[2] - tgt[2]) <= T(E.success_radius);
+        ev.reward = reward_navigation<T>(s.p, s.q, ev.vel, s.w, tgt, ev.hit, ev.success, E.max_episode_steps, sc);
+    } else {
+        for (int j = 0; j < 3; ++j) tgt[j] = T(E.gates[gate_in][j]);
+        ev.pass = norm3(s.p[0] - tgt[0], s.p[1] - tgt[1], s.p[2] - tgt[2]) <= T(E.success_radius);
+        ev.gate = (gate_in + (ev.pass ? 1 : 0)) % E.n_gates;
+        for (int j = 0; j < 3; ++j) tgt[j] = T(E.gates[ev.gate][j]);
+        ev.reward = reward_hover<T>(s.p, s.q, ev.vel, s.w, tgt) + (ev.pass ? T(20) : T(0));
+    }
+    ev.ep_done = ep_done_in || ev.success || ev.hit.out || (E.collision_reset && ev.is_col);
+    ev.done = ev.ep_done || sc >= E.max_episode_steps;
+}
+
+// Reverse mode of one fused env step for one agent.
+//   a        : delayed action as the forward saw it (already zeroed when the agent was younger than the FIFO)
+//   age_in, gate_in : step count / gate index at the start of the step
+//   g        : in = dL/d(packed state returned by the step), out = dL/d(s0)
+//   gobs     : dL/d(observation returned by the step) (13 or 16 wide);  gr : dL/d(reward)
+// A finished agent was re-initialised inside the step: its returned state / observation are constants, only the
+// reward (computed before the reset) carries gradient (reference: in-place overwrite, dynamics.py:249-263).
+template <class T>
+VF_HD void env_step_bwd_agent(const Params<T>& P, const VfEnvSpec& E, int substeps, int integrator, int action_type,
+                              bool ctrl_delay, bool no_reset, const T a[4], const State<T>& s0, int age_in,
+                              int gate_in, const T* gobs, T gr, State<T>& g, T ga[4], Tape<T>* tape) {
+    Command<T> c;
+    State<T> s_raw;
+    step_fwd_taped(P, substeps, integrator, action_type, ctrl_delay, a, s0, c, s_raw, tape);
+    State<T> s = s_raw;
+    clamp_state(P, s);
+    EnvEval<T> ev;
+    env_eval(P, E, s, age_in + 1, gate_in, false, ev);
+    if (ev.done && !no_reset) {
+        for (int j = 0; j < 3; ++j) g.p[j] = g.v[j] = g.w[j] = g.al[j] = T(0);
+        for (int j = 0; j < 4; ++j) g.q[j] = g.mot[j] = T(0);
+    } else if (gobs) {
+        if (E.obs_kind == VF_OBS_STATE13) {
+            for (int j = 0; j < 3; ++j) { g.p[j] += gobs[j]; g.v[j] += gobs[7 + j]; g.w[j] += gobs[10 + j]; }
+            for (int j = 0; j < 4; ++j) g.q[j] += gobs[3 + j];
+        } else {
+            for (int j = 0; j < 3; ++j) {
+                g.p[j] -= (gobs[j] + gobs[3 + j]) / T(10);
+                g.v[j] += gobs[10 + j] / T(10);
+                g.w[j] += gobs[13 + j] / T(10);
+            }
+            for (int j = 0; j < 4; ++j) g.q[j] += gobs[6 + j];
+        }
+    }
+    T tgt[3];
+    if (E.task == VF_TASK_NAVIGATION) {
+        for (int j = 0; j < 3; ++j) tgt[j] = T(E.target[j]);
+        reward_navigation_adj<T>(s.p, s.q, ev.vel, s.w, tgt, ev.hit, ev.success, E.max_episode_steps, age_in + 1, gr,
+                                 g.p, g.q, g.v, g.w);
+    } else {
+        for (int j = 0; j < 3; ++j) tgt[j] = E.task == VF_TASK_HOVER ? T(E.target[j]) : T(E.gates[ev.gate][j]);
+        reward_hover_adj<T>(s.p, s.q, ev.vel, s.w, tgt, gr, g.p, g.q, g.v, g.w);
+    }
+    step_bwd_taped(P, substeps, integrator, action_type, ctrl_delay, s0, c, s_raw, tape, g, ga);
+}
+
 // first gate from where the agent stands (RacingEnv.py:173-185)
 template <class T> VF_HD int racing_first_gate(const T p[3]) {
     const T rx = p[0] - T(4), ry = p[1] - T(0);

@@ -209,7 +209,8 @@ vf_env_step_fwd_kernel(const __grid_constant__ VfParams params, const __grid_con
                        float* __restrict__ returns, unsigned char* __restrict__ ebits, int* __restrict__ gate,
                        int* __restrict__ gates_passed, float* __restrict__ state_out, float* __restrict__ obs_out,
                        float* __restrict__ reward_out, unsigned char* __restrict__ done_out,
-                       float* __restrict__ record_out, float* __restrict__ term_obs_out) {
+                       float* __restrict__ record_out, float* __restrict__ term_obs_out,
+                       int* __restrict__ saved_out) {
     __shared__ __align__(16) float s_obs[(BLOCK / 32) * kWarpObs];
     const vf::Params<float>& P = reinterpret_cast<const vf::Params<float>&>(params);
     const int i = blockIdx.x * BLOCK + threadIdx.x;
@@ -229,32 +230,23 @@ vf_env_step_fwd_kernel(const __grid_constant__ VfParams params, const __grid_con
         vf::Wrench<float> k;
         vf::step_fwd<float>(P, substeps, INTEG, ACT, LAG, a, s, k);
 
-        float vel[3] = {s.v[0] + P.wind[0], s.v[1] + P.wind[1], s.v[2] + P.wind[2]};
-        const vf::BoxHit<float> hit = vf::box_hit<float>(s.p, E.bbox_lo, E.bbox_hi);
         unsigned eb = ebits[i];
-        const bool is_col = hit.dis < E.uav_radius;
-        bool once = (eb & VF_EBIT_ONCE_COLLIDED) || is_col;
         int sc = age + 1;
         int passed = 0;
-        bool success = false;
-        float reward;
-        if (E.task == VF_TASK_HOVER) {
-            reward = vf::reward_hover<float>(s.p, s.q, vel, s.w, E.target);
-        } else if (E.task == VF_TASK_NAVIGATION) {
-            success = vf::norm3(s.p[0] - E.target[0], s.p[1] - E.target[1], s.p[2] - E.target[2]) <= E.success_radius;
-            reward = vf::reward_navigation<float>(s.p, s.q, vel, s.w, E.target, hit, success, E.max_episode_steps, sc);
-        } else {
-            g = gate[i];
-            passed = gates_passed[i];
-            const bool pass = vf::norm3(s.p[0] - E.gates[g][0], s.p[1] - E.gates[g][1], s.p[2] - E.gates[g][2]) <=
-                              E.success_radius;
-            g = (g + (pass ? 1 : 0)) % E.n_gates;
-            passed += pass ? 1 : 0;
-            reward = vf::reward_hover<float>(s.p, s.q, vel, s.w, E.gates[g]) + (pass ? 20.f : 0.f);
-        }
+        int g_in = 0;
+        if (E.task == VF_TASK_RACING) { g_in = gate[i]; passed = gates_passed[i]; }
+        if (saved_out) reinterpret_cast<int2*>(saved_out)[i] = make_int2(age, g_in);
+        vf::EnvEval<float> ev;
+        vf::env_eval<float>(P, E, s, sc, g_in, (eb & VF_EBIT_EPISODE_DONE) != 0, ev);
+        float vel[3] = {ev.vel[0], ev.vel[1], ev.vel[2]};
+        g = ev.gate;
+        passed += ev.pass ? 1 : 0;
+        bool once = (eb & VF_EBIT_ONCE_COLLIDED) || ev.is_col;
+        const bool success = ev.success;
+        const float reward = ev.reward;
         float ret = returns[i] + reward;
-        bool ep_done = (eb & VF_EBIT_EPISODE_DONE) || success || hit.out || (E.collision_reset && is_col);
-        const bool done = ep_done || sc >= E.max_episode_steps;
+        bool ep_done = ev.ep_done;
+        const bool done = ev.done;
 
         unsigned rbits = (done ? VF_RBIT_DONE : 0u) | (ep_done ? VF_RBIT_EPISODE_DONE : 0u) |
                          (success ? VF_RBIT_SUCCESS : 0u) | (sc >= E.max_episode_steps ? VF_RBIT_TRUNCATED : 0u) |
@@ -273,7 +265,7 @@ vf_env_step_fwd_kernel(const __grid_constant__ VfParams params, const __grid_con
             } else {
                 float* t = term_obs_out + size_t(i) * 16;
                 // the reference builds the terminal observation before the gate index advances (RacingEnv.py:254)
-                const int g0 = (E.task == VF_TASK_RACING) ? gate[i] : 0;
+                const int g0 = g_in;
                 for (int kk = 0; kk < 2; ++kk)
                     for (int j = 0; j < 3; ++j) t[3 * kk + j] = (E.gates[(g0 + kk) % E.n_gates][j] - s.p[j]) / 10.f;
                 t[6] = s.q[0]; t[7] = s.q[1]; t[8] = s.q[2]; t[9] = s.q[3];
@@ -318,6 +310,65 @@ vf_env_step_fwd_kernel(const __grid_constant__ VfParams params, const __grid_con
         }
         warp_store_obs(obs_out, s_obs + warp * kWarpObs, n, warp_first, lane, o);
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// reverse mode of the fused env step
+// ---------------------------------------------------------------------------------------------
+template <int INTEG, int ACT, bool LAG, int SMAX, int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+vf_env_step_bwd_kernel(const __grid_constant__ VfParams params, const __grid_constant__ VfEnvSpec E, int n,
+                       int substeps, unsigned env_flags, const float* __restrict__ state_in,
+                       const float* __restrict__ action, const int* __restrict__ saved,
+                       const float* __restrict__ g_state_out, const float* __restrict__ g_obs,
+                       const float* __restrict__ g_reward, float* __restrict__ g_state_in,
+                       float* __restrict__ g_action) {
+    __shared__ __align__(16) float s_obs[(BLOCK / 32) * kWarpObs];
+    const vf::Params<float>& P = reinterpret_cast<const vf::Params<float>&>(params);
+    const int i = blockIdx.x * BLOCK + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int warp_first = i - lane;
+    const bool live = i < n;
+
+    float o[16];
+    const bool have_obs = g_obs != nullptr;
+    if (have_obs) {
+        if (E.obs_kind == VF_OBS_STATE13) {
+            warp_load_obs(g_obs, s_obs + warp * kWarpObs, n, warp_first, lane, o);
+        } else if (live) {
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                const float4 v = ldg4(g_obs, size_t(4) * i + kk);
+                o[4 * kk] = v.x; o[4 * kk + 1] = v.y; o[4 * kk + 2] = v.z; o[4 * kk + 3] = v.w;
+            }
+        }
+    }
+    if (!live) return;
+
+    vf::State<float> g;
+    if (g_state_out) {
+        load_state(g_state_out, n, i, g);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) g.p[j] = g.v[j] = g.w[j] = g.al[j] = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) g.q[j] = g.mot[j] = 0.f;
+    }
+    vf::State<float> s0;
+    load_state(state_in, n, i, s0);
+    const int2 sv = __ldg(reinterpret_cast<const int2*>(saved) + i);
+    float4 a4 = ldg4(action, size_t(i));
+    const bool masked = sv.x < E.fifo_depth;          // the forward replaced the delayed action by zero
+    if (masked) a4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+    const float gr = g_reward ? __ldg(g_reward + i) : 0.f;
+    vf::Tape<float> tape[SMAX];
+    float ga[4];
+    vf::env_step_bwd_agent<float>(P, E, substeps, INTEG, ACT, LAG, (env_flags & VF_ENV_FLAG_NO_RESET) != 0, a, s0,
+                                  sv.x, sv.y, have_obs ? o : nullptr, gr, g, ga, tape);
+    store_state(g_state_in, n, i, g);
+    stg4(g_action, size_t(i), masked ? make_float4(0.f, 0.f, 0.f, 0.f) : make_float4(ga[0], ga[1], ga[2], ga[3]));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -398,6 +449,17 @@ int check_common(const VfParams* params, int n, int substeps, int integrator, in
     return 0;
 }
 
+int check_spec(const VfEnvSpec* spec) {
+    if (!spec) return fail("spec is NULL");
+    if (spec->task < VF_TASK_HOVER || spec->task > VF_TASK_RACING) return fail("spec.task must be a VF_TASK_* value");
+    if (spec->obs_kind != VF_OBS_STATE13 && spec->obs_kind != VF_OBS_RACING16)
+        return fail("spec.obs_kind must be a VF_OBS_* value");
+    if (spec->gen_kind < VF_GEN_UNIFORM || spec->gen_kind > VF_GEN_TABLE) return fail("spec.gen_kind must be a VF_GEN_* value");
+    if (spec->gen_boxes < 1 || spec->gen_boxes > VF_GEN_MAX_BOXES) return fail("spec.gen_boxes out of range");
+    if (spec->task == VF_TASK_RACING && (spec->n_gates < 1 || spec->n_gates > 4)) return fail("spec.n_gates out of range");
+    return 0;
+}
+
 template <int INTEG, int ACT, bool LAG>
 void launch_fwd(const VfParams& p, int n, int substeps, const float* si, const float* a, float* so, float* obs,
                 float* ext, cudaStream_t st) {
@@ -427,10 +489,24 @@ template <int INTEG, int ACT, bool LAG>
 void launch_env_fwd(const VfParams& p, const VfEnvSpec& e, int n, int substeps, unsigned env_flags,
                     unsigned long long step_index, const float* si, const float* a, const float* table, int* sc,
                     float* ret, unsigned char* eb, int* gate, int* passed, float* so, float* obs, float* rew,
-                    unsigned char* done, float* rec, float* tobs, cudaStream_t st) {
+                    unsigned char* done, float* rec, float* tobs, int* saved, cudaStream_t st) {
     const int grid = (n + kBlock - 1) / kBlock;
     vf_env_step_fwd_kernel<INTEG, ACT, LAG, kBlock><<<grid, kBlock, 0, st>>>(
-        p, e, n, substeps, env_flags, step_index, si, a, table, sc, ret, eb, gate, passed, so, obs, rew, done, rec, tobs);
+        p, e, n, substeps, env_flags, step_index, si, a, table, sc, ret, eb, gate, passed, so, obs, rew, done, rec, tobs,
+        saved);
+}
+
+template <int INTEG, int ACT, bool LAG>
+void launch_env_bwd(const VfParams& p, const VfEnvSpec& e, int n, int substeps, unsigned env_flags, const float* si,
+                    const float* a, const int* saved, const float* gso, const float* gobs, const float* gr, float* gsi,
+                    float* ga, cudaStream_t st) {
+    const int grid = (n + kBlock - 1) / kBlock;
+    if (substeps <= 8)
+        vf_env_step_bwd_kernel<INTEG, ACT, LAG, 8, kBlock><<<grid, kBlock, 0, st>>>(p, e, n, substeps, env_flags, si, a, saved, gso, gobs, gr, gsi, ga);
+    else if (substeps <= 16)
+        vf_env_step_bwd_kernel<INTEG, ACT, LAG, 16, kBlock><<<grid, kBlock, 0, st>>>(p, e, n, substeps, env_flags, si, a, saved, gso, gobs, gr, gsi, ga);
+    else
+        vf_env_step_bwd_kernel<INTEG, ACT, LAG, VF_MAX_SUBSTEPS_BWD, kBlock><<<grid, kBlock, 0, st>>>(p, e, n, substeps, env_flags, si, a, saved, gso, gobs, gr, gsi, ga);
 }
 
 #define VF_DISPATCH(FN, ...)                                                                  \
@@ -540,15 +616,9 @@ int vf_env_step_fwd(const VfParams* params, const VfEnvSpec* spec, int n, int su
                     const float* state_in, const float* action, const float* reset_table, int* step_count,
                     float* returns, unsigned char* ebits, int* gate, int* gates_passed, float* state_out,
                     float* obs_out, float* reward_out, unsigned char* done_out, float* record_out,
-                    float* term_obs_out, void* stream) {
+                    float* term_obs_out, int* saved_out, void* stream) {
     if (check_common(params, n, substeps, integrator, action_type)) return 1;
-    if (!spec) return fail("spec is NULL");
-    if (spec->task < VF_TASK_HOVER || spec->task > VF_TASK_RACING) return fail("spec.task must be a VF_TASK_* value");
-    if (spec->obs_kind != VF_OBS_STATE13 && spec->obs_kind != VF_OBS_RACING16)
-        return fail("spec.obs_kind must be a VF_OBS_* value");
-    if (spec->gen_kind < VF_GEN_UNIFORM || spec->gen_kind > VF_GEN_TABLE) return fail("spec.gen_kind must be a VF_GEN_* value");
-    if (spec->gen_boxes < 1 || spec->gen_boxes > VF_GEN_MAX_BOXES) return fail("spec.gen_boxes out of range");
-    if (spec->task == VF_TASK_RACING && (spec->n_gates < 1 || spec->n_gates > 4)) return fail("spec.n_gates out of range");
+    if (check_spec(spec)) return 1;
     if (n == 0) return 0;
     if (!state_in || !action || !state_out || !step_count || !returns || !ebits || !obs_out || !reward_out ||
         !done_out || !record_out)
@@ -562,9 +632,30 @@ int vf_env_step_fwd(const VfParams* params, const VfEnvSpec* spec, int n, int su
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     VF_DISPATCH(launch_env_fwd, *params, *spec, n, substeps, env_flags, step_index, state_in, action, reset_table,
                 step_count, returns, ebits, gate, gates_passed, state_out, obs_out, reward_out, done_out, record_out,
-                term_obs_out, st);
+                term_obs_out, saved_out, st);
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return fail("vf_env_step_fwd launch failed", err);
+    return 0;
+}
+
+int vf_env_step_bwd(const VfParams* params, const VfEnvSpec* spec, int n, int substeps, int integrator,
+                    int action_type, unsigned flags, unsigned env_flags, const float* state_in, const float* action,
+                    const int* saved, const float* grad_state_out, const float* grad_obs, const float* grad_reward,
+                    float* grad_state_in, float* grad_action, void* stream) {
+    if (check_common(params, n, substeps, integrator, action_type)) return 1;
+    if (check_spec(spec)) return 1;
+    if (substeps > VF_MAX_SUBSTEPS_BWD) return fail("substeps exceeds VF_MAX_SUBSTEPS_BWD for the reverse sweep");
+    if (n == 0) return 0;
+    if (!state_in || !action || !saved || !grad_state_in || !grad_action)
+        return fail("vf_env_step_bwd: a required buffer is NULL");
+    if (!aligned16(state_in) || !aligned16(action) || !aligned16(grad_state_out) || !aligned16(grad_obs) ||
+        !aligned16(grad_state_in) || !aligned16(grad_action) || (reinterpret_cast<size_t>(saved) & 7u))
+        return fail("all buffers must be 16-byte aligned (saved: 8-byte)");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    VF_DISPATCH(launch_env_bwd, *params, *spec, n, substeps, env_flags, state_in, action, saved, grad_state_out,
+                grad_obs, grad_reward, grad_state_in, grad_action, st);
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return fail("vf_env_step_bwd launch failed", err);
     return 0;
 }
 

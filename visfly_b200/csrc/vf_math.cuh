@@ -489,19 +489,12 @@ template <class T> struct Tape {
     T q[4], v[3], w[3], mot[4];
 };
 
-// Reverse-mode control step.
-//   s0  : state at the start of the step
-//   g   : in  = dL/d(state after the step) [gradient w.r.t. the observation already folded in by the caller],
-//         out = dL/d(s0)
-//   ga  : out = dL/d(action)
-//   tape: scratch of at least `substeps` entries
+// Forward re-run for the reverse sweep: records each sub-step's inputs; `s` ends as the UNCLAMPED end state.
 template <class T>
-VF_HD void step_bwd(const Params<T>& P, int substeps, int integrator, int action_type, bool ctrl_delay,
-                    const T a[4], const State<T>& s0, State<T>& g, T ga[4], Tape<T>* tape) {
-    // ---- forward re-run, recording each sub-step's inputs ----
-    Command<T> c;
+VF_HD void step_fwd_taped(const Params<T>& P, int substeps, int integrator, int action_type, bool ctrl_delay,
+                          const T a[4], const State<T>& s0, Command<T>& c, State<T>& s, Tape<T>* tape) {
     command_fwd(P, action_type, a, s0.w, s0.al, c);
-    State<T> s = s0;
+    s = s0;
     Wrench<T> k;
     for (int it = 0; it < substeps; ++it) {
         Tape<T>& t = tape[it];
@@ -509,11 +502,20 @@ VF_HD void step_bwd(const Params<T>& P, int substeps, int integrator, int action
         for (int i = 0; i < 3; ++i) { t.v[i] = s.v[i]; t.w[i] = s.w[i]; }
         substep_fwd(P, integrator, ctrl_delay, c, s, k);
     }
+}
+
+// Reverse sweep over a recorded step.
+//   s_raw: unclamped end state from step_fwd_taped (gradient gates of the post-step clamps)
+//   g    : in = dL/d(clamped state after the step), out = dL/d(s0);   ga: out = dL/d(action)
+template <class T>
+VF_HD void step_bwd_taped(const Params<T>& P, int substeps, int integrator, int action_type, bool ctrl_delay,
+                          const State<T>& s0, const Command<T>& c, const State<T>& s_raw, const Tape<T>* tape,
+                          State<T>& g, T ga[4]) {
     // ---- gates of the post-step clamps (gradient w.r.t. the unclamped values) ----
     for (int i = 0; i < 3; ++i) {
-        g.p[i] = vgate(s.p[i], P.pos_lo[i], P.pos_hi[i], g.p[i]);
-        g.v[i] = vgate(s.v[i], -P.vel_lim, P.vel_lim, g.v[i]);
-        g.w[i] = vgate(s.w[i], -P.rate_lim, P.rate_lim, g.w[i]);
+        g.p[i] = vgate(s_raw.p[i], P.pos_lo[i], P.pos_hi[i], g.p[i]);
+        g.v[i] = vgate(s_raw.v[i], -P.vel_lim, P.vel_lim, g.v[i]);
+        g.w[i] = vgate(s_raw.w[i], -P.rate_lim, P.rate_lim, g.w[i]);
     }
     // ---- reverse sweep ----
     T g_wdes[4] = {T(0), T(0), T(0), T(0)};
@@ -555,6 +557,21 @@ VF_HD void step_bwd(const Params<T>& P, int substeps, int integrator, int action
         for (int i = 0; i < 4; ++i) g_tdes[i] += g_wdes[i] / c.disc[i];
     g.al[0] = g.al[1] = g.al[2] = T(0);         // start-of-step alpha only enters through the PID D term
     command_adj(P, action_type, s0.w, c, g_tdes, ga, g.w, g.al);
+}
+
+// Reverse-mode control step.
+//   s0  : state at the start of the step
+//   g   : in  = dL/d(state after the step) [gradient w.r.t. the observation already folded in by the caller],
+//         out = dL/d(s0)
+//   ga  : out = dL/d(action)
+//   tape: scratch of at least `substeps` entries
+template <class T>
+VF_HD void step_bwd(const Params<T>& P, int substeps, int integrator, int action_type, bool ctrl_delay,
+                    const T a[4], const State<T>& s0, State<T>& g, T ga[4], Tape<T>* tape) {
+    Command<T> c;
+    State<T> s;
+    step_fwd_taped(P, substeps, integrator, action_type, ctrl_delay, a, s0, c, s, tape);
+    step_bwd_taped(P, substeps, integrator, action_type, ctrl_delay, s0, c, s, tape, g, ga);
 }
 
 }  // namespace vf

@@ -145,6 +145,7 @@ class DroneGymEnvsBase(VecEnv):
         self._info = None
         self._indiv_rewards = self._indiv_reward = None
         self.keep_terminal_observation = True     # False: skip writing info["terminal_observation"] rows
+        self.use_fused_step = True                # False: force the generic tensor-op path (debugging / comparison)
         self._fused = None                        # FusedEnvStep, created by built-in tasks (_make_fused)
         self.render_mode = ["None"] * n
         self._is_initial = False
@@ -161,7 +162,7 @@ class DroneGymEnvsBase(VecEnv):
         if self.debug_checks:                                   # reference droneGymEnv.py:144 (host sync)
             assert self._action.max() <= 1 and self._action.min() >= -1
         if self._fused is not None:
-            if not self.requires_grad and not is_test and self._fused.refresh():
+            if not is_test and self._fused.refresh():
                 return self._step_fused()
             self._fused.leave()
         with self._grad_ctx():
@@ -208,7 +209,9 @@ class DroneGymEnvsBase(VecEnv):
 
     def _step_fused(self):
         from .fused import RecordInfo
-        obs, reward, done, record, term = self._fused.step(self._action)
+        if self.requires_grad and not self.tensor_output:
+            raise ValueError("requires_grad should be False if tensor_output is False")
+        obs, reward, done, record, term = self._fused.step(self._action, grad=self.requires_grad)
         self._obs_tensors = self._fused_obs(obs)
         term_obs = self._fused_obs(term) if term is not None else {}
         info = RecordInfo(self.num_agent, record, term_obs, self.envs.dynamics.ctrl_dt,

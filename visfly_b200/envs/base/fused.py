@@ -1,11 +1,12 @@
 """Host side of the fused env step (``vf_env_step_fwd``): one kernel launch per ``env.step`` for the built-in tasks.
 
-``DroneGymEnvsBase.step`` takes this path when nothing needs autograd or Python-defined task code:
-``requires_grad=False``, ``is_test=False``, the task's ``get_reward / get_success / get_failure / get_observation``
-are the built-in ones, the IMU noise model is zero, the state generator is one the kernel can sample
-(Uniform / Normal / Union of those, or a reset table), and the orientation output is the quaternion.  Everything else
-(custom tasks, analytic-gradient training) keeps using the generic tensor-op path, which has identical semantics;
-``tests/test_gpu_env.py`` replays the reference's golden runs through both.
+``DroneGymEnvsBase.step`` takes this path when no Python-defined task code is involved: ``is_test=False``, the
+task's ``get_reward / get_success / get_failure / get_observation`` are the built-in ones, the IMU noise model is
+zero, the state generator is one the kernel can sample (Uniform / Normal / Union of those, or a reset table), the
+orientation output is the quaternion and ``env.use_fused_step`` is True.  With ``requires_grad=True`` the step goes
+through ``EnvControlStep`` (backward = one launch of ``vf_env_step_bwd``, the hand-derived adjoint of step + reward).
+Everything else (custom tasks) keeps using the generic tensor-op path, which has identical semantics;
+``tests/test_gpu_env.py`` replays the reference's golden runs and gradients through both.
 """
 from __future__ import annotations
 
@@ -170,7 +171,7 @@ class FusedEnvStep:
         env = self.env
         envs = env.envs
         key = (id(envs.stateGenerator), id(envs._reset_table), env.max_episode_steps, env.is_collision_reset,
-               "_generate_state" in envs.__dict__)
+               "_generate_state" in envs.__dict__, env.use_fused_step)
         if key == self._key:
             return self._ok
         self._key = key
@@ -179,7 +180,7 @@ class FusedEnvStep:
 
     def _refresh(self) -> bool:
         env, s = self.env, self.spec
-        if os.environ.get("VISFLY_B200_NO_FUSED_ENV") or not env.envs._imu_noise_free:
+        if os.environ.get("VISFLY_B200_NO_FUSED_ENV") or not env.use_fused_step or not env.envs._imu_noise_free:
             return False
         if not env.envs.dynamics.is_quat_output or "_generate_state" in vars(env.envs):
             return False
@@ -202,7 +203,6 @@ class FusedEnvStep:
         if self.task == P.TASK_RACING:
             self.gate = env._next_target_i.to(th.int32).clone()
             self.passed = env._past_targets_num.to(th.int32).clone()
-        dyn.detach()
         env.envs._fused = self
         for t, dt in ((self.sc, th.int32), (self.ret, th.float32), (self.eb, th.uint8)):
             assert t.is_cuda and t.is_contiguous() and t.dtype == dt
@@ -235,24 +235,16 @@ class FusedEnvStep:
         self.active = False
 
     # -- the step -------------------------------------------------------------------------------------------
-    def step(self, action: th.Tensor):
+    def _launch(self, state_in: th.Tensor, action: th.Tensor, want_saved: bool):
+        """Allocate the step's outputs and launch ``vf_env_step_fwd`` (status buffers are updated in place)."""
         env, dyn, n, dev = self.env, self.env.envs.dynamics, self.n, self.device
-        if self._fn is None:
-            self._bind()
-        if not self.active:
-            self.enter()
-        if dyn._comm_delay_steps:
-            dyn._pre_action.append(action)
-            action = dyn._pre_action.pop(0)
-        if not action.is_contiguous():
-            action = action.contiguous()
-        state_in = dyn._state
         state_out = th.empty_like(state_in)
         obs = th.empty((n, self.obs_width), dtype=th.float32, device=dev)
         reward = th.empty((n,), dtype=th.float32, device=dev)
         done = th.empty((n,), dtype=th.bool, device=dev)
         record = th.empty((n, 4), dtype=th.float32, device=dev)
         term = th.empty((n, self.obs_width), dtype=th.float32, device=dev) if env.keep_terminal_observation else None
+        saved = th.empty((n, 2), dtype=th.int32, device=dev) if want_saved else None
         cfg = dyn._cfg
         # hot call: tensors created above / owned by this object are float32-contiguous-CUDA by construction, the
         # action was normalised by the wrapper; the C side still validates NULLs and alignment
@@ -263,12 +255,32 @@ class FusedEnvStep:
                       None if self.table is None else self.table.data_ptr(), self._p_sc, self._p_ret, self._p_eb,
                       self._p_gate, self._p_passed, state_out.data_ptr(), obs.data_ptr(), reward.data_ptr(),
                       done.data_ptr(), record.data_ptr(), None if term is None else term.data_ptr(),
-                      _raw_stream(dev.index))
+                      None if saved is None else saved.data_ptr(), _raw_stream(dev.index))
         if rc != 0:
             raise RuntimeError("visfly_b200: " + _lib.load().vf_last_error().decode())
         self.global_step += 1
+        return state_out, obs, reward, done, record, term, saved
+
+    def step(self, action: th.Tensor, grad: bool = False):
+        """One env step = one launch.  ``grad=True`` routes through ``EnvControlStep`` so that the returned state,
+        observation and reward carry autograd history (backward = one launch of ``vf_env_step_bwd``)."""
+        env, dyn = self.env, self.env.envs.dynamics
+        if self._fn is None:
+            self._bind()
+        if not self.active:
+            self.enter()
+        if dyn._comm_delay_steps:
+            dyn._pre_action.append(action)
+            action = dyn._pre_action.pop(0)
+        if not action.is_contiguous():
+            action = action.contiguous()
+        state_in = dyn._state
+        if grad:
+            state_out, obs, reward, done, record, term = EnvControlStep.apply(state_in, action, self)
+        else:
+            state_out, obs, reward, done, record, term, _ = self._launch(state_in, action, False)
         # keep the Dynamics object coherent (lazy views, diagnostics)
-        dyn._prev = (state_in, action)
+        dyn._prev = (state_in.detach(), action.detach()) if grad else (state_in, action)
         dyn._state = state_out
         dyn._obs_t = obs if self.obs_kind == P.OBS_STATE13 else None
         dyn._n_steps += 1
@@ -280,3 +292,30 @@ class FusedEnvStep:
         if self.gate is not None:
             env._next_target_i, env._past_targets_num = self.gate, self.passed
         return obs, reward, done, record, term
+
+
+class EnvControlStep(th.autograd.Function):
+    """``(state, action) -> (state', obs, reward | done, record, terminal obs)`` — the fused env step with its
+    hand-derived adjoint; saves nothing but the step's inputs and 8 bytes per agent of start-of-step status."""
+
+    @staticmethod
+    def forward(ctx, state: th.Tensor, action: th.Tensor, fz: FusedEnvStep):
+        state_out, obs, reward, done, record, term, saved = fz._launch(state, action, True)
+        ctx.fz = fz
+        ctx.save_for_backward(state, action, saved)
+        ctx.set_materialize_grads(False)
+        outs = (state_out, obs, reward, done, record) + (() if term is None else (term,))
+        ctx.mark_non_differentiable(done, record, *(() if term is None else (term,)))
+        return outs if term is not None else outs + (None,)
+
+    @staticmethod
+    @th.autograd.function.once_differentiable
+    def backward(ctx, g_state_out, g_obs, g_reward, *_):
+        state, action, saved = ctx.saved_tensors
+        fz = ctx.fz
+        cfg = fz.env.envs.dynamics._cfg
+        g_state, g_action = th.empty_like(state), th.empty_like(action)
+        c = lambda t: None if t is None else t.contiguous()
+        _lib.env_step_bwd(cfg.params, fz.spec, cfg.substeps, cfg.integrator, cfg.action_type, cfg.flags, 0,
+                          state, action, saved, c(g_state_out), c(g_obs), c(g_reward), g_state, g_action)
+        return g_state, g_action, None
