@@ -344,6 +344,9 @@ def run_ours(args):
            "d2h_bytes_per_step": n * (13 * 4 + 4 + 1), "ms_per_step": 1e3 * float(e2e_s) / K,
            "api": "HoverEnv(tensor_output=False).step(numpy actions) -> numpy obs/reward/done"}
 
+    # ---- config[2]: APG-style analytic policy gradient through NavigationEnv (requires_grad=True) -----------------
+    apg = apg_benchmark(n, dev, rank, world, barrier)
+
     if rank == 0:
         cpu = None
         if not args.no_cpu_baseline:
@@ -360,13 +363,72 @@ def run_ours(args):
                        "l2": "value = min(cold: 256 MiB L2 flush before every timed step, one CUDA-event pair per step; "
                              "hot: K steps back to back inside barrier+synchronize, host overhead included)",
                        "parallelism": f"agents sharded over {world} GPU(s), one all_gather of episode returns per rollout"},
-            "clocks": clk.summary(), "e2e": e2e, "gpu_launches": K * env_launches_per_step(env),
+            "clocks": clk.summary(), "e2e": e2e, "gpu_launches": K * env_launches_per_step(env), "apg": apg,
             "roofline": roofline, "cpu_baseline": cpu,
             "cold_l2_device_value": cold_value, "hot_l2_bracketed_value": hot_value, "kernel_only_value": n / k_avg,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def make_policy(device, seed=0):
+    """Fixed small MLP (state 13 + target 3 -> 64 -> 64 -> 4, tanh output), SURVEY.md §8d config 3."""
+    g = th.Generator().manual_seed(seed)
+    net = th.nn.Sequential(th.nn.Linear(16, 64), th.nn.Tanh(), th.nn.Linear(64, 64), th.nn.Tanh(),
+                           th.nn.Linear(64, 4), th.nn.Tanh())
+    with th.no_grad():
+        for p_ in net.parameters():
+            p_.copy_((th.rand(p_.shape, generator=g) * 2 - 1) * (0.3 if p_.dim() > 1 else 0.0))
+        net[-2].bias[0] = -0.35          # hover-ish collective
+    return net.to(device)
+
+
+def apg_benchmark(n, dev, rank, world, barrier, H=32, rollouts=5, gamma=0.99):
+    """BPTT rollout (reference utils/algorithms/BPTT.py:107-134): H steps with grad through NavigationEnv, loss =
+    -sum gamma^t r_t, backward, env.detach().  Forward = one fused env-step launch per step, backward = one adjoint
+    launch per step (EnvControlStep); the policy MLP is plain torch."""
+    import torch.distributed as dist
+    from visfly_b200.envs import NavigationEnv
+    env = NavigationEnv(num_agent_per_scene=n, visual=False, device=dev, dynamics_kwargs=dict(DYN), seed=7 + rank,
+                        requires_grad=True, max_episode_steps=256,
+                        random_kwargs={"state_generator": {"class": "Uniform", "kwargs": [
+                            {"position": {"mean": [2., 0., 1.5], "half": [1.0, 1.0, 0.5]}}]}})
+    policy = make_policy(dev)
+    opt_params = list(policy.parameters())
+    obs = env.reset()
+
+    def rollout():
+        nonlocal obs
+        loss = 0.0
+        for t in range(H):
+            a = policy(th.cat([obs["state"], obs["target"]], 1))
+            obs, r, d, info = env.step(a)
+            loss = loss - (gamma ** t) * r
+        loss = loss.mean()
+        grads = th.autograd.grad(loss, opt_params)
+        env.detach()
+        obs = env._obs_tensors.detach()
+        return loss, grads
+
+    for _ in range(2):
+        rollout()
+    barrier()
+    e0, e1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(rollouts):
+        loss, grads = rollout()
+    e1.record()
+    barrier()
+    ms = th.tensor([max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)], device=dev, dtype=th.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    finite = all(bool(th.isfinite(g_).all()) for g_ in grads)
+    return {"workload": "NavigationEnv 65536 agents/GPU requires_grad=True RK4 (BASELINE configs[2]), H=32 BPTT rollouts, "
+                        "MLP 16-64-64-4 policy", "value": world * n * H * rollouts / (float(ms) * 1e-3), "unit": UNIT + " (fwd+bwd)",
+            "ms_per_rollout": float(ms) / rollouts, "horizon": H, "grads_finite": finite,
+            "fused": bool(env._fused is not None and env._fused.active)}
 
 
 def env_launches_per_step(env) -> int:
