@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define VF_ABI_VERSION 4
+#define VF_ABI_VERSION 5
 
 /* integrator: reference `integrator=` kwarg, utils/maths.py:331 (euler) and :353 (rk4, repaired R1-R3) */
 #define VF_INTEGRATOR_EULER 0
@@ -206,6 +206,18 @@ typedef struct VfEnvSpec {
 
 int vf_env_spec_size(void);
 
+/* Optional second destination of what env.step hands back to a caller that lives in HOST memory (the reference's
+ * numpy output mode, envs/base/droneGymEnv.py:218).  The pointers are page-locked host buffers (cudaHostAlloc /
+ * cudaHostRegister; the library resolves their device alias with cudaHostGetDevicePointer): the kernel stores
+ * observation, reward and done flag there directly (zero-copy over PCIe, overlapped with the arithmetic of the other
+ * warps) in addition to the device outputs, so the step needs no device->host copy afterwards — only a stream
+ * synchronisation before the host reads.  Any member may be NULL. */
+typedef struct VfEnvMirror {
+    float* obs;      /* [n][13|16]                                                          */
+    float* reward;   /* [n]                                                                 */
+    int*   done;     /* [n]  0/1 as int32 (the reference returns done.astype(np.int32))     */
+} VfEnvMirror;
+
 /*
  * One env step for n agents.
  *   state_in/action/state_out   as vf_step_fwd (action = output of the caller's comm-delay FIFO)
@@ -221,13 +233,15 @@ int vf_env_spec_size(void);
  *   record_out  float[n][4]   [episode return, episode length, VF_RBIT_* as float, gates passed] of this step
  *   term_obs_out float[n][13|16] or NULL: observation BEFORE the reset, written only for finished agents
  *   saved_out   int32[n][2] or NULL: [step_count, gate] at the START of the step — what vf_env_step_bwd needs
+ *   host_mirror NULL, or page-locked host destinations written in addition to obs_out / reward_out / done_out
  */
 int vf_env_step_fwd(const VfParams* params, const VfEnvSpec* spec, int n, int substeps, int integrator,
                     int action_type, unsigned flags, unsigned env_flags, unsigned long long step_index,
                     const float* state_in, const float* action, const float* reset_table,
                     int* step_count, float* returns, unsigned char* ebits, int* gate, int* gates_passed,
                     float* state_out, float* obs_out, float* reward_out, unsigned char* done_out,
-                    float* record_out, float* term_obs_out, int* saved_out, void* stream);
+                    float* record_out, float* term_obs_out, int* saved_out, const VfEnvMirror* host_mirror,
+                    void* stream);
 
 /*
  * Reverse mode of vf_env_step_fwd with respect to (state_in, action), given the gradients of its differentiable

@@ -248,3 +248,61 @@ def test_fused_env_gradients_match_generic_autograd(task):
     assert abs(float(res[True][2] - res[False][2])) < 1e-5
     assert rel_l2(res[True][0].cpu(), res[False][0].cpu()) < 1e-4
     assert rel_l2(res[True][1].cpu(), res[False][1].cpu()) < 1e-4
+
+
+@pytest.mark.parametrize("task", TASKS)
+def test_numpy_mode_host_mirror_equals_tensor_mode(task):
+    """numpy output mode of the fused step (kernel writes obs / reward / done straight into page-locked host memory)
+    returns exactly what the tensor mode returns; host actions may be page-locked, pageable numpy or CPU tensors."""
+    z = load_env_golden(task, "rk4")
+    acts = z["actions"]
+    T, n = acts.shape[:2]
+    steps = int(z["max_episode_steps"]) if "max_episode_steps" in z.files else 20
+
+    def build(tensor_output):
+        env = make_env(task, n, "rk4", steps, table_of(z), path="fused", tensor_output=tensor_output)
+        env.reset()
+        return env
+
+    dev_env, np_env = build(True), build(False)
+    pinned = th.empty((n, 4), pin_memory=True)
+    held = []
+    for t in range(T):
+        o1, r1, d1, i1 = dev_env.step(th.from_numpy(acts[t]).cuda())
+        if t % 3 == 0:                                   # page-locked host array
+            pinned.copy_(th.from_numpy(acts[t]))
+            a = pinned.numpy()
+        elif t % 3 == 1:                                 # pageable numpy
+            a = acts[t].copy()
+        else:                                            # CPU tensor
+            a = th.from_numpy(acts[t].copy())
+        o2, r2, d2, i2 = np_env.step(a)
+        assert np_env._fused.active and dev_env._fused.active
+        assert isinstance(o2["state"], np.ndarray) and isinstance(r2, np.ndarray) and d2.dtype == np.int32
+        assert set(o1.keys()) == set(o2.keys())
+        for k in o1.keys():
+            assert np.array_equal(o1[k].cpu().numpy(), np.asarray(o2[k])), (t, k)
+        assert np.array_equal(r1.cpu().numpy(), r2) and np.array_equal(d1.cpu().numpy().astype(np.int32), d2)
+        for i in np.nonzero(d2)[0]:
+            assert float(i1[int(i)]["episode"]["r"]) == float(i2[int(i)]["episode"]["r"])
+        held.append((o2["state"], o2["state"].copy()))
+        if len(held) >= 2:                                # arrays handed out one step ago are still intact
+            view, snap = held[-2]
+            assert np.array_equal(view, snap)
+
+
+def test_numpy_mode_host_mirror_ragged_batch():
+    """Agent counts that are not a multiple of the warp size take the scalar store path of the mirror as well."""
+    from visfly_b200.envs import HoverEnv
+    n = 83
+    envs = [HoverEnv(num_agent_per_scene=n, visual=False, dynamics_kwargs=dict(DYN["rk4"]), seed=5, max_episode_steps=6,
+                     tensor_output=mode) for mode in (True, False)]
+    o1, o2 = envs[0].reset(), envs[1].reset()
+    assert np.array_equal(o1["state"].cpu().numpy(), o2["state"])
+    g = th.Generator().manual_seed(3)
+    for t in range(14):                                   # crosses two auto-resets (Philox keyed by seed/agent/step)
+        a = th.rand(n, 4, generator=g) * 2 - 1
+        o1, r1, d1, _ = envs[0].step(a.cuda())
+        o2, r2, d2, _ = envs[1].step(a.numpy())
+        assert np.array_equal(o1["state"].cpu().numpy(), o2["state"]) and np.array_equal(r1.cpu().numpy(), r2)
+        assert np.array_equal(d1.cpu().numpy().astype(np.int32), d2)

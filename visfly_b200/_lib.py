@@ -11,11 +11,11 @@ from typing import Optional
 
 import torch as th
 
-from .params import VfEnvSpec, VfParams
+from .params import VfEnvMirror, VfEnvSpec, VfParams
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvisfly_b200.so")
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 INTEGRATOR_ID = {"euler": 0, "rk4": 1}
 FLAG_CTRL_DELAY = 1
@@ -39,7 +39,8 @@ SIGNATURES = {
     "vf_unpack_state": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "vf_env_spec_size": (_i, []),
     "vf_env_step_fwd": (_i, [_P(VfParams), _P(VfEnvSpec), _i, _i, _i, _i, _u, _u, ctypes.c_ulonglong,
-                             _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+                             _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                             _P(VfEnvMirror), _vp]),
     "vf_env_step_bwd": (_i, [_P(VfParams), _P(VfEnvSpec), _i, _i, _i, _i, _u, _u,
                              _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
 }
@@ -177,7 +178,8 @@ def env_step_fwd(params: VfParams, spec: VfEnvSpec, substeps: int, integrator: i
                  reset_table: Optional[th.Tensor], step_count: th.Tensor, returns: th.Tensor, ebits: th.Tensor,
                  gate: Optional[th.Tensor], gates_passed: Optional[th.Tensor], state_out: th.Tensor,
                  obs_out: th.Tensor, reward_out: th.Tensor, done_out: th.Tensor, record_out: th.Tensor,
-                 term_obs_out: Optional[th.Tensor], saved_out: Optional[th.Tensor] = None) -> None:
+                 term_obs_out: Optional[th.Tensor], saved_out: Optional[th.Tensor] = None,
+                 host_mirror: Optional[VfEnvMirror] = None) -> None:
     """Binding of ``vf_env_step_fwd`` (fused control step + env wrapper tail, one launch)."""
     lib = load(require_cuda=True)
     n = state_in.shape[1]
@@ -191,7 +193,7 @@ def env_step_fwd(params: VfParams, spec: VfEnvSpec, substeps: int, integrator: i
             _dev_ptr(obs_out, "obs_out"), _dev_ptr(reward_out, "reward_out"),
             _any_ptr(done_out, "done_out", th.bool), _dev_ptr(record_out, "record_out"),
             _dev_ptr(term_obs_out, "term_obs_out"), _any_ptr(saved_out, "saved_out", th.int32),
-            _stream(state_in.device)))
+            None if host_mirror is None else ctypes.byref(host_mirror), _stream(state_in.device)))
 
 
 def env_step_bwd(params: VfParams, spec: VfEnvSpec, substeps: int, integrator: int, action_type: int, flags: int,

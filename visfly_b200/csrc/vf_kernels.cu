@@ -64,24 +64,35 @@ __device__ __forceinline__ void store_state(float* __restrict__ st, int n, int i
 
 // Warp-cooperative transpose of 32 agents x 13 floats between registers and the row-major (n,13) array.
 // `smem` is this warp's 416-float slice.  lane*13+j is conflict-free (13 is odd).
+// `obs2` (optional) is a second destination with the same layout (the page-locked host mirror).
 __device__ __forceinline__ void warp_store_obs(float* __restrict__ obs, float* smem, int n, int warp_first,
-                                               int lane, const float o[kObs]) {
+                                               int lane, const float o[kObs], float* __restrict__ obs2 = nullptr) {
     if (warp_first + 32 <= n) {
 #pragma unroll
         for (int j = 0; j < kObs; ++j) smem[lane * kObs + j] = o[j];
         __syncwarp();
         float4* dst = reinterpret_cast<float4*>(obs + size_t(warp_first) * kObs);
+        float4* dst2 = reinterpret_cast<float4*>(obs2 + size_t(warp_first) * kObs);
         const float4* src = reinterpret_cast<const float4*>(smem);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const int idx = lane + 32 * k;
-            if (idx < kWarpObs / 4) dst[idx] = src[idx];
+            if (idx < kWarpObs / 4) {
+                const float4 v = src[idx];
+                dst[idx] = v;
+                if (obs2) dst2[idx] = v;
+            }
         }
         __syncwarp();
     } else if (warp_first + lane < n) {
         float* dst = obs + size_t(warp_first + lane) * kObs;
 #pragma unroll
         for (int j = 0; j < kObs; ++j) dst[j] = o[j];
+        if (obs2) {
+            float* dst2 = obs2 + size_t(warp_first + lane) * kObs;
+#pragma unroll
+            for (int j = 0; j < kObs; ++j) dst2[j] = o[j];
+        }
     }
 }
 
@@ -210,7 +221,7 @@ vf_env_step_fwd_kernel(const __grid_constant__ VfParams params, const __grid_con
                        int* __restrict__ gates_passed, float* __restrict__ state_out, float* __restrict__ obs_out,
                        float* __restrict__ reward_out, unsigned char* __restrict__ done_out,
                        float* __restrict__ record_out, float* __restrict__ term_obs_out,
-                       int* __restrict__ saved_out) {
+                       int* __restrict__ saved_out, const VfEnvMirror mirror) {
     __shared__ __align__(16) float s_obs[(BLOCK / 32) * kWarpObs];
     const vf::Params<float>& P = reinterpret_cast<const vf::Params<float>&>(params);
     const int i = blockIdx.x * BLOCK + threadIdx.x;
@@ -254,6 +265,8 @@ vf_env_step_fwd_kernel(const __grid_constant__ VfParams params, const __grid_con
         stg4(record_out, size_t(i), make_float4(ret, float(sc), float(rbits), float(passed)));
         reward_out[i] = reward;
         done_out[i] = done ? 1 : 0;
+        if (mirror.reward) mirror.reward[i] = reward;
+        if (mirror.done) mirror.done[i] = done ? 1 : 0;
 
         if (done && term_obs_out) {                 // rare: scalar stores are fine
             if (E.obs_kind == VF_OBS_STATE13) {
@@ -296,8 +309,11 @@ vf_env_step_fwd_kernel(const __grid_constant__ VfParams params, const __grid_con
                 for (int j = 0; j < 3; ++j) o[3 * kk + j] = (E.gates[(g + kk) % E.n_gates][j] - s.p[j]) / 10.f;
             o[6] = s.q[0]; o[7] = s.q[1]; o[8] = s.q[2]; o[9] = s.q[3];
             for (int j = 0; j < 3; ++j) { o[10 + j] = vel[j] / 10.f; o[13 + j] = s.w[j] / 10.f; }
-            for (int kk = 0; kk < 4; ++kk)
-                stg4(obs_out, size_t(4) * i + kk, make_float4(o[4 * kk], o[4 * kk + 1], o[4 * kk + 2], o[4 * kk + 3]));
+            for (int kk = 0; kk < 4; ++kk) {
+                const float4 v = make_float4(o[4 * kk], o[4 * kk + 1], o[4 * kk + 2], o[4 * kk + 3]);
+                stg4(obs_out, size_t(4) * i + kk, v);
+                if (mirror.obs) stg4(mirror.obs, size_t(4) * i + kk, v);
+            }
         }
     }
     if (E.obs_kind == VF_OBS_STATE13) {
@@ -308,7 +324,7 @@ vf_env_step_fwd_kernel(const __grid_constant__ VfParams params, const __grid_con
             o[7] = s.v[0] + P.wind[0]; o[8] = s.v[1] + P.wind[1]; o[9] = s.v[2] + P.wind[2];
             o[10] = s.w[0]; o[11] = s.w[1]; o[12] = s.w[2];
         }
-        warp_store_obs(obs_out, s_obs + warp * kWarpObs, n, warp_first, lane, o);
+        warp_store_obs(obs_out, s_obs + warp * kWarpObs, n, warp_first, lane, o, mirror.obs);
     }
 }
 
@@ -489,11 +505,12 @@ template <int INTEG, int ACT, bool LAG>
 void launch_env_fwd(const VfParams& p, const VfEnvSpec& e, int n, int substeps, unsigned env_flags,
                     unsigned long long step_index, const float* si, const float* a, const float* table, int* sc,
                     float* ret, unsigned char* eb, int* gate, int* passed, float* so, float* obs, float* rew,
-                    unsigned char* done, float* rec, float* tobs, int* saved, cudaStream_t st) {
+                    unsigned char* done, float* rec, float* tobs, int* saved, const VfEnvMirror& mirror,
+                    cudaStream_t st) {
     const int grid = (n + kBlock - 1) / kBlock;
     vf_env_step_fwd_kernel<INTEG, ACT, LAG, kBlock><<<grid, kBlock, 0, st>>>(
         p, e, n, substeps, env_flags, step_index, si, a, table, sc, ret, eb, gate, passed, so, obs, rew, done, rec, tobs,
-        saved);
+        saved, mirror);
 }
 
 template <int INTEG, int ACT, bool LAG>
@@ -616,7 +633,7 @@ int vf_env_step_fwd(const VfParams* params, const VfEnvSpec* spec, int n, int su
                     const float* state_in, const float* action, const float* reset_table, int* step_count,
                     float* returns, unsigned char* ebits, int* gate, int* gates_passed, float* state_out,
                     float* obs_out, float* reward_out, unsigned char* done_out, float* record_out,
-                    float* term_obs_out, int* saved_out, void* stream) {
+                    float* term_obs_out, int* saved_out, const VfEnvMirror* host_mirror, void* stream) {
     if (check_common(params, n, substeps, integrator, action_type)) return 1;
     if (check_spec(spec)) return 1;
     if (n == 0) return 0;
@@ -629,10 +646,37 @@ int vf_env_step_fwd(const VfParams* params, const VfEnvSpec* spec, int n, int su
     if (!aligned16(state_in) || !aligned16(action) || !aligned16(state_out) || !aligned16(obs_out) ||
         !aligned16(record_out))
         return fail("all float4 buffers must be 16-byte aligned");
+    // page-locked host destinations -> their device aliases (identity under unified addressing; an error here means
+    // the caller passed pageable memory)
+    VfEnvMirror mirror = {nullptr, nullptr, nullptr};
+    if (host_mirror) {
+        void* d = nullptr;
+        if (host_mirror->obs) {
+            if (cudaHostGetDevicePointer(&d, host_mirror->obs, 0) != cudaSuccess || !aligned16(d)) {
+                (void)cudaGetLastError();
+                return fail("host_mirror.obs must be page-locked (cudaHostAlloc / cudaHostRegister) and 16-byte aligned");
+            }
+            mirror.obs = static_cast<float*>(d);
+        }
+        if (host_mirror->reward) {
+            if (cudaHostGetDevicePointer(&d, host_mirror->reward, 0) != cudaSuccess) {
+                (void)cudaGetLastError();
+                return fail("host_mirror.reward must be page-locked host memory");
+            }
+            mirror.reward = static_cast<float*>(d);
+        }
+        if (host_mirror->done) {
+            if (cudaHostGetDevicePointer(&d, host_mirror->done, 0) != cudaSuccess) {
+                (void)cudaGetLastError();
+                return fail("host_mirror.done must be page-locked host memory");
+            }
+            mirror.done = static_cast<int*>(d);
+        }
+    }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     VF_DISPATCH(launch_env_fwd, *params, *spec, n, substeps, env_flags, step_index, state_in, action, reset_table,
                 step_count, returns, ebits, gate, gates_passed, state_out, obs_out, reward_out, done_out, record_out,
-                term_obs_out, saved_out, st);
+                term_obs_out, saved_out, mirror, st);
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return fail("vf_env_step_fwd launch failed", err);
     return 0;

@@ -207,11 +207,27 @@ class DroneGymEnvsBase(VecEnv):
     def _fused_obs(self, obs: th.Tensor) -> TensorDict:
         return TensorDict({"state": obs})
 
+    def _fused_np_obs(self, obs: np.ndarray) -> TensorDict:
+        """numpy-mode twin of ``_fused_obs``: the kernel's host copy of the observation, plus host copies of whatever
+        else the task puts next to it (constant tensors such as the navigation target are converted once)."""
+        out = TensorDict({"state": obs})
+        cache = self.__dict__.setdefault("_np_const", {})
+        for k, v in self._obs_tensors.items():
+            if k == "state":
+                continue
+            hit = cache.get(k)
+            if hit is None or hit[0] is not v:
+                hit = cache[k] = (v, v.detach().cpu().numpy())
+            out[k] = hit[1]
+        return out
+
     def _step_fused(self):
         from .fused import RecordInfo
         if self.requires_grad and not self.tensor_output:
             raise ValueError("requires_grad should be False if tensor_output is False")
-        obs, reward, done, record, term = self._fused.step(self._action, grad=self.requires_grad)
+        slot = None if self.tensor_output else self._fused.host_slot()
+        obs, reward, done, record, term = self._fused.step(self._action, grad=self.requires_grad,
+                                                           mirror=None if slot is None else slot["ref"])
         self._obs_tensors = self._fused_obs(obs)
         term_obs = self._fused_obs(term) if term is not None else {}
         info = RecordInfo(self.num_agent, record, term_obs, self.envs.dynamics.ctrl_dt,
@@ -220,7 +236,12 @@ class DroneGymEnvsBase(VecEnv):
         if self.tensor_output:                   # kernel outputs never carry autograd history: nothing to detach
             self._observations = self._obs_tensors
             return self._obs_tensors, reward, done, info
-        return self._format_step_output(reward, done, info)
+        # numpy mode (reference droneGymEnv.py:218): the kernel has already written obs / reward / done into the
+        # page-locked host slot (zero-copy stores over PCIe); one stream synchronisation makes them readable
+        th.cuda.current_stream(self.device).synchronize()
+        np_obs, np_reward, np_done = slot["np"]
+        self._observations = self._fused_np_obs(np_obs)
+        return self._observations, np_reward, np_done, info
 
     def _snapshot_info(self) -> LazyInfo:
         return LazyInfo(self.num_agent, self._done, self._episode_done, self._success, self._step_count,
@@ -282,6 +303,10 @@ class DroneGymEnvsBase(VecEnv):
         if isinstance(action, th.Tensor) and action.is_cuda:
             return action.to(self.device, dtype=th.float32)
         src = action if isinstance(action, th.Tensor) else th.as_tensor(np.asarray(action))
+        if not self.tensor_output and src.dtype == th.float32 and src.is_contiguous() and src.is_pinned():
+            # numpy mode ends every step with a stream synchronisation, so the DMA engine may read the caller's
+            # page-locked array directly (no host-side staging copy)
+            return src.to(self.device, non_blocking=True)
         pin = getattr(self, "_act_pin", None)
         if pin is None or pin.shape != src.shape:
             pin = self._act_pin = th.empty(src.shape, dtype=th.float32, pin_memory=True)
@@ -294,7 +319,7 @@ class DroneGymEnvsBase(VecEnv):
         self._act_evt.record(th.cuda.current_stream(self.device))
         return dev
 
-    _TRANSIENT = ("_host_ring", "_host_turn", "_act_pin", "_act_evt")
+    _TRANSIENT = ("_host_ring", "_host_turn", "_act_pin", "_act_evt", "_np_const")
 
     def __deepcopy__(self, memo):
         """Deep-copyable like the reference env (utils/algorithms/shac.py:121); host staging buffers and CUDA

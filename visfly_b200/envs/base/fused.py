@@ -142,7 +142,7 @@ class FusedEnvStep:
         self._fn = None
         self._bind()
 
-    _CTYPES_REFS = ("_fn", "_params_ref", "_spec_ref")
+    _CTYPES_REFS = ("_fn", "_params_ref", "_spec_ref", "_host_ring", "_host_turn")
 
     def __deepcopy__(self, memo):
         """ctypes references are per-object handles: the copy re-creates them against its own env / spec."""
@@ -235,8 +235,9 @@ class FusedEnvStep:
         self.active = False
 
     # -- the step -------------------------------------------------------------------------------------------
-    def _launch(self, state_in: th.Tensor, action: th.Tensor, want_saved: bool):
-        """Allocate the step's outputs and launch ``vf_env_step_fwd`` (status buffers are updated in place)."""
+    def _launch(self, state_in: th.Tensor, action: th.Tensor, want_saved: bool, mirror=None):
+        """Allocate the step's outputs and launch ``vf_env_step_fwd`` (status buffers are updated in place).
+        ``mirror``: ``ctypes.byref(VfEnvMirror)`` of page-locked host destinations for obs / reward / done, or None."""
         env, dyn, n, dev = self.env, self.env.envs.dynamics, self.n, self.device
         state_out = th.empty_like(state_in)
         obs = th.empty((n, self.obs_width), dtype=th.float32, device=dev)
@@ -255,13 +256,30 @@ class FusedEnvStep:
                       None if self.table is None else self.table.data_ptr(), self._p_sc, self._p_ret, self._p_eb,
                       self._p_gate, self._p_passed, state_out.data_ptr(), obs.data_ptr(), reward.data_ptr(),
                       done.data_ptr(), record.data_ptr(), None if term is None else term.data_ptr(),
-                      None if saved is None else saved.data_ptr(), _raw_stream(dev.index))
+                      None if saved is None else saved.data_ptr(), mirror, _raw_stream(dev.index))
         if rc != 0:
             raise RuntimeError("visfly_b200: " + _lib.load().vf_last_error().decode())
         self.global_step += 1
         return state_out, obs, reward, done, record, term, saved
 
-    def step(self, action: th.Tensor, grad: bool = False):
+    def host_slot(self):
+        """Page-locked host destinations of obs / reward / done for the numpy output mode: two alternating sets (the
+        arrays handed out by the previous step stay valid for one more step), each with its ``VfEnvMirror``."""
+        ring = getattr(self, "_host_ring", None)
+        if ring is None:
+            ring = []
+            for _ in range(2):
+                obs = th.empty((self.n, self.obs_width), dtype=th.float32, pin_memory=True)
+                reward = th.empty((self.n,), dtype=th.float32, pin_memory=True)
+                done = th.empty((self.n,), dtype=th.int32, pin_memory=True)
+                m = P.VfEnvMirror(obs.data_ptr(), reward.data_ptr(), done.data_ptr())
+                ring.append({"obs": obs, "reward": reward, "done": done, "mirror": m, "ref": ctypes.byref(m),
+                             "np": (obs.numpy(), reward.numpy(), done.numpy())})
+            self._host_ring, self._host_turn = ring, 0
+        self._host_turn ^= 1
+        return ring[self._host_turn]
+
+    def step(self, action: th.Tensor, grad: bool = False, mirror=None):
         """One env step = one launch.  ``grad=True`` routes through ``EnvControlStep`` so that the returned state,
         observation and reward carry autograd history (backward = one launch of ``vf_env_step_bwd``)."""
         env, dyn = self.env, self.env.envs.dynamics
@@ -278,7 +296,7 @@ class FusedEnvStep:
         if grad:
             state_out, obs, reward, done, record, term = EnvControlStep.apply(state_in, action, self)
         else:
-            state_out, obs, reward, done, record, term, _ = self._launch(state_in, action, False)
+            state_out, obs, reward, done, record, term, _ = self._launch(state_in, action, False, mirror)
         # keep the Dynamics object coherent (lazy views, diagnostics)
         dyn._prev = (state_in.detach(), action.detach()) if grad else (state_in, action)
         dyn._state = state_out

@@ -262,3 +262,8 @@ class VfEnvSpec(ctypes.Structure):
         ("init_motor_omega", ctypes.c_float),
         ("seed", ctypes.c_ulonglong),
     ]
+
+
+class VfEnvMirror(ctypes.Structure):
+    """ctypes mirror of ``struct VfEnvMirror``: page-locked host destinations of obs / reward / done (numpy mode)."""
+    _fields_ = [("obs", ctypes.c_void_p), ("reward", ctypes.c_void_p), ("done", ctypes.c_void_p)]
