@@ -321,16 +321,33 @@ def run_ours(args):
                          "frac": FLOP_PER_AGENT_STEP * n / k_avg / 1e12 / FP32_PEAK_TFLOPS,
                          "note": "RK4 x8 is fp32-pipe/latency bound (23 FLOP/B, ridge ~11.5), SURVEY.md §8d"}}
 
+    # the same kernel with the page-locked host mirror as a second destination (what the e2e step launches)
+    from visfly_b200.params import VfEnvMirror
+    m_obs, m_rew = th.empty((n, 13), pin_memory=True), th.empty(n, pin_memory=True)
+    m_done = th.empty(n, dtype=th.int32, pin_memory=True)
+    mirror = VfEnvMirror(m_obs.data_ptr(), m_rew.data_ptr(), m_done.data_ptr())
+
+    def kernel_mirror(i):
+        _lib.env_step_fwd(cfg.params, fz.spec, cfg.substeps, cfg.integrator, cfg.action_type, cfg.flags, 0, 20_000 + i,
+                          st_in, acts[i % pool], None, sc, ret, eb, None, None, st_out, obs_out, rew_o, done_o, rec_o,
+                          None, None, mirror)
+
+    for i in range(5):
+        kernel_mirror(i)
+    km_avg = float(np.mean(timed_steps(kernel_mirror, 50, flush, stream))) * 1e-3
+
     # ---- e2e: numpy in / numpy out through the public env API -------------------------------------------
     env_np = HoverEnv(num_agent_per_scene=n, visual=False, device=dev, dynamics_kwargs=dict(DYN), seed=142 + rank,
                       max_episode_steps=256, tensor_output=False)
     env_np.reset()
     host_acts = [th.empty((n, 4), pin_memory=True).copy_(acts[i].cpu()).numpy() for i in range(pool)]
-    sink = np.zeros(n, dtype=np.float64)
+    sink = [0.0, 0.0, 0]
 
     def e2e_step(i):
         obs, reward, done, info = env_np.step(host_acts[i % pool])
-        sink[:] += reward                                     # the host really consumes the result
+        sink[0] += float(reward[0]) + float(reward[-1])        # the host really reads what came back
+        sink[1] += float(obs["state"][0, 2]) + float(obs["state"][-1, 2])
+        sink[2] += int(done[0]) + int(done[-1])
 
     for i in range(W):
         e2e_step(i)
@@ -345,6 +362,8 @@ def run_ours(args):
     e2e = {"value": world * n * K / float(e2e_s), "unit": UNIT, "h2d_bytes_per_step": n * 16,
            "d2h_bytes_per_step": n * (13 * 4 + 4 + 4), "ms_per_step": 1e3 * float(e2e_s) / K,
            "api": "HoverEnv(tensor_output=False).step(numpy actions) -> numpy obs/reward/done",
+           "kernel_with_host_mirror_us": km_avg * 1e6,
+           "pcie_write_gbs_of_that_kernel": n * (13 * 4 + 4 + 4) / km_avg / 1e9,
            "transfers": "H2D: async DMA of the page-locked action array; D2H: the kernel stores obs/reward/done "
                         "straight into page-locked host memory (zero-copy over PCIe), one stream sync per step"}
 

@@ -49,6 +49,8 @@ extern "C" {
 /* action type: values of reference utils/type.py:14-18 ACTION_TYPE */
 #define VF_ACTION_THRUST   0
 #define VF_ACTION_BODYRATE 1
+#define VF_ACTION_VELOCITY 2   /* [-, vx, vy, vz] set-point, yaw follows the velocity   dynamics.py:414-454 */
+#define VF_ACTION_POSITION 3   /* [yaw, x, y, z] set-point                              dynamics.py:455-496 */
 
 /* flags */
 #define VF_FLAG_CTRL_DELAY 1u  /* first-order motor lag, reference dynamics.py:510-516; off => T = T_des (:518) */
@@ -85,6 +87,11 @@ typedef struct VfParams {
     float pos_hi[3];
     float vel_lim;
     float rate_lim;
+    /* outer loops of the velocity / position action types (geometric attitude controller) */
+    float Kp[9];           /* Kp of the body-rate PID (un-multiplied by J)       :452, :486-491      */
+    float vel_kp;          /* VELOCITY_PID.p                                      :416                */
+    float vel_kd;          /* VELOCITY_PID.d                                      :433, :458          */
+    float pos_kd;          /* POSITION_PID.d                                      :457, :469          */
 } VfParams;
 
 int         vf_abi_version(void);
@@ -119,6 +126,9 @@ int vf_step_fwd(const VfParams* params, int n, int substeps, int integrator, int
  *
  * torch.autograd conventions are reproduced exactly: clamp passes gradient on the
  * closed interval, d(v|v|)/dv = 2|v|.  substeps must be <= VF_MAX_SUBSTEPS_BWD.
+ * Only VF_ACTION_THRUST / VF_ACTION_BODYRATE: the reference's own autograd graph is broken for the velocity and
+ * position action types (in-place row writes in a per-agent loop, dynamics.py:446-450 — backward raises), so
+ * there is no gradient to be faithful to; the call returns an error for them.
  */
 int vf_step_bwd(const VfParams* params, int n, int substeps, int integrator, int action_type,
                 unsigned flags, const float* state_in, const float* action,

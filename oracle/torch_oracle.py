@@ -115,6 +115,18 @@ class OracleModel:
         self.acc_mean = th.atleast_1d(acc_max - self.acc_half * 1)
         self.rate_half = th.atleast_1d((rate_max - rate_min) / 2)
         self.rate_mean = th.atleast_1d(rate_max - self.rate_half * 1)
+        # velocity / position action types: outer-loop gains and set-point scaling        dynamics.py:574-575, :655-687
+        self.vel_p, self.vel_d = t(d["VELOCITY_PID"]["p"]), t(d["VELOCITY_PID"]["d"])
+        self.pos_d = t(d["POSITION_PID"]["d"])
+        spd_max, pos_max = t(d["max_spd"]), t(d["max_pos"])
+        self.spd_half = th.atleast_1d((spd_max - (-spd_max)) / 2)
+        self.spd_mean = th.atleast_1d(spd_max - self.spd_half * 1)
+        self.pos_half = th.atleast_1d((pos_max - (-pos_max)) / 2)
+        self.pos_mean = th.atleast_1d(pos_max - self.pos_half * 1)
+        yaw_scale = th.as_tensor(th.pi - (-th.pi), dtype=dtype) / 2
+        self.yaw_mean = th.atleast_1d(th.pi - yaw_scale * 1)
+        self.yaw_half_velocity = self.yaw_mean.clone()       # the reference passes half=yaw_bias here (:671)
+        self.yaw_half_position = th.atleast_1d(yaw_scale)
         for k, v in list(vars(self).items()):
             if isinstance(v, th.Tensor):
                 setattr(self, k, v.to(device))
@@ -132,7 +144,8 @@ class OracleModel:
 # the control step
 # ---------------------------------------------------------------------------------------------------
 class OracleDynamics:
-    """Restatement of reference ``Dynamics`` for action types ``bodyrate`` and ``thrust``.
+    """Restatement of reference ``Dynamics`` for the four action types (``velocity`` / ``position``: forward
+    only — the reference's own backward raises there, and its per-agent Python loop is kept as a loop).
 
     State is held like the reference holds it: ``pos/vel/ang_vel/ang_acc (3,N)``, ``motor/thrusts (4,N)``,
     quaternion as four ``(N,)`` tensors, ``t (N,)``, FIFO of ``(4,N)`` delayed actions.
@@ -142,7 +155,7 @@ class OracleDynamics:
                  ctrl_delay: bool = True, comm_delay: float = 0.06, integrator: str = "euler",
                  cfg: str = "drone_state", wind: Sequence[float] = (0, 0, 0), device="cpu",
                  dtype=th.float32, random_reset_time: bool = False):
-        assert action_type in ("bodyrate", "thrust")
+        assert action_type in ("bodyrate", "thrust", "velocity", "position")
         assert integrator in ("euler", "rk4")
         self.num, self.action_type, self.integrator = num, action_type, integrator
         self.random_reset_time = random_reset_time     # reference quirk C9: partial reset draws t ~ U(0, 6.28)
@@ -236,16 +249,76 @@ class OracleDynamics:
             cmd = th.hstack([(action[:, :1] * M.acc_half + M.acc_mean) * M.m,
                              action[:, 1:] * M.rate_half + M.rate_mean])
             return cmd.T
-        return M.m * (action * M.acc_half + M.acc_mean).T
+        if self.action_type == "thrust":
+            return M.m * (action * M.acc_half + M.acc_mean).T
+        if self.action_type == "velocity":                                        # dynamics.py:714-720 (N,4)
+            return th.hstack([action[:, :1] * M.yaw_half_velocity + M.yaw_mean,
+                              action[:, 1:] * M.spd_half + M.spd_mean])
+        return th.hstack([action[:, :1] * M.yaw_half_position + M.yaw_mean,       # dynamics.py:722-728
+                          action[:, 1:] * M.pos_half + M.pos_mean])
 
-    def _thrust_des(self, cmd):                                                   # dynamics.py:398-413, :501
+    def _yaw(self):                                                               # maths.py:248
+        w, x, y, z = self.q
+        return th.atan2(2 * (w * z + x * y), 1 - 2 * (y.pow(2) + z.pow(2)))
+
+    def _R(self):                                                                 # maths.py:113-117
+        w, x, y, z = self.q
+        return th.stack([
+            th.stack([1 - 2 * (y.pow(2) + z.pow(2)), 2 * (x * y - z * w), 2 * (x * z + y * w)]),
+            th.stack([2 * (x * y + z * w), 1 - 2 * (x.pow(2) + z.pow(2)), 2 * (y * z - x * w)]),
+            th.stack([2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x.pow(2) + y.pow(2))])])
+
+    def _geometric(self, F_des, yaw_des, yaw_spd_des):
+        """Desired frame, attitude / rate errors (dynamics.py:435-450, :471-485), incl. the per-agent loop."""
+        gross = q_inv_rotate(self.q, F_des)[2]
+        R = self._R()
+        b3 = F_des / F_des.norm(dim=0)
+        c1 = th.stack([yaw_des.cos(), yaw_des.sin(), th.zeros_like(yaw_des)], dim=0)
+        b2 = cross3(b3, c1)
+        b2 = b2 / b2.norm(dim=0)
+        b1 = cross3(b2, b3)
+        R_des = th.stack([b1, b2, b3]).transpose(0, 1)
+        pose_err, rate_err = th.zeros_like(self.pos), th.zeros_like(self.pos)
+        for i in range(self.num):
+            m = 0.5 * (R_des[..., i].T @ R[..., i] - R[..., i].T @ R_des[..., i])
+            pose_err[:, i] = -th.as_tensor([-m[1, 2], m[0, 2], -m[0, 1]], device=self.device)
+            rate_err[:, i] = (R_des[..., i].T @ R[..., i]
+                              @ th.tensor([[0], [0], [yaw_spd_des[i]]], device=self.device, dtype=self.dtype).squeeze()
+                              - self.ang_vel[:, i])
+        return gross, pose_err, rate_err
+
+    def _thrust_des(self, cmd):                                                   # dynamics.py:398-501
         M = self.M
         if self.action_type == "bodyrate":
             err = cmd[1:] - self.ang_vel
             tau_des = M.J @ M.Kp @ err + cross3(self.ang_vel + 0, M.J @ (self.ang_vel + 0)) - M.Kd @ self.ang_acc
             t_des = M.B_inv @ th.cat([cmd[0:1, :], tau_des])
-        else:
+        elif self.action_type == "thrust":
             t_des = cmd
+        elif self.action_type == "velocity":                                      # dynamics.py:414-454
+            cmd = cmd.T
+            a_des = M.vel_p * (cmd[1:] - self.vel)
+            F_des = M.m * (a_des - M.g)
+            vh = self.vel[:2, :]
+            yaw = self._yaw()
+            yaw_des = th.where(vh.norm(dim=0) > 0.1, th.atan2(vh[1], vh[0]), yaw)
+            err = yaw_des - yaw
+            err = th.atan2(th.sin(err), th.cos(err))
+            gross, pose_err, rate_err = self._geometric(F_des, yaw_des, err * M.vel_d * 2.0)
+            tau_des = M.J @ (M.Kp @ pose_err + M.Kp @ rate_err - cross3(self.ang_vel, self.ang_vel))
+            t_des = M.B_inv @ th.vstack([gross, tau_des])
+        else:                                                                     # dynamics.py:455-496
+            cmd = cmd.T
+            v_des = M.pos_d * (cmd[1:] - self.pos)
+            a_des = M.vel_d * (v_des - self.vel)
+            F_des = M.m * (a_des - M.g)
+            yaw_des = cmd[0]
+            err = yaw_des - self._yaw()
+            err = th.atan2(th.sin(err), th.cos(err))
+            gross, pose_err, rate_err = self._geometric(F_des, yaw_des, err * M.pos_d * 2.0)
+            tau_des = M.J @ (M.Kp @ pose_err + 1.2 * M.Kp @ rate_err - M.Kd @ self.ang_acc
+                             - cross3(self.ang_vel, M.J @ self.ang_vel))
+            t_des = M.B_inv @ th.vstack([gross, tau_des])
         return th.clamp(t_des, M.thrust_min, M.thrust_max)
 
     def _derivs(self, vel, q, acc, w, tau):                                       # maths.py:300-315

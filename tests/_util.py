@@ -18,12 +18,13 @@ from visfly_b200.type import ACTION_TYPE  # noqa: E402
 from oracle.torch_oracle import OracleDynamics  # noqa: E402
 
 INTEGRATOR = {"euler": 0, "rk4": 1}
-ACTION = {"thrust": 0, "bodyrate": 1}
+ACTION = {"thrust": 0, "bodyrate": 1, "velocity": 2, "position": 3}
 FLAG_CTRL_DELAY = 1
 
 
 def vf_params(action_type="bodyrate", dt=0.005, cfg="drone_state", wind=(0.0, 0.0, 0.0)) -> VfParams:
-    at = ACTION_TYPE.BODYRATE if action_type == "bodyrate" else ACTION_TYPE.THRUST
+    at = {"bodyrate": ACTION_TYPE.BODYRATE, "thrust": ACTION_TYPE.THRUST, "velocity": ACTION_TYPE.VELOCITY,
+          "position": ACTION_TYPE.POSITION}[action_type]
     model = load_drone_model(cfg, dt)
     return build_vf_params(model, at, action_scaling(model, at), wind)
 

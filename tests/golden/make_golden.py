@@ -40,8 +40,15 @@ CONFIGS = {
     # 12 sub-steps (the reference's default ctrl_dt).  float32 only: the reference's own `ctrl_dt % dt == 0`
     # check (dynamics.py:71) is evaluated in the default dtype and rejects 0.03 / 0.0025 in float64.
     "rk4_s12": dict(action_type="bodyrate", integrator="rk4", dt=0.0025, ctrl_dt=0.03, comm_delay=0.06, ctrl_delay=True),
+    # velocity / position set-points (geometric attitude controller, reference dynamics.py:414-496).  Forward only:
+    # the reference's backward raises on this branch (in-place writes in its per-agent loop, :446-450).
+    "euler_velocity": dict(action_type="velocity", integrator="euler", dt=0.005, ctrl_dt=0.02, comm_delay=0.06, ctrl_delay=True),
+    "rk4_velocity": dict(action_type="velocity", integrator="rk4", dt=0.0025, ctrl_dt=0.02, comm_delay=0.0, ctrl_delay=True),
+    "euler_position": dict(action_type="position", integrator="euler", dt=0.005, ctrl_dt=0.02, comm_delay=0.0, ctrl_delay=False),
+    "rk4_position": dict(action_type="position", integrator="rk4", dt=0.0025, ctrl_dt=0.02, comm_delay=0.06, ctrl_delay=True),
 }
 F32_ONLY = {"rk4_s12"}
+FWD_ONLY = {"euler_velocity", "rk4_velocity", "euler_position", "rk4_position"}
 
 
 def dtypes_for(name):
@@ -174,11 +181,16 @@ def main():
     if not reference_available():
         raise SystemExit("reference tree not found; golden vectors can only be regenerated where it is mounted")
     th.manual_seed(0)
-    make_kat()
+    only = sys.argv[1:]                       # optional: names of the configs to (re)generate
+    if not only:
+        make_kat()
     for name, kw in CONFIGS.items():
+        if only and name not in only:
+            continue
         make_traj(name, kw)
         make_step(name, kw)
-        make_grad(name, kw)
+        if name not in FWD_ONLY:
+            make_grad(name, kw)
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")

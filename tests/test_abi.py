@@ -52,8 +52,11 @@ def test_argument_validation_needs_no_gpu():
     assert b"substeps" in lib.vf_last_error()
     assert lib.vf_step_fwd(ctypes.byref(p), 4, 4, 7, 1, 1, None, None, None, None, None, None) != 0
     assert b"integrator" in lib.vf_last_error()
-    assert lib.vf_step_fwd(ctypes.byref(p), 4, 4, 0, 3, 1, None, None, None, None, None, None) != 0
+    assert lib.vf_step_fwd(ctypes.byref(p), 4, 4, 0, 4, 1, None, None, None, None, None, None) != 0
     assert b"action_type" in lib.vf_last_error()
+    # velocity (2) / position (3) run forward only: the adjoint entry points refuse them
+    assert lib.vf_step_bwd(ctypes.byref(p), 4, 4, 0, 3, 1, None, None, None, None, None, None, None) != 0
+    assert b"no gradient for the velocity / position" in lib.vf_last_error()
     assert lib.vf_step_fwd(ctypes.byref(p), 4, 4, 0, 1, 1, None, None, None, None, None, None) != 0
     assert b"NULL" in lib.vf_last_error()
     assert lib.vf_step_bwd(ctypes.byref(p), 4, 65, 0, 1, 1, None, None, None, None, None, None, None) != 0

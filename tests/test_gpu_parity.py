@@ -19,7 +19,12 @@ CONFIGS = {
     "rk4_nolag": dict(action_type="bodyrate", integrator="rk4", dt=0.0025, ctrl_dt=0.02, comm_delay=0.0, ctrl_delay=False),
     "euler_thrust": dict(action_type="thrust", integrator="euler", dt=0.005, ctrl_dt=0.02, comm_delay=0.0, ctrl_delay=True),
     "rk4_s12": dict(action_type="bodyrate", integrator="rk4", dt=0.0025, ctrl_dt=0.03, comm_delay=0.06, ctrl_delay=True),
+    "euler_velocity": dict(action_type="velocity", integrator="euler", dt=0.005, ctrl_dt=0.02, comm_delay=0.06, ctrl_delay=True),
+    "rk4_velocity": dict(action_type="velocity", integrator="rk4", dt=0.0025, ctrl_dt=0.02, comm_delay=0.0, ctrl_delay=True),
+    "euler_position": dict(action_type="position", integrator="euler", dt=0.005, ctrl_dt=0.02, comm_delay=0.0, ctrl_delay=False),
+    "rk4_position": dict(action_type="position", integrator="rk4", dt=0.0025, ctrl_dt=0.02, comm_delay=0.06, ctrl_delay=True),
 }
+FWD_ONLY = {"euler_velocity", "rk4_velocity", "euler_position", "rk4_position"}   # the reference's backward raises there
 TRAJ_TOL = 1e-5      # north-star: state trajectories within 1e-5 rel-L2 of the reference
 GRAD_TOL = 1e-4      # north-star: analytic gradients within 1e-4 of PyTorch autograd
 
@@ -55,10 +60,11 @@ def make_dynamics(n, **kw):
 
 # -- one step, seeded inputs, all kernel variants ---------------------------------------------------------
 @pytest.mark.parametrize("integ,dt", [("euler", 0.005), ("rk4", 0.0025)])
-@pytest.mark.parametrize("at", ["bodyrate", "thrust"])
+@pytest.mark.parametrize("at", ["bodyrate", "thrust", "velocity", "position"])
 @pytest.mark.parametrize("lag", [True, False])
 def test_forward_one_step_vs_oracle(integ, dt, at, lag):
-    n, S, wind = 1000, int(0.02 / dt), (0.3, -0.2, 0.1)          # 1000: ragged last warp and last CTA
+    # 1000: ragged last warp and last CTA (velocity / position: the oracle keeps the reference's per-agent loop)
+    n, S, wind = 1000 if at in ("bodyrate", "thrust") else 200, int(0.02 / dt), (0.3, -0.2, 0.1)
     P = vf_params(at, dt, wind=wind)
     packed = pack(*random_flight_state(n, seed=3))
     g = th.Generator().manual_seed(5)
@@ -203,7 +209,19 @@ def _hover_loss(dyn, acts, gamma=0.99):
     return -total.mean()
 
 
-@pytest.mark.parametrize("cfg", list(CONFIGS))
+@pytest.mark.parametrize("at", ["velocity", "position"])
+def test_velocity_and_position_have_no_gradient_like_the_reference(at):
+    """The reference's backward raises for these action types (in-place writes in its per-agent loop,
+    dynamics.py:446-450); the engine runs them forward and refuses the adjoint with a clear error."""
+    d = make_dynamics(8, action_type=at, integrator="rk4", dt=0.0025, ctrl_dt=0.02)
+    a = th.zeros(8, 4, device="cuda", requires_grad=True)
+    s = d.step(a)
+    assert s.shape == (8, 13) and bool(th.isfinite(s).all())
+    with pytest.raises(RuntimeError, match="no gradient for the velocity / position"):
+        s.sum().backward()
+
+
+@pytest.mark.parametrize("cfg", [c for c in CONFIGS if c not in FWD_ONLY])
 def test_rollout_gradients_vs_reference_autograd_golden(cfg):
     """8-step BPTT through the drop-in Dynamics + autograd.Function against gradients recorded from
     torch.autograd through the real reference (tests/golden/grad_*.npz)."""

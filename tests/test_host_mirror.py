@@ -17,6 +17,10 @@ STEP_CFG = {
     "rk4_nolag": ("bodyrate", "rk4", 0.0025, 0.02, False),
     "euler_thrust": ("thrust", "euler", 0.005, 0.02, True),
     "rk4_s12": ("bodyrate", "rk4", 0.0025, 0.03, True),
+    "euler_velocity": ("velocity", "euler", 0.005, 0.02, True),
+    "rk4_velocity": ("velocity", "rk4", 0.0025, 0.02, True),
+    "euler_position": ("position", "euler", 0.005, 0.02, False),
+    "rk4_position": ("position", "rk4", 0.0025, 0.02, True),
 }
 
 

@@ -16,7 +16,12 @@ CONFIGS = {
     "rk4_nolag": dict(action_type="bodyrate", integrator="rk4", dt=0.0025, ctrl_dt=0.02, comm_delay=0.0, ctrl_delay=False),
     "euler_thrust": dict(action_type="thrust", integrator="euler", dt=0.005, ctrl_dt=0.02, comm_delay=0.0, ctrl_delay=True),
     "rk4_s12": dict(action_type="bodyrate", integrator="rk4", dt=0.0025, ctrl_dt=0.03, comm_delay=0.06, ctrl_delay=True),
+    "euler_velocity": dict(action_type="velocity", integrator="euler", dt=0.005, ctrl_dt=0.02, comm_delay=0.06, ctrl_delay=True),
+    "rk4_velocity": dict(action_type="velocity", integrator="rk4", dt=0.0025, ctrl_dt=0.02, comm_delay=0.0, ctrl_delay=True),
+    "euler_position": dict(action_type="position", integrator="euler", dt=0.005, ctrl_dt=0.02, comm_delay=0.0, ctrl_delay=False),
+    "rk4_position": dict(action_type="position", integrator="rk4", dt=0.0025, ctrl_dt=0.02, comm_delay=0.06, ctrl_delay=True),
 }
+FWD_ONLY = {"euler_velocity", "rk4_velocity", "euler_position", "rk4_position"}   # the reference's backward raises there
 DT = {"f32": th.float32, "f64": th.float64}
 
 
@@ -94,7 +99,7 @@ def hover_loss(dyn, acts, gamma=0.99):
     return -total.mean()
 
 
-@pytest.mark.parametrize("cfg", list(CONFIGS))
+@pytest.mark.parametrize("cfg", [c for c in CONFIGS if c not in FWD_ONLY])
 def test_oracle_gradients_match_reference_autograd_golden(cfg):
     z = load(f"grad_{cfg}.npz")
     for tag in tags(z, "grad_actions"):

@@ -454,14 +454,17 @@ int block_override() {
 
 bool aligned16(const void* p) { return (reinterpret_cast<size_t>(p) & 15u) == 0; }
 
-int check_common(const VfParams* params, int n, int substeps, int integrator, int action_type) {
+int check_common(const VfParams* params, int n, int substeps, int integrator, int action_type, bool backward = false) {
     if (!params) return fail("params is NULL");
     if (n < 0) return fail("n must be >= 0");
     if (substeps < 1) return fail("substeps must be >= 1");
     if (integrator != VF_INTEGRATOR_EULER && integrator != VF_INTEGRATOR_RK4)
         return fail("integrator must be VF_INTEGRATOR_EULER or VF_INTEGRATOR_RK4");
-    if (action_type != VF_ACTION_THRUST && action_type != VF_ACTION_BODYRATE)
-        return fail("action_type must be VF_ACTION_THRUST or VF_ACTION_BODYRATE");
+    if (action_type < VF_ACTION_THRUST || action_type > VF_ACTION_POSITION)
+        return fail("action_type must be a VF_ACTION_* value");
+    if (backward && action_type != VF_ACTION_THRUST && action_type != VF_ACTION_BODYRATE)
+        return fail("no gradient for the velocity / position action types: the reference's autograd graph is broken "
+                    "there (in-place writes in a per-agent loop, envs/base/dynamics.py:446-450)");
     return 0;
 }
 
@@ -526,6 +529,33 @@ void launch_env_bwd(const VfParams& p, const VfEnvSpec& e, int n, int substeps, 
         vf_env_step_bwd_kernel<INTEG, ACT, LAG, VF_MAX_SUBSTEPS_BWD, kBlock><<<grid, kBlock, 0, st>>>(p, e, n, substeps, env_flags, si, a, saved, gso, gobs, gr, gsi, ga);
 }
 
+// forward-only dispatch: all four action types
+#define VF_DISPATCH_FWD(FN, ...)                                                              \
+    do {                                                                                      \
+        if (action_type == VF_ACTION_VELOCITY || action_type == VF_ACTION_POSITION) {         \
+            const bool lag = (flags & VF_FLAG_CTRL_DELAY) != 0;                               \
+            if (integrator == VF_INTEGRATOR_RK4) {                                            \
+                if (action_type == VF_ACTION_VELOCITY) {                                      \
+                    if (lag) FN<VF_INTEGRATOR_RK4, VF_ACTION_VELOCITY, true>(__VA_ARGS__);    \
+                    else     FN<VF_INTEGRATOR_RK4, VF_ACTION_VELOCITY, false>(__VA_ARGS__);   \
+                } else {                                                                      \
+                    if (lag) FN<VF_INTEGRATOR_RK4, VF_ACTION_POSITION, true>(__VA_ARGS__);    \
+                    else     FN<VF_INTEGRATOR_RK4, VF_ACTION_POSITION, false>(__VA_ARGS__);   \
+                }                                                                             \
+            } else {                                                                          \
+                if (action_type == VF_ACTION_VELOCITY) {                                      \
+                    if (lag) FN<VF_INTEGRATOR_EULER, VF_ACTION_VELOCITY, true>(__VA_ARGS__);  \
+                    else     FN<VF_INTEGRATOR_EULER, VF_ACTION_VELOCITY, false>(__VA_ARGS__); \
+                } else {                                                                      \
+                    if (lag) FN<VF_INTEGRATOR_EULER, VF_ACTION_POSITION, true>(__VA_ARGS__);  \
+                    else     FN<VF_INTEGRATOR_EULER, VF_ACTION_POSITION, false>(__VA_ARGS__); \
+                }                                                                             \
+            }                                                                                 \
+        } else {                                                                              \
+            VF_DISPATCH(FN, __VA_ARGS__);                                                     \
+        }                                                                                     \
+    } while (0)
+
 #define VF_DISPATCH(FN, ...)                                                                  \
     do {                                                                                      \
         const bool lag = (flags & VF_FLAG_CTRL_DELAY) != 0;                                   \
@@ -579,7 +609,7 @@ int vf_step_fwd(const VfParams* params, int n, int substeps, int integrator, int
         !aligned16(ext_out))
         return fail("all buffers must be 16-byte aligned");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    VF_DISPATCH(launch_fwd, *params, n, substeps, state_in, action, state_out, obs_out, ext_out, st);
+    VF_DISPATCH_FWD(launch_fwd, *params, n, substeps, state_in, action, state_out, obs_out, ext_out, st);
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return fail("vf_step_fwd launch failed", err);
     return 0;
@@ -588,7 +618,7 @@ int vf_step_fwd(const VfParams* params, int n, int substeps, int integrator, int
 int vf_step_bwd(const VfParams* params, int n, int substeps, int integrator, int action_type, unsigned flags,
                 const float* state_in, const float* action, const float* grad_state_out, const float* grad_obs,
                 float* grad_state_in, float* grad_action, void* stream) {
-    if (check_common(params, n, substeps, integrator, action_type)) return 1;
+    if (check_common(params, n, substeps, integrator, action_type, true)) return 1;
     if (substeps > VF_MAX_SUBSTEPS_BWD) return fail("substeps exceeds VF_MAX_SUBSTEPS_BWD for the reverse sweep");
     if (n == 0) return 0;
     if (!state_in || !action || !grad_state_in || !grad_action)
@@ -674,7 +704,7 @@ int vf_env_step_fwd(const VfParams* params, const VfEnvSpec* spec, int n, int su
         }
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    VF_DISPATCH(launch_env_fwd, *params, *spec, n, substeps, env_flags, step_index, state_in, action, reset_table,
+    VF_DISPATCH_FWD(launch_env_fwd, *params, *spec, n, substeps, env_flags, step_index, state_in, action, reset_table,
                 step_count, returns, ebits, gate, gates_passed, state_out, obs_out, reward_out, done_out, record_out,
                 term_obs_out, saved_out, mirror, st);
     cudaError_t err = cudaGetLastError();
@@ -686,7 +716,7 @@ int vf_env_step_bwd(const VfParams* params, const VfEnvSpec* spec, int n, int su
                     int action_type, unsigned flags, unsigned env_flags, const float* state_in, const float* action,
                     const int* saved, const float* grad_state_out, const float* grad_obs, const float* grad_reward,
                     float* grad_state_in, float* grad_action, void* stream) {
-    if (check_common(params, n, substeps, integrator, action_type)) return 1;
+    if (check_common(params, n, substeps, integrator, action_type, true)) return 1;
     if (check_spec(spec)) return 1;
     if (substeps > VF_MAX_SUBSTEPS_BWD) return fail("substeps exceeds VF_MAX_SUBSTEPS_BWD for the reverse sweep");
     if (n == 0) return 0;

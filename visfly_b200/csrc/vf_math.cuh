@@ -47,6 +47,12 @@ VF_HD float  vsqrt(float x) { return sqrtf(x); }
 VF_HD double vsqrt(double x) { return sqrt(x); }
 VF_HD float  vabs(float x) { return fabsf(x); }
 VF_HD double vabs(double x) { return fabs(x); }
+VF_HD float  vsin(float x) { return sinf(x); }
+VF_HD double vsin(double x) { return sin(x); }
+VF_HD float  vcos(float x) { return cosf(x); }
+VF_HD double vcos(double x) { return cos(x); }
+VF_HD float  vatan2(float y, float x) { return atan2f(y, x); }
+VF_HD double vatan2(double y, double x) { return atan2(y, x); }
 template <class T> VF_HD T vclamp(T x, T lo, T hi) { return x < lo ? lo : (x > hi ? hi : x); }
 // torch.clamp backward: gradient passes on the closed interval [lo, hi]
 template <class T> VF_HD T vgate(T x, T lo, T hi, T g) { return (x >= lo && x <= hi) ? g : T(0); }
@@ -64,6 +70,8 @@ template <class T> struct Params {
     T gravity[3], wind[3];
     T pos_lo[3], pos_hi[3];
     T vel_lim, rate_lim;
+    T Kp[9];
+    T vel_kp, vel_kd, pos_kd;
 
     Params() = default;
     explicit Params(const VfParams& s) {
@@ -185,10 +193,86 @@ template <class T> struct Command {
     T disc[4];    // sqrt(b^2 - 4 a (c - T_des))  (= 1 / dW_des/dT_des)
 };
 
+// Outer loops of the velocity / position action types: set-point -> desired force -> geometric attitude
+// controller -> [collective thrust, body torque]                     reference dynamics.py:414-496.
+// Forward only (the reference's autograd graph is broken on this branch: per-agent in-place writes, :446-450).
 template <class T>
-VF_HD void command_fwd(const Params<T>& P, int action_type, const T a[4], const T w[3], const T al[3],
-                       Command<T>& c) {
-    if (action_type == VF_ACTION_BODYRATE) {
+VF_HD void geometric_cmd(const Params<T>& P, int action_type, const T a[4], const T p[3], const T q[4],
+                         const T v[3], const T w[3], const T al[3], T ft[4]) {
+    T cmd[4];                                                     // [yaw, x, y, z]               :714-729
+    for (int i = 0; i < 4; ++i) cmd[i] = a[i] * P.act_half[i] + P.act_mean[i];
+    const T qw = q[0], qx = q[1], qy = q[2], qz = q[3];
+    const T yaw = vatan2(T(2) * (qw * qz + qx * qy), T(1) - T(2) * (qy * qy + qz * qz));   // maths.py:248
+    T a_des[3], yaw_des, yaw_gain;
+    if (action_type == VF_ACTION_VELOCITY) {
+        for (int i = 0; i < 3; ++i) a_des[i] = P.vel_kp * (cmd[1 + i] - v[i]);              // :416
+        const T vn = vsqrt(v[0] * v[0] + v[1] * v[1]);                                      // :421
+        yaw_des = vn > T(0.1) ? vatan2(v[1], v[0]) : yaw;                                   // :423-427
+        yaw_gain = P.vel_kd * T(2);                                                         // :433
+    } else {
+        for (int i = 0; i < 3; ++i) {
+            const T v_des = P.pos_kd * (cmd[1 + i] - p[i]);                                 // :457
+            a_des[i] = P.vel_kd * (v_des - v[i]);                                           // :458
+        }
+        yaw_des = cmd[0];                                                                   // :462
+        yaw_gain = P.pos_kd * T(2);                                                         // :469
+    }
+    T F[3];
+    for (int i = 0; i < 3; ++i) F[i] = P.mass * (a_des[i] - P.gravity[i]);                  // :417 / :459
+    T e = yaw_des - yaw;                                                                    // :430-432
+    e = vatan2(vsin(e), vcos(e));
+    const T yaw_spd = e * yaw_gain;
+    T Fb[3];
+    sandwich(q, F, T(-1), Fb);                                                              // :435 transform()
+    ft[0] = Fb[2];
+    // R(q), unit-norm form                                                                 maths.py:113-117
+    const T R[3][3] = {
+        {T(1) - T(2) * (qy * qy + qz * qz), T(2) * (qx * qy - qz * qw), T(2) * (qx * qz + qy * qw)},
+        {T(2) * (qx * qy + qz * qw), T(1) - T(2) * (qx * qx + qz * qz), T(2) * (qy * qz - qx * qw)},
+        {T(2) * (qx * qz - qy * qw), T(2) * (qy * qz + qx * qw), T(1) - T(2) * (qx * qx + qy * qy)}};
+    // desired body frame                                                                   :437-442
+    const T Fn = vsqrt(F[0] * F[0] + F[1] * F[1] + F[2] * F[2]);
+    const T b3[3] = {F[0] / Fn, F[1] / Fn, F[2] / Fn};
+    const T c1[3] = {vcos(yaw_des), vsin(yaw_des), T(0)};
+    T b2[3] = {b3[1] * c1[2] - b3[2] * c1[1], b3[2] * c1[0] - b3[0] * c1[2], b3[0] * c1[1] - b3[1] * c1[0]};
+    const T b2n = vsqrt(b2[0] * b2[0] + b2[1] * b2[1] + b2[2] * b2[2]);
+    for (int i = 0; i < 3; ++i) b2[i] = b2[i] / b2n;
+    const T b1[3] = {b2[1] * b3[2] - b2[2] * b3[1], b2[2] * b3[0] - b2[0] * b3[2], b2[0] * b3[1] - b2[1] * b3[0]};
+    // M = R_des^T R  (R_des has columns b1 b2 b3)
+    const T* bb[3] = {b1, b2, b3};
+    T M[3][3];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) M[i][j] = bb[i][0] * R[0][j] + bb[i][1] * R[1][j] + bb[i][2] * R[2][j];
+    // attitude error  -vee(0.5 (M - M^T))  and rate error                                  :446-450
+    const T pe[3] = {T(0.5) * (M[1][2] - M[2][1]), -T(0.5) * (M[0][2] - M[2][0]), T(0.5) * (M[0][1] - M[1][0])};
+    T ave[3];
+    for (int i = 0; i < 3; ++i) ave[i] = M[i][2] * yaw_spd - w[i];
+    T gy[3] = {T(0), T(0), T(0)};
+    T rate_gain = T(1);
+    if (action_type == VF_ACTION_POSITION) {                                                // :486-491
+        gyro(P, w, gy);
+        rate_gain = T(1.2);
+    }
+    for (int i = 0; i < 3; ++i) {
+        T t = P.Kp[3 * i] * pe[0] + P.Kp[3 * i + 1] * pe[1] + P.Kp[3 * i + 2] * pe[2] +
+              rate_gain * (P.Kp[3 * i] * ave[0] + P.Kp[3 * i + 1] * ave[1] + P.Kp[3 * i + 2] * ave[2]);
+        if (action_type == VF_ACTION_POSITION)
+            t -= (P.Kd[3 * i] * al[0] + P.Kd[3 * i + 1] * al[1] + P.Kd[3 * i + 2] * al[2]) + gy[i];
+        ft[1 + i] = P.J[i] * t;                                                             // :452 (J diagonal)
+    }
+}
+
+template <class T>
+VF_HD void command_fwd(const Params<T>& P, int action_type, const T a[4], const State<T>& s, Command<T>& c) {
+    const T* w = s.w;
+    const T* al = s.al;
+    if (action_type == VF_ACTION_VELOCITY || action_type == VF_ACTION_POSITION) {
+        T ft[4];
+        geometric_cmd(P, action_type, a, s.p, s.q, s.v, s.w, s.al, ft);
+        for (int i = 0; i < 4; ++i)
+            c.t_pre[i] = P.B_inv[4 * i] * ft[0] + P.B_inv[4 * i + 1] * ft[1] + P.B_inv[4 * i + 2] * ft[2] +
+                         P.B_inv[4 * i + 3] * ft[3];
+    } else if (action_type == VF_ACTION_BODYRATE) {
         // dynamics.py:705-707 : collective thrust [N] and body-rate set-points [rad/s]
         T ft[4];
         ft[0] = (a[0] * P.act_half[0] + P.act_mean[0]) * P.mass;
@@ -479,7 +563,7 @@ template <class T>
 VF_HD void step_fwd(const Params<T>& P, int substeps, int integrator, int action_type, bool ctrl_delay,
                     const T a[4], State<T>& s, Wrench<T>& k) {
     Command<T> c;
-    command_fwd(P, action_type, a, s.w, s.al, c);
+    command_fwd(P, action_type, a, s, c);
     for (int it = 0; it < substeps; ++it) substep_fwd(P, integrator, ctrl_delay, c, s, k);
     clamp_state(P, s);
 }
@@ -493,7 +577,7 @@ template <class T> struct Tape {
 template <class T>
 VF_HD void step_fwd_taped(const Params<T>& P, int substeps, int integrator, int action_type, bool ctrl_delay,
                           const T a[4], const State<T>& s0, Command<T>& c, State<T>& s, Tape<T>* tape) {
-    command_fwd(P, action_type, a, s0.w, s0.al, c);
+    command_fwd(P, action_type, a, s0, c);
     s = s0;
     Wrench<T> k;
     for (int it = 0; it < substeps; ++it) {

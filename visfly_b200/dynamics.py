@@ -16,8 +16,10 @@ keep working; what is different is where the work happens:
 Deliberate deviations from the reference (documented in DESIGN.md): inputs of ``reset`` are copied (the
 reference aliases and later mutates them); the two per-step device synchronising asserts
 (dynamics.py:333, droneGymEnv.py:144) are opt-in via ``debug_checks``; ``t`` after a partial reset is 0 unless
-``random_reset_time=True`` (reference draws U(0, 2*pi), C9); action types ``velocity`` / ``position``,
-string wind functions and ``drag_random`` are not fused yet and raise ``NotImplementedError``.
+``random_reset_time=True`` (reference draws U(0, 2*pi), C9); string wind functions and ``drag_random`` are not
+fused yet and raise ``NotImplementedError``.  Action types ``velocity`` / ``position`` (geometric attitude
+controller, reference dynamics.py:414-496, per-agent Python loop there) run forward in the same kernel; their
+backward raises, as the reference's own autograd does on that branch.
 """
 from __future__ import annotations
 

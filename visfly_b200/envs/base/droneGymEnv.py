@@ -158,11 +158,18 @@ class DroneGymEnvsBase(VecEnv):
         assert self._is_initial, "You should call reset() before step()"
         if world is not None or predict:
             raise NotImplementedError("world-model rollouts are not part of the dynamics path")
+        fused = self._fused is not None and not is_test and self._fused.refresh()
+        # numpy mode + comm-delay FIFO: this step's kernel consumes an OLDER action, so the host->device copy of the
+        # new one can run on a side stream concurrently with the kernel (joined before step() returns)
+        overlap = fused and not self.tensor_output and not self.debug_checks and self._fused.spec.fifo_depth >= 1 \
+            and not (isinstance(_action, th.Tensor) and _action.is_cuda)
+        if overlap:
+            return self._step_fused(host_action=_action)
         self._action = self._stage_action(_action)
         if self.debug_checks:                                   # reference droneGymEnv.py:144 (host sync)
             assert self._action.max() <= 1 and self._action.min() >= -1
         if self._fused is not None:
-            if not is_test and self._fused.refresh():
+            if fused:
                 return self._step_fused()
             self._fused.leave()
         with self._grad_ctx():
@@ -221,13 +228,19 @@ class DroneGymEnvsBase(VecEnv):
             out[k] = hit[1]
         return out
 
-    def _step_fused(self):
+    def _step_fused(self, host_action=None):
         from .fused import RecordInfo
         if self.requires_grad and not self.tensor_output:
             raise ValueError("requires_grad should be False if tensor_output is False")
         slot = None if self.tensor_output else self._fused.host_slot()
-        obs, reward, done, record, term = self._fused.step(self._action, grad=self.requires_grad,
-                                                           mirror=None if slot is None else slot["ref"])
+        late = None
+        if host_action is not None:
+            def late():
+                self._action = self._stage_action(host_action, side_stream=True)
+                return self._action
+        obs, reward, done, record, term = self._fused.step(None if late else self._action, grad=self.requires_grad,
+                                                           mirror=None if slot is None else slot["ref"],
+                                                           late_action=late)
         self._obs_tensors = self._fused_obs(obs)
         term_obs = self._fused_obs(term) if term is not None else {}
         info = RecordInfo(self.num_agent, record, term_obs, self.envs.dynamics.ctrl_dt,
@@ -239,6 +252,9 @@ class DroneGymEnvsBase(VecEnv):
         # numpy mode (reference droneGymEnv.py:218): the kernel has already written obs / reward / done into the
         # page-locked host slot (zero-copy stores over PCIe); one stream synchronisation makes them readable
         th.cuda.current_stream(self.device).synchronize()
+        evt = self.__dict__.pop("_h2d_evt", None)
+        if evt is not None:
+            evt.synchronize()                        # join the side-stream copy of this step's action
         np_obs, np_reward, np_done = slot["np"]
         self._observations = self._fused_np_obs(np_obs)
         return self._observations, np_reward, np_done, info
@@ -298,7 +314,7 @@ class DroneGymEnvsBase(VecEnv):
         self._host_turn ^= 1
         return ring[self._host_turn]
 
-    def _stage_action(self, action) -> th.Tensor:
+    def _stage_action(self, action, side_stream: bool = False) -> th.Tensor:
         """Host actions (numpy / CPU tensors) reach the device through a pinned staging buffer."""
         if isinstance(action, th.Tensor) and action.is_cuda:
             return action.to(self.device, dtype=th.float32)
@@ -306,7 +322,17 @@ class DroneGymEnvsBase(VecEnv):
         if not self.tensor_output and src.dtype == th.float32 and src.is_contiguous() and src.is_pinned():
             # numpy mode ends every step with a stream synchronisation, so the DMA engine may read the caller's
             # page-locked array directly (no host-side staging copy)
-            return src.to(self.device, non_blocking=True)
+            if not side_stream:
+                return src.to(self.device, non_blocking=True)
+            main = th.cuda.current_stream(self.device)
+            cs = getattr(self, "_copy_stream", None)
+            if cs is None:
+                cs = self._copy_stream = th.cuda.Stream(self.device)
+            with th.cuda.stream(cs):                  # destination comes from the side stream's own pool
+                dev = src.to(self.device, non_blocking=True)
+                self._h2d_evt = cs.record_event()
+            dev.record_stream(main)                   # consumed by main-stream kernels a few steps later
+            return dev
         pin = getattr(self, "_act_pin", None)
         if pin is None or pin.shape != src.shape:
             pin = self._act_pin = th.empty(src.shape, dtype=th.float32, pin_memory=True)
@@ -319,7 +345,7 @@ class DroneGymEnvsBase(VecEnv):
         self._act_evt.record(th.cuda.current_stream(self.device))
         return dev
 
-    _TRANSIENT = ("_host_ring", "_host_turn", "_act_pin", "_act_evt", "_np_const")
+    _TRANSIENT = ("_host_ring", "_host_turn", "_act_pin", "_act_evt", "_np_const", "_copy_stream", "_h2d_evt")
 
     def __deepcopy__(self, memo):
         """Deep-copyable like the reference env (utils/algorithms/shac.py:121); host staging buffers and CUDA

@@ -279,15 +279,19 @@ class FusedEnvStep:
         self._host_turn ^= 1
         return ring[self._host_turn]
 
-    def step(self, action: th.Tensor, grad: bool = False, mirror=None):
+    def step(self, action, grad: bool = False, mirror=None, late_action=None):
         """One env step = one launch.  ``grad=True`` routes through ``EnvControlStep`` so that the returned state,
-        observation and reward carry autograd history (backward = one launch of ``vf_env_step_bwd``)."""
+        observation and reward carry autograd history (backward = one launch of ``vf_env_step_bwd``).
+        ``late_action`` (numpy mode with a comm-delay FIFO): a callable that stages this step's host action; it is
+        called AFTER the launch — the kernel consumes an older FIFO entry, so the staging overlaps with it."""
         env, dyn = self.env, self.env.envs.dynamics
         if self._fn is None:
             self._bind()
         if not self.active:
             self.enter()
-        if dyn._comm_delay_steps:
+        if late_action is not None:
+            action = dyn._pre_action.pop(0)
+        elif dyn._comm_delay_steps:
             dyn._pre_action.append(action)
             action = dyn._pre_action.pop(0)
         if not action.is_contiguous():
@@ -297,6 +301,8 @@ class FusedEnvStep:
             state_out, obs, reward, done, record, term = EnvControlStep.apply(state_in, action, self)
         else:
             state_out, obs, reward, done, record, term, _ = self._launch(state_in, action, False, mirror)
+        if late_action is not None:
+            dyn._pre_action.append(late_action())
         # keep the Dynamics object coherent (lazy views, diagnostics)
         dyn._prev = (state_in.detach(), action.detach()) if grad else (state_in, action)
         dyn._state = state_out

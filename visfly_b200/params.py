@@ -61,6 +61,10 @@ class VfParams(ctypes.Structure):
         ("pos_hi", ctypes.c_float * 3),
         ("vel_lim", ctypes.c_float),
         ("rate_lim", ctypes.c_float),
+        ("Kp", ctypes.c_float * 9),
+        ("vel_kp", ctypes.c_float),
+        ("vel_kd", ctypes.c_float),
+        ("pos_kd", ctypes.c_float),
     ]
 
     def as_dict(self) -> Dict[str, object]:
@@ -220,9 +224,15 @@ def build_vf_params(model: DroneModel, action_type: ACTION_TYPE, scaling: Dict[s
     elif action_type == ACTION_TYPE.THRUST:
         halves = [scaling["acc"].half] * 4
         means = [scaling["acc"].mean] * 4
-    else:
-        raise NotImplementedError(
-            f"action_type {action_type} has no fused kernel yet (SURVEY.md §8f row n2); use 'bodyrate' or 'thrust'")
+    else:                                            # velocity / position: [yaw, x, y, z]   dynamics.py:714-729
+        halves = [scaling["yaw"].half] + [scaling["velocity"].half] * 3
+        means = [scaling["yaw"].mean] + [scaling["velocity"].mean] * 3
+    kp = model.BODYRATE_PID.p.to(th.float32)
+    for i in range(9):
+        p.Kp[i] = float(kp.flatten()[i])
+    p.vel_kp = float(model.VELOCITY_PID.p)
+    p.vel_kd = float(model.VELOCITY_PID.d)
+    p.pos_kd = float(model.POSITION_PID.d)
     for i in range(4):
         p.act_half[i] = float(halves[i])
         p.act_mean[i] = float(means[i])
