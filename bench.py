@@ -396,62 +396,36 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def make_policy(device, seed=0):
-    """Fixed small MLP (state 13 + target 3 -> 64 -> 64 -> 4, tanh output), SURVEY.md §8d config 3."""
-    g = th.Generator().manual_seed(seed)
-    net = th.nn.Sequential(th.nn.Linear(16, 64), th.nn.Tanh(), th.nn.Linear(64, 64), th.nn.Tanh(),
-                           th.nn.Linear(64, 4), th.nn.Tanh())
-    with th.no_grad():
-        for p_ in net.parameters():
-            p_.copy_((th.rand(p_.shape, generator=g) * 2 - 1) * (0.3 if p_.dim() > 1 else 0.0))
-        net[-2].bias[0] = -0.35          # hover-ish collective
-    return net.to(device)
-
-
 def apg_benchmark(n, dev, rank, world, barrier, H=32, rollouts=5, gamma=0.99):
-    """BPTT rollout (reference utils/algorithms/BPTT.py:107-134): H steps with grad through NavigationEnv, loss =
-    -sum gamma^t r_t, backward, env.detach().  Forward = one fused env-step launch per step, backward = one adjoint
-    launch per step (EnvControlStep); the policy MLP is plain torch."""
+    """BPTT updates (reference utils/algorithms/BPTT.py:107-134) through visfly_b200.algorithms.BPTT: H steps with grad
+    through NavigationEnv, loss = -sum discount_t r_t, backward, gradient all-reduce over the ranks, Adam step,
+    env.detach().  Forward = one fused env-step launch per step, backward = one adjoint launch per step; the policy
+    MLP (16-64-64-4, tanh) is plain torch."""
     import torch.distributed as dist
+    from visfly_b200.algorithms import BPTT
     from visfly_b200.envs import NavigationEnv
     env = NavigationEnv(num_agent_per_scene=n, visual=False, device=dev, dynamics_kwargs=dict(DYN), seed=7 + rank,
                         requires_grad=True, max_episode_steps=256,
                         random_kwargs={"state_generator": {"class": "Uniform", "kwargs": [
                             {"position": {"mean": [2., 0., 1.5], "half": [1.0, 1.0, 0.5]}}]}})
-    policy = make_policy(dev)
-    opt_params = list(policy.parameters())
-    obs = env.reset()
-
-    def rollout():
-        nonlocal obs
-        loss = 0.0
-        for t in range(H):
-            a = policy(th.cat([obs["state"], obs["target"]], 1))
-            obs, r, d, info = env.step(a)
-            loss = loss - (gamma ** t) * r
-        loss = loss.mean()
-        grads = th.autograd.grad(loss, opt_params)
-        env.detach()
-        obs = env._obs_tensors.detach()
-        return loss, grads
-
-    for _ in range(2):
-        rollout()
+    algo = BPTT(env, horizon=H, gamma=gamma, learning_rate=1e-3, policy_kwargs=dict(net_arch=[64, 64]), seed=0,
+                make_eval_env=False, dump_step=1 << 62)
+    algo.learn(total_timesteps=2 * n * H)                      # warm-up: two updates
     barrier()
     e0, e1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
     e0.record()
-    for _ in range(rollouts):
-        loss, grads = rollout()
+    algo.learn(total_timesteps=rollouts * n * H)
     e1.record()
     barrier()
     ms = th.tensor([max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)], device=dev, dtype=th.float64)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    finite = all(bool(th.isfinite(g_).all()) for g_ in grads)
-    return {"workload": "NavigationEnv 65536 agents/GPU requires_grad=True RK4 (BASELINE configs[2]), H=32 BPTT rollouts, "
-                        "MLP 16-64-64-4 policy", "value": world * n * H * rollouts / (float(ms) * 1e-3), "unit": UNIT + " (fwd+bwd)",
-            "ms_per_rollout": float(ms) / rollouts, "horizon": H, "grads_finite": finite,
+    finite = all(bool(th.isfinite(p_).all()) for p_ in algo.actor.parameters())
+    return {"workload": "NavigationEnv 65536 agents/GPU requires_grad=True RK4 (BASELINE configs[2]), BPTT updates of "
+                        "H=32 (visfly_b200.algorithms.BPTT, MLP 16-64-64-4 policy, grad all-reduce over ranks)",
+            "value": world * n * H * rollouts / (float(ms) * 1e-3), "unit": UNIT + " (fwd+bwd+update)",
+            "ms_per_update": float(ms) / rollouts, "horizon": H, "weights_finite": finite,
             "fused": bool(env._fused is not None and env._fused.active)}
 
 

@@ -1,0 +1,69 @@
+"""Analytic-gradient trainers on the GPU env: BPTT improves a hover policy, its horizon
+gradient is the same through the one-kernel adjoint path and through the generic autograd path, SHAC runs with
+TD(lambda) critic targets."""
+import copy
+
+import pytest
+import torch as th
+
+from _env_util import DYN
+from _util import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def hover_env(n, seed=3, **kw):
+    from visfly_b200.envs import HoverEnv
+    return HoverEnv(num_agent_per_scene=n, visual=False, device="cuda", seed=seed, max_episode_steps=64,
+                    dynamics_kwargs=dict(DYN["rk4"]), requires_grad=True, tensor_output=True, **kw)
+
+
+def test_bptt_horizon_gradient_fused_adjoint_equals_generic_autograd():
+    from visfly_b200.algorithms import BPTT
+    grads = {}
+    for fused in (True, False):
+        th.manual_seed(11)
+        env = hover_env(256)
+        env.use_fused_step = fused
+        algo = BPTT(env, horizon=24, policy_kwargs=dict(net_arch=[32, 32]), seed=5, make_eval_env=False)
+        assert env.requires_grad
+        loss = algo.rollout_loss()
+        assert (env._fused is not None and env._fused.active) == fused
+        algo.actor.optimizer.zero_grad()
+        loss.backward()
+        grads[fused] = (float(loss), th.cat([p.grad.reshape(-1) for p in algo.actor.parameters() if p.grad is not None]))
+    assert abs(grads[True][0] - grads[False][0]) < 1e-5
+    assert rel_l2(grads[True][1].cpu(), grads[False][1].cpu()) < 1e-4
+
+
+def test_bptt_learns_to_hover_better():
+    from visfly_b200.algorithms import BPTT
+    env = hover_env(2048)
+    algo = BPTT(env, horizon=32, learning_rate=3e-3, policy_kwargs=dict(net_arch=[64, 64]), seed=1,
+                dump_step=2048 * 32 * 5)
+    before = algo.evaluate()
+    algo.learn(total_timesteps=2048 * 32 * 40)
+    after = algo.evaluate()
+    assert after["ep_rew_mean"] > before["ep_rew_mean"] + 0.05 * abs(before["ep_rew_mean"]), (before, after)
+    assert len(algo.history) >= 7 and all(th.isfinite(th.tensor(h["actor_loss"])) for h in algo.history)
+    assert algo.history[-1]["actor_loss"] < algo.history[0]["actor_loss"]
+
+
+def test_shac_updates_actor_critic_and_target():
+    from visfly_b200.algorithms import SHAC
+    from visfly_b200.envs import NavigationEnv
+    env = NavigationEnv(num_agent_per_scene=512, visual=False, device="cuda", seed=2, max_episode_steps=48,
+                        dynamics_kwargs=dict(DYN["rk4"]), requires_grad=True,
+                        random_kwargs={"state_generator": {"class": "Uniform", "kwargs": [
+                            {"position": {"mean": [2., 0., 1.5], "half": [1.0, 1.0, 0.5]}}]}})
+    algo = SHAC(env, horizon=16, gradient_steps=3, policy_kwargs=dict(net_arch=[32, 32]), seed=4,
+                dump_step=512 * 16, make_eval_env=True)
+    actor0 = copy.deepcopy(algo.actor.state_dict())
+    target0 = copy.deepcopy(algo.critic_target.state_dict())
+    algo.learn(total_timesteps=512 * 16 * 4)
+    assert len(algo.history) == 4
+    for h in algo.history:
+        assert all(th.isfinite(th.tensor(float(h[k]))) for k in ("actor_loss", "critic_loss", "ep_rew_mean"))
+    assert any(not th.equal(v, algo.actor.state_dict()[k]) for k, v in actor0.items())
+    assert any(not th.equal(v, algo.critic_target.state_dict()[k]) for k, v in target0.items())
+    assert env._fused is not None and env._fused.active          # the horizon ran on the one-kernel path

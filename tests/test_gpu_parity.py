@@ -213,7 +213,7 @@ def _hover_loss(dyn, acts, gamma=0.99):
 def test_velocity_and_position_have_no_gradient_like_the_reference(at):
     """The reference's backward raises for these action types (in-place writes in its per-agent loop,
     dynamics.py:446-450); the engine runs them forward and refuses the adjoint with a clear error."""
-    d = make_dynamics(8, action_type=at, integrator="rk4", dt=0.0025, ctrl_dt=0.02)
+    d = make_dynamics(8, action_type=at, integrator="rk4", dt=0.0025, ctrl_dt=0.02, comm_delay=0.0)
     a = th.zeros(8, 4, device="cuda", requires_grad=True)
     s = d.step(a)
     assert s.shape == (8, 13) and bool(th.isfinite(s).all())

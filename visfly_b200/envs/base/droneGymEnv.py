@@ -86,6 +86,10 @@ class LazyInfo(Sequence):
     def done_indices(self):
         return np.nonzero(self._fetch()["done"])[0]
 
+    def episode_done_tensor(self) -> th.Tensor:
+        """``[info[i]["episode_done"] for i in range(n)]`` as one bool device tensor (no host round trip)."""
+        return self._dev["episode_done"] & self._dev["done"]
+
 
 class DroneGymEnvsBase(VecEnv):
     def __init__(

@@ -106,6 +106,10 @@ class RecordInfo(Sequence):
     def done_indices(self):
         return np.nonzero(self._fetch()[:, 2].astype(np.int64) & P.RBIT_DONE)[0]
 
+    def episode_done_tensor(self) -> th.Tensor:
+        """``[info[i]["episode_done"] for i in range(n)]`` as one bool device tensor (no host round trip)."""
+        return (self._record[:, 2].to(th.int32) & P.RBIT_EPISODE_DONE) != 0
+
 
 class FusedEnvStep:
     """Owns the spec and the in-place per-agent env state of one env object while the fused path is active."""
