@@ -158,6 +158,21 @@ int vf_pack_state(int n, int m, const long long* index,
 int vf_unpack_state(int n, const float* state, float* pos, float* quat, float* vel, float* rate,
                     float* motor, float* alpha, void* stream);
 
+/*
+ * Renderer hand-off: poses of all agents in Habitat-sim's frame, straight from the packed
+ * state.  Replaces the reference's per-step `std_to_habitat` on host copies (utils/common.py:131-179, called from
+ * SceneManager.set_pose, utils/SceneManager.py:347-348, with Dynamics.position / orientation / velocity,
+ * envs/base/droneEnv.py:376):
+ *     hab_pos = (-y,  z, -x)            hab_ori (w first) = (w, -y, z, -x)            hab_vel = like hab_pos
+ *   pose_out [n][7]  = [hab_pos, hab_ori] per agent — the row the reference appends to its trajectory log
+ *                      (SceneManager.py:355-357)
+ *   vel_out  [n][3]  = velocity incl. the constant wind (Dynamics.velocity, dynamics.py:750-752), or NULL
+ * Both outputs may be device memory or page-locked host memory (written zero-copy, see VfEnvMirror); the host-side
+ * consumer synchronises the stream before reading.
+ */
+int vf_export_pose_habitat(const VfParams* params, int n, const float* state, float* pose_out, float* vel_out,
+                           void* stream);
+
 /* =====================================================================================================
  * Fused env step: the control step above PLUS the wrapper tail the reference runs
  * around it with ~100 aten ops and per-agent Python loops — analytic bounding-box collision

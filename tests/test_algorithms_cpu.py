@@ -109,7 +109,7 @@ def test_rollout_buffer_flattens_like_the_reference():
         buf.add(obs=obs, reward=th.ones(n), action=th.zeros(n, 4), next_obs=obs, done=th.zeros(n, dtype=th.bool),
                 episode_done=th.zeros(n, dtype=th.bool), value=th.zeros(n))
     buf.compute_returns()
-    assert buf.returns.shape == (h * n,) and buf.obs["state"].shape == (h, n, 13) and buf.action.shape == (h * n, 4)
+    assert buf.returns.shape == (h * n,) and buf.obs["state"].shape == (h * n, 13) and buf.action.shape == (h * n, 4)
     assert buf.returns[0] > buf.returns[-1] > 0
 
 

@@ -451,3 +451,30 @@ def test_partial_reset_cuts_the_gradient_like_the_reference():
     assert rel_l2(gg.cpu(), gc) < GRAD_TOL
     d.detach()
     assert not d._state.requires_grad and all(not a.requires_grad for a in d._pre_action)
+
+
+def test_habitat_pose_export_matches_reference_transform():
+    """Renderer hand-off: poses in Habitat's frame written by one kernel into page-locked host
+    memory / device memory == the reference's std_to_habitat (utils/common.py:131-179) on Dynamics.position /
+    orientation / velocity — exact, it is a signed axis permutation."""
+    from visfly_b200.render_handoff import HabitatPoseExporter, habitat_to_std, std_to_habitat
+    for n in (1, 31, 257, 4096):
+        d = make_dynamics(n, action_type="bodyrate", integrator="rk4", dt=0.0025, ctrl_dt=0.02, comm_delay=0.0,
+                          wind_settings=[0.3, -0.2, 0.1])
+        pos, quat, vel, rate, _, _ = random_flight_state(n, seed=n)
+        d.reset(pos=pos, ori=quat, vel=vel, ori_vel=rate)
+        d.step(th.zeros(n, 4, device="cuda"))
+        # the reference's matrices, applied with numpy exactly as it does
+        ref_pos = d.position.cpu().numpy() @ np.array([[0, 0, -1], [-1, 0, 0], [0, 1, 0]])
+        ref_ori = d.orientation.cpu().numpy() @ np.array([[1, 0, 0, 0], [0, 0, 0, -1], [0, -1, 0, 0], [0, 0, 1, 0]])
+        ref_vel = d.velocity.cpu().numpy() @ np.array([[0, 0, -1], [-1, 0, 0], [0, 1, 0]])
+        for host in (True, False):
+            pose, hv = HabitatPoseExporter(d, host=host).export()
+            pose, hv = (pose, hv) if host else (pose.cpu().numpy(), hv.cpu().numpy())
+            assert np.array_equal(pose[:, :3], ref_pos.astype(np.float32))
+            assert np.array_equal(pose[:, 3:], ref_ori.astype(np.float32))
+            assert np.array_equal(hv, ref_vel.astype(np.float32))
+        hp, ho = std_to_habitat(d.position, d.orientation)
+        assert np.array_equal(hp, ref_pos.astype(np.float32)) and np.array_equal(ho, ref_ori.astype(np.float32))
+        sp, so = habitat_to_std(hp, ho)                      # round trip
+        assert th.equal(sp, d.position.cpu()) and th.equal(so, d.orientation.cpu())

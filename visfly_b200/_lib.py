@@ -37,6 +37,7 @@ SIGNATURES = {
     "vf_step_fwd_host": (_i, [_P(VfParams), _i, _i, _i, _i, _u, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "vf_pack_state": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "vf_unpack_state": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "vf_export_pose_habitat": (_i, [_P(VfParams), _i, _vp, _vp, _vp, _vp]),
     "vf_env_spec_size": (_i, []),
     "vf_env_step_fwd": (_i, [_P(VfParams), _P(VfEnvSpec), _i, _i, _i, _i, _u, _u, ctypes.c_ulonglong,
                              _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
@@ -209,3 +210,19 @@ def env_step_bwd(params: VfParams, spec: VfEnvSpec, substeps: int, integrator: i
             _dev_ptr(state_in, "state_in"), _dev_ptr(action, "action"), _any_ptr(saved, "saved", th.int32),
             _dev_ptr(g_state_out, "grad_state_out"), _dev_ptr(g_obs, "grad_obs"), _dev_ptr(g_reward, "grad_reward"),
             _dev_ptr(g_state_in, "grad_state_in"), _dev_ptr(g_action, "grad_action"), _stream(state_in.device)))
+
+
+def export_pose_habitat(params: VfParams, state: th.Tensor, pose_out: th.Tensor, vel_out: Optional[th.Tensor]) -> None:
+    """Binding of ``vf_export_pose_habitat``; outputs are float32 contiguous, CUDA or page-locked host tensors."""
+    lib = load(require_cuda=True)
+    n = state.shape[1]
+    for t, what, w in ((pose_out, "pose_out", 7), (vel_out, "vel_out", 3)):
+        if t is None:
+            continue
+        if t.dtype != th.float32 or not t.is_contiguous() or tuple(t.shape) != (n, w):
+            raise ValueError(f"{what} must be a contiguous float32 ({n},{w}) tensor")
+        if not t.is_cuda and not t.is_pinned():
+            raise ValueError(f"{what} must live on the device or in page-locked host memory")
+    with th.cuda.device(state.device):
+        _check(lib.vf_export_pose_habitat(ctypes.byref(params), n, _dev_ptr(state, "state"), pose_out.data_ptr(),
+                                          None if vel_out is None else vel_out.data_ptr(), _stream(state.device)))

@@ -64,9 +64,10 @@ class RolloutBuffer:
 
     def flatten(self):
         self.reward = th.vstack(self.reward).flatten()
-        self.obs = TensorDict.stack(self.obs)
+        # (H, N, ...) -> (H*N, ...): rows line up with the flattened action / return vectors
+        self.obs = TensorDict({k: v.flatten(0, 1) for k, v in TensorDict.stack(self.obs).items()})
         self.action = th.vstack(self.action)
-        self.next_obs = TensorDict.stack(self.next_obs)
+        self.next_obs = TensorDict({k: v.flatten(0, 1) for k, v in TensorDict.stack(self.next_obs).items()})
         self.done = th.vstack(self.done).flatten()
         self.episode_done = th.vstack(self.episode_done).flatten()
         self.returns = th.vstack(self.returns).flatten()

@@ -437,6 +437,59 @@ __global__ void vf_unpack_kernel(int n, const float* __restrict__ st, float* __r
 }
 
 // ---------------------------------------------------------------------------------------------
+// renderer hand-off: poses in Habitat-sim's frame (pure sign / axis permutation of the packed state)
+// ---------------------------------------------------------------------------------------------
+// Warp-cooperative store of 32 rows of W floats (row-major, W odd => lane*W+j is conflict-free in shared memory).
+template <int W>
+__device__ __forceinline__ void warp_store_rows(float* __restrict__ dst_base, float* smem, int n, int warp_first,
+                                                int lane, const float* row) {
+    if (warp_first + 32 <= n) {
+#pragma unroll
+        for (int j = 0; j < W; ++j) smem[lane * W + j] = row[j];
+        __syncwarp();
+        float4* dst = reinterpret_cast<float4*>(dst_base + size_t(warp_first) * W);
+        const float4* src = reinterpret_cast<const float4*>(smem);
+#pragma unroll
+        for (int k = 0; k < (8 * W + 31) / 32; ++k) {
+            const int idx = lane + 32 * k;
+            if (idx < 8 * W) dst[idx] = src[idx];
+        }
+        __syncwarp();
+    } else if (warp_first + lane < n) {
+        float* dst = dst_base + size_t(warp_first + lane) * W;
+#pragma unroll
+        for (int j = 0; j < W; ++j) dst[j] = row[j];
+    }
+}
+
+constexpr int kPoseBlock = 128;
+
+__global__ void __launch_bounds__(kPoseBlock)
+vf_export_pose_kernel(const __grid_constant__ VfParams params, int n, const float* __restrict__ st,
+                      float* __restrict__ pose_out, float* __restrict__ vel_out) {
+    __shared__ __align__(16) float s_rows[(kPoseBlock / 32) * 32 * 7];
+    const int i = blockIdx.x * kPoseBlock + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int warp_first = i - lane;
+    float pose[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, vel[3] = {0.f, 0.f, 0.f};
+    if (i < n) {
+        const float4 p = ldg4(st, size_t(i));
+        const float4 q = ldg4(st, size_t(n) + i);
+        // utils/common.py:159-176 : pos @ [[0,0,-1],[-1,0,0],[0,1,0]],  ori @ [[1,0,0,0],[0,0,0,-1],[0,-1,0,0],[0,0,1,0]]
+        pose[0] = -p.y; pose[1] = p.z; pose[2] = -p.x;
+        pose[3] = q.x; pose[4] = -q.z; pose[5] = q.w; pose[6] = -q.y;
+        if (vel_out) {
+            const float4 v = ldg4(st, size_t(2) * n + i);
+            const float vx = v.x + params.wind[0], vy = v.y + params.wind[1], vz = v.z + params.wind[2];
+            vel[0] = -vy; vel[1] = vz; vel[2] = -vx;
+        }
+    }
+    warp_store_rows<7>(pose_out, s_rows + warp * 32 * 7, n, warp_first, lane, pose);
+    if (vel_out) warp_store_rows<3>(vel_out, s_rows + warp * 32 * 7, n, warp_first, lane, vel);
+}
+
+// ---------------------------------------------------------------------------------------------
 // dispatch
 // ---------------------------------------------------------------------------------------------
 constexpr int kBlock = 64;   // 65 536 agents -> 1024 CTAs -> 6.9 per SM: <= 14 warps on the fullest SM
@@ -730,6 +783,34 @@ int vf_env_step_bwd(const VfParams* params, const VfEnvSpec* spec, int n, int su
                 grad_obs, grad_reward, grad_state_in, grad_action, st);
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return fail("vf_env_step_bwd launch failed", err);
+    return 0;
+}
+
+int vf_export_pose_habitat(const VfParams* params, int n, const float* state, float* pose_out, float* vel_out,
+                           void* stream) {
+    if (!params) return fail("params is NULL");
+    if (n < 0) return fail("n must be >= 0");
+    if (n == 0) return 0;
+    if (!state || !pose_out) return fail("state and pose_out must not be NULL");
+    // page-locked host destinations resolve to their device alias; device pointers pass through unchanged
+    float* outs[2] = {pose_out, vel_out};
+    for (float*& o : outs) {
+        if (!o) continue;
+        cudaPointerAttributes attr;
+        if (cudaPointerGetAttributes(&attr, o) != cudaSuccess) {
+            (void)cudaGetLastError();
+            return fail("vf_export_pose_habitat: output is neither device nor page-locked host memory");
+        }
+        if (attr.type == cudaMemoryTypeHost) o = static_cast<float*>(attr.devicePointer);
+        else if (attr.type == cudaMemoryTypeUnregistered)
+            return fail("vf_export_pose_habitat: output is pageable host memory (use cudaHostAlloc / pin_memory)");
+        if (!aligned16(o)) return fail("vf_export_pose_habitat: outputs must be 16-byte aligned");
+    }
+    if (!aligned16(state)) return fail("state must be 16-byte aligned");
+    vf_export_pose_kernel<<<(n + kPoseBlock - 1) / kPoseBlock, kPoseBlock, 0, static_cast<cudaStream_t>(stream)>>>(
+        *params, n, state, outs[0], outs[1]);
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return fail("vf_export_pose_habitat launch failed", err);
     return 0;
 }
 
