@@ -182,6 +182,28 @@ def cpu_reference_run(steps: int, warmup: int, budget_s: float, agents: int = AG
             "dynamics_only_value": n / dyn_dt, "steps": steps}
 
 
+def reference_dynamics_on_gpu(n, dev, steps=5):
+    """north_star's second baseline: the reference's PyTorch dynamics executed on the B200 — the oracle port of
+    Dynamics.step (same aten-op sequence, ~8 200 launches per RK4x8 control step) with its tensors on the device."""
+    try:
+        from oracle.torch_oracle import OracleDynamics
+        dyn = OracleDynamics(n, device=dev, **{k: v for k, v in DYN.items()})
+        acts = hover_actions(n, 4, dev)
+        with th.no_grad():
+            for i in range(2):
+                dyn.step(acts[i])
+            th.cuda.synchronize()
+            t0 = time.perf_counter()
+            for i in range(steps):
+                dyn.step(acts[i % 4])
+            th.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / steps
+        return {"value": n / dt, "unit": UNIT, "ms_per_step": dt * 1e3, "agents": n, "kind": "port",
+                "what": "OracleDynamics.step (Dynamics.step only, no env wrapper) with all tensors on cuda"}
+    except Exception as e:  # noqa: BLE001 - a baseline must never take the bench down
+        return {"error": repr(e)[:200]}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -284,6 +306,23 @@ def run_ours(args):
     # (realistic, 12 MB working set) hot L2 but including all host overhead between steps
     value, total_ms = (cold_value, cold_ms) if cold_value <= hot_value else (hot_value, hot_ms)
 
+    # ---- Dynamics.step alone through the drop-in class (SURVEY.md §8d reports both) -------------------------
+    from visfly_b200.dynamics import Dynamics
+    dyn_only = Dynamics(num=n, device=dev, **DYN)
+    with th.no_grad():
+        for i in range(W):
+            dyn_only.step(act_list[i % pool])
+        barrier()
+        d0, d1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        d0.record(stream)
+        for i in range(K):
+            dyn_only.step(act_list[i % pool])
+        d1.record(stream)
+        th.cuda.synchronize()
+        dyn_ms = max(d0.elapsed_time(d1), (time.perf_counter() - t0) * 1e3)
+    dynamics_step_value = n * K / (dyn_ms * 1e-3)
+
     # ---- roofline: the fused control-step kernel alone, cold L2 -----------------------------------------
     dynm = env.envs.dynamics
     cfg = dynm._cfg
@@ -371,6 +410,9 @@ def run_ours(args):
     apg = apg_benchmark(n, dev, rank, world, barrier)
     clk.__exit__(None, None, None)
 
+    ref_gpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        ref_gpu = reference_dynamics_on_gpu(n, dev)
     if rank == 0:
         cpu = None
         if not args.no_cpu_baseline:
@@ -388,7 +430,8 @@ def run_ours(args):
                              "hot: K steps back to back inside barrier+synchronize, host overhead included)",
                        "parallelism": f"agents sharded over {world} GPU(s), one all_gather of episode returns per rollout"},
             "clocks": clk.summary(), "e2e": e2e, "gpu_launches": K * env_launches_per_step(env), "apg": apg,
-            "roofline": roofline, "cpu_baseline": cpu,
+            "roofline": roofline, "cpu_baseline": cpu, "reference_dynamics_on_gpu": ref_gpu,
+            "dynamics_step_value_per_gpu": dynamics_step_value,
             "cold_l2_device_value": cold_value, "hot_l2_bracketed_value": hot_value, "kernel_only_value": n / k_avg,
         }
         print(json.dumps(line), flush=True)
