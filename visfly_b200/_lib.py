@@ -79,6 +79,28 @@ def load(require_cuda: bool = False) -> ctypes.CDLL:
     return _lib
 
 
+_fast = None
+
+
+def fast():
+    """The torch-extension plumbing module (``visfly_b200/_vf_torch*.so``, csrc/vf_torch.cpp): output allocation +
+    C-ABI launch in one Python->C++ transition for the two per-step hot calls.  Same kernels, same entry points as
+    the ctypes binding; required (no silent slow path) — build it with ``__graft_entry__.build()``."""
+    global _fast
+    if _fast is None:
+        load()                                   # the ABI / struct-size checks, and the library itself
+        try:
+            from . import _vf_torch
+        except ImportError as e:
+            raise ExtensionMissing(
+                "visfly_b200/_vf_torch*.so not found or not loadable: build it with "
+                f"`python -c 'import __graft_entry__ as g; g.build()'` ({e})") from e
+        if _vf_torch.abi_version() != ABI_VERSION:
+            raise ExtensionMissing("_vf_torch was built against a different libvisfly_b200.so: rebuild")
+        _fast = _vf_torch
+    return _fast
+
+
 def _check(rc: int):
     if rc != 0:
         raise RuntimeError("visfly_b200: " + load().vf_last_error().decode())

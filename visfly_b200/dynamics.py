@@ -46,16 +46,20 @@ class StepConfig:
         self.params, self.substeps, self.integrator = params, substeps, integrator
         self.action_type, self.flags = action_type, flags
 
+    @property
+    def params_addr(self) -> int:
+        """Address of the ``VfParams`` struct (owned by this object) for the C++ plumbing."""
+        import ctypes
+        return ctypes.addressof(self.params)
+
 
 class ControlStep(th.autograd.Function):
     """``(state[5,N,4], action[N,4]) -> (state'[5,N,4], obs[N,13])`` — one kernel each way."""
 
     @staticmethod
     def forward(ctx, state: th.Tensor, action: th.Tensor, cfg: StepConfig):
-        state_out = th.empty_like(state)
-        obs = th.empty((state.shape[1], 13), dtype=th.float32, device=state.device)
-        _lib.step_fwd(cfg.params, cfg.substeps, cfg.integrator, cfg.action_type, cfg.flags,
-                      state, action, state_out, obs, None)
+        state_out, obs = _lib.fast().step_fwd(cfg.params_addr, cfg.substeps, cfg.integrator, cfg.action_type,
+                                              cfg.flags, state, action)
         ctx.cfg = cfg
         ctx.save_for_backward(state, action)
         ctx.set_materialize_grads(False)

@@ -146,7 +146,7 @@ class FusedEnvStep:
         self._fn = None
         self._bind()
 
-    _CTYPES_REFS = ("_fn", "_params_ref", "_spec_ref", "_host_ring", "_host_turn")
+    _CTYPES_REFS = ("_fn", "_params_addr", "_spec_addr", "_host_ring", "_host_turn")
 
     def __deepcopy__(self, memo):
         """ctypes references are per-object handles: the copy re-creates them against its own env / spec."""
@@ -160,13 +160,9 @@ class FusedEnvStep:
         return twin
 
     def _bind(self):
-        self._fn = _lib.load().vf_env_step_fwd
-        self._params_ref = ctypes.byref(self.env.envs.dynamics._cfg.params)
-        self._spec_ref = ctypes.byref(self.spec)
-        if self.active:
-            self._p_sc, self._p_ret, self._p_eb = self.sc.data_ptr(), self.ret.data_ptr(), self.eb.data_ptr()
-            self._p_gate = None if self.gate is None else self.gate.data_ptr()
-            self._p_passed = None if self.passed is None else self.passed.data_ptr()
+        self._fn = _lib.fast().env_step_fwd
+        self._params_addr = ctypes.addressof(self.env.envs.dynamics._cfg.params)
+        self._spec_addr = ctypes.addressof(self.spec)
 
     # -- eligibility ------------------------------------------------------------------------------------
     def refresh(self) -> bool:
@@ -210,9 +206,6 @@ class FusedEnvStep:
         env.envs._fused = self
         for t, dt in ((self.sc, th.int32), (self.ret, th.float32), (self.eb, th.uint8)):
             assert t.is_cuda and t.is_contiguous() and t.dtype == dt
-        self._p_sc, self._p_ret, self._p_eb = self.sc.data_ptr(), self.ret.data_ptr(), self.eb.data_ptr()
-        self._p_gate = None if self.gate is None else self.gate.data_ptr()
-        self._p_passed = None if self.passed is None else self.passed.data_ptr()
         self.active = True
 
     def leave(self):
@@ -241,30 +234,15 @@ class FusedEnvStep:
     # -- the step -------------------------------------------------------------------------------------------
     def _launch(self, state_in: th.Tensor, action: th.Tensor, want_saved: bool, mirror=None):
         """Allocate the step's outputs and launch ``vf_env_step_fwd`` (status buffers are updated in place).
-        ``mirror``: ``ctypes.byref(VfEnvMirror)`` of page-locked host destinations for obs / reward / done, or None."""
-        env, dyn, n, dev = self.env, self.env.envs.dynamics, self.n, self.device
-        state_out = th.empty_like(state_in)
-        obs = th.empty((n, self.obs_width), dtype=th.float32, device=dev)
-        reward = th.empty((n,), dtype=th.float32, device=dev)
-        done = th.empty((n,), dtype=th.bool, device=dev)
-        record = th.empty((n, 4), dtype=th.float32, device=dev)
-        term = th.empty((n, self.obs_width), dtype=th.float32, device=dev) if env.keep_terminal_observation else None
-        saved = th.empty((n, 2), dtype=th.int32, device=dev) if want_saved else None
-        cfg = dyn._cfg
-        # hot call: tensors created above / owned by this object are float32-contiguous-CUDA by construction, the
-        # action was normalised by the wrapper; the C side still validates NULLs and alignment
-        if th.cuda.current_device() != dev.index:
-            th.cuda.set_device(dev)
-        rc = self._fn(self._params_ref, self._spec_ref, n, cfg.substeps, cfg.integrator, cfg.action_type, cfg.flags,
-                      0, self.global_step, state_in.data_ptr(), action.data_ptr(),
-                      None if self.table is None else self.table.data_ptr(), self._p_sc, self._p_ret, self._p_eb,
-                      self._p_gate, self._p_passed, state_out.data_ptr(), obs.data_ptr(), reward.data_ptr(),
-                      done.data_ptr(), record.data_ptr(), None if term is None else term.data_ptr(),
-                      None if saved is None else saved.data_ptr(), mirror, _raw_stream(dev.index))
-        if rc != 0:
-            raise RuntimeError("visfly_b200: " + _lib.load().vf_last_error().decode())
+        ``mirror``: address of a ``VfEnvMirror`` (page-locked host destinations for obs / reward / done), or None."""
+        cfg = self.env.envs.dynamics._cfg
+        # hot call: one Python->C++ transition allocates the outputs (torch caching allocator) and launches through
+        # the C-ABI on the current stream of the state's device (csrc/vf_torch.cpp)
+        out = self._fn(self._params_addr, self._spec_addr, cfg.substeps, cfg.integrator, cfg.action_type, cfg.flags,
+                       0, self.global_step, state_in, action, self.table, self.sc, self.ret, self.eb, self.gate,
+                       self.passed, self.obs_width, self.env.keep_terminal_observation, want_saved, mirror or 0)
         self.global_step += 1
-        return state_out, obs, reward, done, record, term, saved
+        return out
 
     def host_slot(self):
         """Page-locked host destinations of obs / reward / done for the numpy output mode: two alternating sets (the
@@ -277,7 +255,7 @@ class FusedEnvStep:
                 reward = th.empty((self.n,), dtype=th.float32, pin_memory=True)
                 done = th.empty((self.n,), dtype=th.int32, pin_memory=True)
                 m = P.VfEnvMirror(obs.data_ptr(), reward.data_ptr(), done.data_ptr())
-                ring.append({"obs": obs, "reward": reward, "done": done, "mirror": m, "ref": ctypes.byref(m),
+                ring.append({"obs": obs, "reward": reward, "done": done, "mirror": m, "ref": ctypes.addressof(m),
                              "np": (obs.numpy(), reward.numpy(), done.numpy())})
             self._host_ring, self._host_turn = ring, 0
         self._host_turn ^= 1
