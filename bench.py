@@ -43,6 +43,7 @@ MOVED_BYTES_FWD = 176 + 52 + 39   # + the (n,13) observation + reward/done/episo
 FLOP_PER_AGENT_STEP = 4100    # SURVEY.md §8(d) lean count, RK4 x 8 sub-steps
 FP32_PEAK_TFLOPS = 74.0       # 148 SM x 128 lanes x 2 x 1.965 GHz (nominal)
 L2_FLUSH_BYTES = 256 << 20
+HOT_PREROLL = 600             # untimed back-to-back steps before the bracketed loop (host clock ramp, see run_ours)
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -60,6 +61,7 @@ class ClockSampler:
     def __init__(self, index: int):
         self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
         self._stop = threading.Event()
+        self._ready = threading.Event()          # set after the first sample: NVML import / init is over by then
         self._thread = None
 
     def _nvml_loop(self):
@@ -78,11 +80,12 @@ class ClockSampler:
             getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons")
         while not self._stop.is_set():
             self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+            self._ready.set()
             mask = get_reasons(h)
             for bit, name in names.items():
                 if mask & bit:
                     self.reasons.add(name)
-            time.sleep(0.02)
+            time.sleep(float(os.environ.get("VF_CLOCK_SAMPLE_S", "0.02")))
 
     def _smi_loop(self):
         import subprocess
@@ -93,6 +96,7 @@ class ClockSampler:
                                  capture_output=True, text=True).stdout.strip().split(",")
             if len(out) >= 6:
                 self.samples.append(int(out[0]))
+                self._ready.set()
                 self.max_mhz = int(out[1])
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), out[2:]):
                     if "Active" in v and "Not" not in v:
@@ -100,6 +104,9 @@ class ClockSampler:
             time.sleep(0.1)
 
     def _loop(self):
+        if os.environ.get("VF_NO_SAMPLER"):
+            self._ready.set()
+            return
         try:
             self._nvml_loop()
         except Exception:  # noqa: BLE001
@@ -111,6 +118,7 @@ class ClockSampler:
     def __enter__(self):
         self._thread = threading.Thread(target=self._loop, daemon=True)
         self._thread.start()
+        self._ready.wait(timeout=5.0)            # keep the sampler's start-up (imports, nvmlInit) out of timed regions
         return self
 
     def __exit__(self, *exc):
@@ -276,6 +284,11 @@ def run_ours(args):
 
     for i in range(W):
         env_step(i)
+    # long-lived objects (modules, the envs) leave the garbage collector's working set: a full collection walking
+    # them costs ~1 ms, which is 50 env steps on this path
+    import gc
+    gc.collect()
+    gc.freeze()
     barrier()
     clk = ClockSampler(local)
     clk.__enter__()                         # sampled across every timed region below (value, roofline, e2e, apg)
@@ -283,19 +296,35 @@ def run_ours(args):
         # (A) cold L2: one CUDA-event pair per step, 256 MiB flush before every timed step
         per_step = timed_steps(env_step, K, flush, stream)
         barrier()
+        # the back-to-back loop gets its own warm-up: the host thread slept in the barrier above while the GPU drained
+        # the flush-heavy cold pass, and its core needs a few ms of work to clock back up (measured: 19.8 -> 17.1 ->
+        # 14.5 us/step over three consecutive 200-step loops); max(W, HOT_PREROLL) untimed steps bring it to steady state
+        for i in range(max(W, HOT_PREROLL)):
+            env_step(i)
+        barrier()
         # (B) hot L2, the contract's bracket: barrier + synchronize, K steps back to back, events at both ends;
         #     includes every host-side microsecond between launches and the rollout's one collective
         e0, e1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         e0.record(stream)
+        dbg = [] if os.environ.get("VF_BENCH_DEBUG") else None
         for i in range(K):
+            if dbg is not None:
+                dbg.append(time.perf_counter())
             env_step(i)
+        if dbg:
+            dbg.append(time.perf_counter())
+            d = sorted(((b - a, j) for j, (a, b) in enumerate(zip(dbg, dbg[1:]))), reverse=True)[:6]
+            print("slowest host steps in the hot loop:", [(j, round(t * 1e6)) for t, j in d], file=sys.stderr)
+            print("host enqueue of the whole loop: %.3f ms" % ((dbg[-1] - dbg[0]) * 1e3), file=sys.stderr)
         # the one collective of the path: episode returns of all shards, once per rollout (no-op at world 1)
         all_returns = gather_episode_returns(env._rewards)
         e1.record(stream)
         barrier()
         wall_hot = time.perf_counter() - t0
         dev_hot_ms = e0.elapsed_time(e1)
+        if dbg:
+            print("hot loop: device %.3f ms, wall %.3f ms" % (dev_hot_ms, wall_hot * 1e3), file=sys.stderr)
     tot = th.tensor([sum(per_step), max(dev_hot_ms, wall_hot * 1e3)], device=dev, dtype=th.float64)
     if world > 1:
         dist.all_reduce(tot, op=dist.ReduceOp.MAX)
@@ -427,7 +456,8 @@ def run_ours(args):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "agents_per_gpu": n, "substeps": 8, "actions": "smooth-hover law",
                        "l2": "value = min(cold: 256 MiB L2 flush before every timed step, one CUDA-event pair per step; "
-                             "hot: K steps back to back inside barrier+synchronize, host overhead included)",
+                             "hot: K steps back to back inside barrier+synchronize, host overhead included, "
+                             "after max(W, 600) untimed back-to-back steps)",
                        "parallelism": f"agents sharded over {world} GPU(s), one all_gather of episode returns per rollout"},
             "clocks": clk.summary(), "e2e": e2e, "gpu_launches": K * env_launches_per_step(env), "apg": apg,
             "roofline": roofline, "cpu_baseline": cpu, "reference_dynamics_on_gpu": ref_gpu,
