@@ -228,7 +228,7 @@ def run_reference(args):
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -464,7 +464,7 @@ def run_ours(args):
             "dynamics_step_value_per_gpu": dynamics_step_value,
             "cold_l2_device_value": cold_value, "hot_l2_bracketed_value": hot_value, "kernel_only_value": n / k_avg,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -507,7 +507,30 @@ def env_launches_per_step(env) -> int:
     return int(getattr(env, "native_launches_per_step", 1))
 
 
+_JSON_FD = None
+
+
+def protect_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write banners to fd 1 (e.g. "NCCL version ..." on the first
+    collective), so fd 1 is pointed at stderr for the duration of the run and the JSON line goes to the saved fd."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    protect_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
