@@ -309,3 +309,32 @@ def test_numpy_mode_host_mirror_ragged_batch():
         o2, r2, d2, _ = envs[1].step(a.numpy())
         assert np.array_equal(o1["state"].cpu().numpy(), o2["state"]) and np.array_equal(r1.cpu().numpy(), r2)
         assert np.array_equal(d1.cpu().numpy().astype(np.int32), d2)
+
+
+@pytest.mark.parametrize("action_type", ["velocity", "position"])
+def test_fused_env_step_runs_velocity_and_position_action_types(action_type):
+    """The one-kernel env step is instantiated for the geometric-controller action types too: same results as the
+    generic path (control-step kernel + tensor ops), which is itself checked against the reference golden runs."""
+    from visfly_b200.envs import NavigationEnv
+    n, T = 96, 40
+    dyn = dict(DYN["rk4"], action_type=action_type)
+    z = load_env_golden("navigation", "rk4")
+    g = th.Generator().manual_seed(8)
+    acts = (th.rand(T, n, 4, generator=g) * 2 - 1) * 0.3
+    table = tuple(x.repeat(3, 1)[:n] for x in table_of(z))
+
+    def run(fused):
+        env = NavigationEnv(num_agent_per_scene=n, visual=False, dynamics_kwargs=dict(dyn), max_episode_steps=15)
+        env.envs.set_reset_table(*[x.cuda() for x in table])
+        env.use_fused_step = fused
+        env.reset()
+        out = []
+        for t in range(T):
+            obs, r, d, info = env.step(acts[t].cuda())
+            assert env._fused.active == fused
+            out.append((obs["state"].clone(), r.clone(), d.clone()))
+        return out
+
+    for (o1, r1, d1), (o2, r2, d2) in zip(run(True), run(False)):
+        assert th.allclose(o1, o2, atol=2e-5, rtol=2e-5) and th.allclose(r1, r2, atol=2e-5) and th.equal(d1, d2)
+    assert bool(th.stack([d for _, _, d in run(True)]).any())          # the runs cross auto-resets
