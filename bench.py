@@ -8,8 +8,11 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 One JSON line on stdout (rank 0).  What is measured
-  value     env.step throughput with actions and state resident in HBM (tensor mode), timed on the device with one
-            CUDA-event pair per step and an L2 flush (256 MiB write) before every timed step; max over ranks.
+  value     env.step throughput with actions and state resident in HBM (tensor mode): exactly K steps inside
+            barrier + synchronize, 16 independent env replicas taking turns so that every step's inputs are evicted
+            from L2 (inputs larger than L2, no flush kernel in the timed region); max over ranks.  Two diagnostics
+            ride along: one env with a 256 MiB flush + CUDA-event pair per step (cold_l2_device_value) and one env
+            back to back (hot_l2_bracketed_value).
   e2e       the same env driven like an SB3/numpy training loop: actions arrive in (pinned) host memory every step,
             observation / reward / done come back as numpy arrays — host<->device copies inside the timed region.
   roofline  the dominant kernel (the fused control step) timed alone, cold L2, against the measured HBM peak.
@@ -43,6 +46,7 @@ MOVED_BYTES_FWD = 176 + 52 + 39   # + the (n,13) observation + reward/done/episo
 FLOP_PER_AGENT_STEP = 4100    # SURVEY.md §8(d) lean count, RK4 x 8 sub-steps
 FP32_PEAK_TFLOPS = 74.0       # 148 SM x 128 lanes x 2 x 1.965 GHz (nominal)
 L2_FLUSH_BYTES = 256 << 20
+REPLICAS = 16                 # env copies rotated in the timed loop: 16 x ~17 MB per step > 126 MB L2
 HOT_PREROLL = 600             # untimed back-to-back steps before the bracketed loop (host clock ramp, see run_ours)
 
 
@@ -325,15 +329,40 @@ def run_ours(args):
         dev_hot_ms = e0.elapsed_time(e1)
         if dbg:
             print("hot loop: device %.3f ms, wall %.3f ms" % (dev_hot_ms, wall_hot * 1e3), file=sys.stderr)
-    tot = th.tensor([sum(per_step), max(dev_hot_ms, wall_hot * 1e3)], device=dev, dtype=th.float64)
+        # (C) THE reported value: the contract's bracket with inputs larger than L2 and no flush kernel inside it —
+        #     REPLICAS independent copies of the 65 536-agent env take turns, so every step finds its state, actions
+        #     and env status evicted (REPLICAS x ~17 MB per step >> 126 MB L2) while launches stay back to back
+        envs = [env] + [HoverEnv(num_agent_per_scene=n, visual=False, device=dev, dynamics_kwargs=dict(DYN),
+                                 seed=42 + rank + 1000 * j, max_episode_steps=256, tensor_output=True)
+                        for j in range(1, REPLICAS)]
+        for e in envs[1:]:
+            e.reset()
+
+        def rot_step(i):
+            envs[i % REPLICAS].step(act_list[i % pool])
+
+        for i in range(max(W * REPLICAS, HOT_PREROLL)):
+            rot_step(i)
+        barrier()
+        r0, r1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        r0.record(stream)
+        for i in range(K):
+            rot_step(i)
+        all_returns = gather_episode_returns(env._rewards)
+        r1.record(stream)
+        barrier()
+        wall_rot = time.perf_counter() - t0
+        dev_rot_ms = r0.elapsed_time(r1)
+        del envs
+    tot = th.tensor([sum(per_step), max(dev_hot_ms, wall_hot * 1e3), max(dev_rot_ms, wall_rot * 1e3)], device=dev,
+                    dtype=th.float64)
     if world > 1:
         dist.all_reduce(tot, op=dist.ReduceOp.MAX)
-    cold_ms, hot_ms = float(tot[0]), float(tot[1])
+    cold_ms, hot_ms, total_ms = float(tot[0]), float(tot[1]), float(tot[2])
     cold_value = world * n * K / (cold_ms * 1e-3)
     hot_value = world * n * K / (hot_ms * 1e-3)
-    # the reported value is the LOWER of the two: device-timed with a cold L2, or end-to-end bracketed with the
-    # (realistic, 12 MB working set) hot L2 but including all host overhead between steps
-    value, total_ms = (cold_value, cold_ms) if cold_value <= hot_value else (hot_value, hot_ms)
+    value = world * n * K / (total_ms * 1e-3)
 
     # ---- Dynamics.step alone through the drop-in class (SURVEY.md §8d reports both) -------------------------
     from visfly_b200.dynamics import Dynamics
@@ -455,9 +484,10 @@ def run_ours(args):
             "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "agents_per_gpu": n, "substeps": 8, "actions": "smooth-hover law",
-                       "l2": "value = min(cold: 256 MiB L2 flush before every timed step, one CUDA-event pair per step; "
-                             "hot: K steps back to back inside barrier+synchronize, host overhead included, "
-                             "after max(W, 600) untimed back-to-back steps)",
+                       "l2": "inputs larger than L2: 16 independent replicas of the 65536-agent env take turns inside the "
+                             "bracketed K-step loop (16 x ~17 MB touched per step > 126 MB L2), no flush kernel in the timed "
+                             "region, all host overhead included, after max(16 W, 600) untimed steps; cold_l2_device_value = "
+                             "one env, 256 MiB flush + one CUDA-event pair per step; hot_l2_bracketed_value = one env back to back",
                        "parallelism": f"agents sharded over {world} GPU(s), one all_gather of episode returns per rollout"},
             "clocks": clk.summary(), "e2e": e2e, "gpu_launches": K * env_launches_per_step(env), "apg": apg,
             "roofline": roofline, "cpu_baseline": cpu, "reference_dynamics_on_gpu": ref_gpu,
