@@ -418,6 +418,33 @@ def run_ours(args):
                          "frac": FLOP_PER_AGENT_STEP * n / k_avg / 1e12 / FP32_PEAK_TFLOPS,
                          "note": "RK4 x8 is fp32-pipe/latency bound (23 FLOP/B, ridge ~11.5), SURVEY.md §8d"}}
 
+    # the same kernel where the chip is full: 4 194 304 agents (1.1 GB of traffic per launch, far beyond L2) — the
+    # asymptote the 65 536-agent workload cannot reach because it is shorter than a launch ramp
+    try:
+        big = 1 << 22
+        b_in = st_in.repeat(1, big // n, 1).contiguous()
+        b_out, b_obs = th.empty_like(b_in), th.empty((big, 13), device=dev)
+        b_act = acts[0].repeat(big // n, 1).contiguous()
+        b_sc, b_ret, b_eb = sc.repeat(big // n), ret.repeat(big // n), eb.repeat(big // n)
+        b_rew, b_done = th.empty(big, device=dev), th.empty(big, dtype=th.bool, device=dev)
+        b_rec = th.empty((big, 4), device=dev)
+
+        def kernel_big(i):
+            _lib.env_step_fwd(cfg.params, fz.spec, cfg.substeps, cfg.integrator, cfg.action_type, cfg.flags, 0,
+                              30_000 + i, b_in, b_act, None, b_sc, b_ret, b_eb, None, None, b_out, b_obs, b_rew, b_done,
+                              b_rec, None, None)
+
+        for i in range(3):
+            kernel_big(i)
+        kb = float(np.mean(timed_steps(kernel_big, 10, None, stream))) * 1e-3
+        roofline["asymptote_4194304_agents"] = {
+            "kernel_us": kb * 1e6, "achieved": ALGO_BYTES_FWD * big / kb / 1e9, "frac": ALGO_BYTES_FWD * big / kb / 1e9 / peak,
+            "moved_gbs": MOVED_BYTES_FWD * big / kb / 1e9, "fp32_tflops": FLOP_PER_AGENT_STEP * big / kb / 1e12,
+            "fp32_frac": FLOP_PER_AGENT_STEP * big / kb / 1e12 / FP32_PEAK_TFLOPS, "agent_steps_per_s": big / kb}
+        del b_in, b_out, b_obs, b_act, b_sc, b_ret, b_eb, b_rew, b_done, b_rec
+    except Exception as e:  # noqa: BLE001 - a diagnostic must never take the bench down
+        roofline["asymptote_4194304_agents"] = {"error": repr(e)[:200]}
+
     # the same kernel with the page-locked host mirror as a second destination (what the e2e step launches)
     from visfly_b200.params import VfEnvMirror
     m_obs, m_rew = th.empty((n, 13), pin_memory=True), th.empty(n, pin_memory=True)

@@ -28,6 +28,9 @@ std::tuple<at::Tensor, at::Tensor> step_fwd(int64_t params, int64_t substeps, in
     check_f32_cuda(state_in, "state_in");
     check_f32_cuda(action, "action");
     const int64_t n = state_in.size(1);
+    TORCH_CHECK(state_in.dim() == 3 && state_in.size(0) == VF_STATE_PLANES && state_in.size(2) == 4,
+                "state_in must be (5, n, 4)");
+    TORCH_CHECK(action.numel() == 4 * n, "action must be (n, 4)");
     c10::cuda::CUDAGuard guard(state_in.device());
     at::Tensor state_out = at::empty_like(state_in);
     at::Tensor obs = at::empty({n, VF_OBS_FLOATS}, state_in.options());
@@ -50,6 +53,18 @@ env_step_fwd(int64_t params, int64_t spec, int64_t substeps, int64_t integrator,
     check_f32_cuda(state_in, "state_in");
     check_f32_cuda(action, "action");
     const int64_t n = state_in.size(1);
+    TORCH_CHECK(state_in.dim() == 3 && state_in.size(0) == VF_STATE_PLANES && state_in.size(2) == 4,
+                "state_in must be (5, n, 4)");
+    TORCH_CHECK(action.numel() == 4 * n, "action must be (n, 4)");
+    if (reset_table.has_value()) check_f32_cuda(*reset_table, "reset_table");
+    check_f32_cuda(returns, "returns");
+    TORCH_CHECK(step_count.is_cuda() && step_count.scalar_type() == at::kInt && step_count.is_contiguous() &&
+                    step_count.numel() == n, "step_count must be a contiguous int32 CUDA tensor of n elements");
+    TORCH_CHECK(ebits.is_cuda() && ebits.scalar_type() == at::kByte && ebits.is_contiguous() && ebits.numel() == n,
+                "ebits must be a contiguous uint8 CUDA tensor of n elements");
+    for (const OptTensor* t : {&gate, &gates_passed})
+        TORCH_CHECK(!t->has_value() || ((*t)->is_cuda() && (*t)->scalar_type() == at::kInt && (*t)->is_contiguous() &&
+                                        (*t)->numel() == n), "gate / gates_passed must be contiguous int32 CUDA tensors");
     c10::cuda::CUDAGuard guard(state_in.device());
     const auto f32 = state_in.options();
     at::Tensor state_out = at::empty_like(state_in);
