@@ -233,19 +233,22 @@ vf_env_step_fwd_kernel(const __grid_constant__ VfParams params, const __grid_con
     vf::State<float> s;
     int g = 0;
     if (live) {
+        // every input of the step is requested up front: the env status words are only needed after the sub-step
+        // loop, but fetching them there would put a second (cold) HBM round trip on each warp's critical path
         load_state(state_in, n, i, s);
         const int age = step_count[i];
         float4 a4 = ldg4(action, size_t(i));
+        const unsigned eb = ebits[i];
+        const float ret_in = returns[i];
+        int passed = 0;
+        int g_in = 0;
+        if (E.task == VF_TASK_RACING) { g_in = gate[i]; passed = gates_passed[i]; }
         if (age < E.fifo_depth) a4 = make_float4(0.f, 0.f, 0.f, 0.f);   // FIFO rows of a reset agent read as zero
         const float a[4] = {a4.x, a4.y, a4.z, a4.w};
         vf::Wrench<float> k;
         vf::step_fwd<float>(P, substeps, INTEG, ACT, LAG, a, s, k);
 
-        unsigned eb = ebits[i];
         int sc = age + 1;
-        int passed = 0;
-        int g_in = 0;
-        if (E.task == VF_TASK_RACING) { g_in = gate[i]; passed = gates_passed[i]; }
         if (saved_out) reinterpret_cast<int2*>(saved_out)[i] = make_int2(age, g_in);
         vf::EnvEval<float> ev;
         vf::env_eval<float>(P, E, s, sc, g_in, (eb & VF_EBIT_EPISODE_DONE) != 0, ev);
@@ -255,7 +258,7 @@ vf_env_step_fwd_kernel(const __grid_constant__ VfParams params, const __grid_con
         bool once = (eb & VF_EBIT_ONCE_COLLIDED) || ev.is_col;
         const bool success = ev.success;
         const float reward = ev.reward;
-        float ret = returns[i] + reward;
+        float ret = ret_in + reward;
         bool ep_done = ev.ep_done;
         const bool done = ev.done;
 
