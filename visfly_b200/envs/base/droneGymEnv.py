@@ -321,6 +321,8 @@ class DroneGymEnvsBase(VecEnv):
     def _stage_action(self, action, side_stream: bool = False) -> th.Tensor:
         """Host actions (numpy / CPU tensors) reach the device through a pinned staging buffer."""
         if isinstance(action, th.Tensor) and action.is_cuda:
+            if action.dtype is th.float32 and action.device == self.device:
+                return action                                   # the common case: nothing to convert
             return action.to(self.device, dtype=th.float32)
         src = action if isinstance(action, th.Tensor) else th.as_tensor(np.asarray(action))
         if not self.tensor_output and src.dtype == th.float32 and src.is_contiguous() and src.is_pinned():
