@@ -34,6 +34,14 @@ int fail(const char* what, cudaError_t err = cudaSuccess) {
 constexpr int kObs = VF_OBS_FLOATS;       // 13
 constexpr int kWarpObs = 32 * kObs;       // floats one warp's observations occupy (416 = 104 float4)
 
+// Programmatic dependent launch (sm_90+): the step kernels are launched with the programmatic-stream-serialization
+// attribute, so the CTAs of step t+1 become resident while step t is still running (65 536 agents fill less than
+// half of the chip's warp slots) and park at `pdl_wait` — launch latency, CTA rasterisation and the first
+// instruction-cache misses of step t+1 overlap with the arithmetic of step t.  `griddepcontrol.wait` returns once the
+// preceding grid has completed and its writes are visible, so every global access below it is ordered as before.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ float4 ldg4(const float* base, size_t idx4) {
     return __ldg(reinterpret_cast<const float4*>(base) + idx4);
 }
@@ -135,6 +143,8 @@ vf_step_fwd_kernel(const __grid_constant__ VfParams params, int n, int substeps,
     const int warp = threadIdx.x >> 5;
     const int warp_first = i - lane;
     const bool live = i < n;
+    pdl_trigger();
+    pdl_wait();
 
     vf::State<float> s;
     vf::Wrench<float> k;
@@ -177,6 +187,8 @@ vf_step_bwd_kernel(const __grid_constant__ VfParams params, int n, int substeps,
     const int warp = threadIdx.x >> 5;
     const int warp_first = i - lane;
     const bool live = i < n;
+    pdl_trigger();
+    pdl_wait();
 
     vf::State<float> g;
     if (g_state_out && live) {
@@ -229,6 +241,8 @@ vf_env_step_fwd_kernel(const __grid_constant__ VfParams params, const __grid_con
     const int warp = threadIdx.x >> 5;
     const int warp_first = i - lane;
     const bool live = i < n;
+    pdl_trigger();
+    pdl_wait();
 
     vf::State<float> s;
     int g = 0;
@@ -349,6 +363,8 @@ vf_env_step_bwd_kernel(const __grid_constant__ VfParams params, const __grid_con
     const int warp = threadIdx.x >> 5;
     const int warp_first = i - lane;
     const bool live = i < n;
+    pdl_trigger();
+    pdl_wait();
 
     float o[16];
     const bool have_obs = g_obs != nullptr;
@@ -508,6 +524,28 @@ int block_override() {
     return v;
 }
 
+// Launch with the programmatic-stream-serialization attribute (see pdl_trigger / pdl_wait above).  VF_NO_PDL=1 turns
+// the attribute off (plain stream order) for A/B measurements.
+bool pdl_enabled() {
+    static const bool v = std::getenv("VF_NO_PDL") == nullptr;
+    return v;
+}
+
+template <class... KArgs, class... Args>
+void launch_pdl(void (*kernel)(KArgs...), int grid, int block, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(unsigned(grid));
+    cfg.blockDim = dim3(unsigned(block));
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    (void)cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);   // errors surface through cudaGetLastError in the caller
+}
+
 bool aligned16(const void* p) { return (reinterpret_cast<size_t>(p) & 15u) == 0; }
 
 int check_common(const VfParams* params, int n, int substeps, int integrator, int action_type, bool backward = false) {
@@ -539,13 +577,13 @@ template <int INTEG, int ACT, bool LAG>
 void launch_fwd(const VfParams& p, int n, int substeps, const float* si, const float* a, float* so, float* obs,
                 float* ext, cudaStream_t st) {
     switch (block_override()) {
-        case 32: vf_step_fwd_kernel<INTEG, ACT, LAG, 32><<<(n + 31) / 32, 32, 0, st>>>(p, n, substeps, si, a, so, obs, ext); return;
-        case 128: vf_step_fwd_kernel<INTEG, ACT, LAG, 128><<<(n + 127) / 128, 128, 0, st>>>(p, n, substeps, si, a, so, obs, ext); return;
-        case 256: vf_step_fwd_kernel<INTEG, ACT, LAG, 256><<<(n + 255) / 256, 256, 0, st>>>(p, n, substeps, si, a, so, obs, ext); return;
+        case 32: launch_pdl(vf_step_fwd_kernel<INTEG, ACT, LAG, 32>, (n + 31) / 32, 32, st, p, n, substeps, si, a, so, obs, ext); return;
+        case 128: launch_pdl(vf_step_fwd_kernel<INTEG, ACT, LAG, 128>, (n + 127) / 128, 128, st, p, n, substeps, si, a, so, obs, ext); return;
+        case 256: launch_pdl(vf_step_fwd_kernel<INTEG, ACT, LAG, 256>, (n + 255) / 256, 256, st, p, n, substeps, si, a, so, obs, ext); return;
         default: break;
     }
     const int grid = (n + kBlock - 1) / kBlock;
-    vf_step_fwd_kernel<INTEG, ACT, LAG, kBlock><<<grid, kBlock, 0, st>>>(p, n, substeps, si, a, so, obs, ext);
+    launch_pdl(vf_step_fwd_kernel<INTEG, ACT, LAG, kBlock>, grid, kBlock, st, p, n, substeps, si, a, so, obs, ext);
 }
 
 template <int INTEG, int ACT, bool LAG>
@@ -553,11 +591,11 @@ void launch_bwd(const VfParams& p, int n, int substeps, const float* si, const f
                 const float* gobs, float* gsi, float* ga, cudaStream_t st) {
     const int grid = (n + kBlock - 1) / kBlock;
     if (substeps <= 8)
-        vf_step_bwd_kernel<INTEG, ACT, LAG, 8, kBlock><<<grid, kBlock, 0, st>>>(p, n, substeps, si, a, gso, gobs, gsi, ga);
+        launch_pdl(vf_step_bwd_kernel<INTEG, ACT, LAG, 8, kBlock>, grid, kBlock, st, p, n, substeps, si, a, gso, gobs, gsi, ga);
     else if (substeps <= 16)
-        vf_step_bwd_kernel<INTEG, ACT, LAG, 16, kBlock><<<grid, kBlock, 0, st>>>(p, n, substeps, si, a, gso, gobs, gsi, ga);
+        launch_pdl(vf_step_bwd_kernel<INTEG, ACT, LAG, 16, kBlock>, grid, kBlock, st, p, n, substeps, si, a, gso, gobs, gsi, ga);
     else
-        vf_step_bwd_kernel<INTEG, ACT, LAG, VF_MAX_SUBSTEPS_BWD, kBlock><<<grid, kBlock, 0, st>>>(p, n, substeps, si, a, gso, gobs, gsi, ga);
+        launch_pdl(vf_step_bwd_kernel<INTEG, ACT, LAG, VF_MAX_SUBSTEPS_BWD, kBlock>, grid, kBlock, st, p, n, substeps, si, a, gso, gobs, gsi, ga);
 }
 
 template <int INTEG, int ACT, bool LAG>
@@ -567,8 +605,7 @@ void launch_env_fwd(const VfParams& p, const VfEnvSpec& e, int n, int substeps, 
                     unsigned char* done, float* rec, float* tobs, int* saved, const VfEnvMirror& mirror,
                     cudaStream_t st) {
     const int grid = (n + kBlock - 1) / kBlock;
-    vf_env_step_fwd_kernel<INTEG, ACT, LAG, kBlock><<<grid, kBlock, 0, st>>>(
-        p, e, n, substeps, env_flags, step_index, si, a, table, sc, ret, eb, gate, passed, so, obs, rew, done, rec, tobs,
+    launch_pdl(vf_env_step_fwd_kernel<INTEG, ACT, LAG, kBlock>, grid, kBlock, st, p, e, n, substeps, env_flags, step_index, si, a, table, sc, ret, eb, gate, passed, so, obs, rew, done, rec, tobs,
         saved, mirror);
 }
 
@@ -578,11 +615,11 @@ void launch_env_bwd(const VfParams& p, const VfEnvSpec& e, int n, int substeps, 
                     float* ga, cudaStream_t st) {
     const int grid = (n + kBlock - 1) / kBlock;
     if (substeps <= 8)
-        vf_env_step_bwd_kernel<INTEG, ACT, LAG, 8, kBlock><<<grid, kBlock, 0, st>>>(p, e, n, substeps, env_flags, si, a, saved, gso, gobs, gr, gsi, ga);
+        launch_pdl(vf_env_step_bwd_kernel<INTEG, ACT, LAG, 8, kBlock>, grid, kBlock, st, p, e, n, substeps, env_flags, si, a, saved, gso, gobs, gr, gsi, ga);
     else if (substeps <= 16)
-        vf_env_step_bwd_kernel<INTEG, ACT, LAG, 16, kBlock><<<grid, kBlock, 0, st>>>(p, e, n, substeps, env_flags, si, a, saved, gso, gobs, gr, gsi, ga);
+        launch_pdl(vf_env_step_bwd_kernel<INTEG, ACT, LAG, 16, kBlock>, grid, kBlock, st, p, e, n, substeps, env_flags, si, a, saved, gso, gobs, gr, gsi, ga);
     else
-        vf_env_step_bwd_kernel<INTEG, ACT, LAG, VF_MAX_SUBSTEPS_BWD, kBlock><<<grid, kBlock, 0, st>>>(p, e, n, substeps, env_flags, si, a, saved, gso, gobs, gr, gsi, ga);
+        launch_pdl(vf_env_step_bwd_kernel<INTEG, ACT, LAG, VF_MAX_SUBSTEPS_BWD, kBlock>, grid, kBlock, st, p, e, n, substeps, env_flags, si, a, saved, gso, gobs, gr, gsi, ga);
 }
 
 // forward-only dispatch: all four action types

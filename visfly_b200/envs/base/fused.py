@@ -146,7 +146,7 @@ class FusedEnvStep:
         self._fn = None
         self._bind()
 
-    _CTYPES_REFS = ("_fn", "_params_addr", "_spec_addr", "_host_ring", "_host_turn")
+    _CTYPES_REFS = ("_fn", "_stepper", "_params_addr", "_spec_addr", "_host_ring", "_host_turn")
 
     def __deepcopy__(self, memo):
         """ctypes references are per-object handles: the copy re-creates them against its own env / spec."""
@@ -156,13 +156,23 @@ class FusedEnvStep:
         for k, v in self.__dict__.items():
             if k not in self._CTYPES_REFS:
                 setattr(twin, k, copy.deepcopy(v, memo))
-        twin._fn = None            # re-bound on first use (the twin env may not be fully copied yet)
+        twin._fn = twin._stepper = None   # re-bound on first use (the twin env may not be fully copied yet)
         return twin
 
     def _bind(self):
-        self._fn = _lib.fast().env_step_fwd
+        self._fn = _lib.fast().EnvStepper
+        self._stepper = None
         self._params_addr = ctypes.addressof(self.env.envs.dynamics._cfg.params)
         self._spec_addr = ctypes.addressof(self.spec)
+
+    def _make_stepper(self):
+        """Bind what does not change from step to step (parameter blocks, kernel variant, in-place status buffers,
+        reset table) into the C++ stepper; rebuilt whenever one of those is replaced (``enter``, ``_refresh``)."""
+        cfg = self.env.envs.dynamics._cfg
+        self._stepper = self._fn(self._params_addr, self._spec_addr, cfg.substeps, cfg.integrator, cfg.action_type,
+                                 cfg.flags, self.n, self.sc, self.ret, self.eb, self.gate, self.passed, self.table,
+                                 self.obs_width)
+        return self._stepper
 
     # -- eligibility ------------------------------------------------------------------------------------
     def refresh(self) -> bool:
@@ -180,6 +190,7 @@ class FusedEnvStep:
 
     def _refresh(self) -> bool:
         env, s = self.env, self.spec
+        self._stepper = None
         if os.environ.get("VISFLY_B200_NO_FUSED_ENV") or not env.use_fused_step or not env.envs._imu_noise_free:
             return False
         if not env.envs.dynamics.is_quat_output or "_generate_state" in vars(env.envs):
@@ -206,6 +217,7 @@ class FusedEnvStep:
         env.envs._fused = self
         for t, dt in ((self.sc, th.int32), (self.ret, th.float32), (self.eb, th.uint8)):
             assert t.is_cuda and t.is_contiguous() and t.dtype == dt
+        self._stepper = None
         self.active = True
 
     def leave(self):
@@ -235,12 +247,10 @@ class FusedEnvStep:
     def _launch(self, state_in: th.Tensor, action: th.Tensor, want_saved: bool, mirror=None):
         """Allocate the step's outputs and launch ``vf_env_step_fwd`` (status buffers are updated in place).
         ``mirror``: address of a ``VfEnvMirror`` (page-locked host destinations for obs / reward / done), or None."""
-        cfg = self.env.envs.dynamics._cfg
         # hot call: one Python->C++ transition allocates the outputs (torch caching allocator) and launches through
-        # the C-ABI on the current stream of the state's device (csrc/vf_torch.cpp)
-        out = self._fn(self._params_addr, self._spec_addr, cfg.substeps, cfg.integrator, cfg.action_type, cfg.flags,
-                       0, self.global_step, state_in, action, self.table, self.sc, self.ret, self.eb, self.gate,
-                       self.passed, self.obs_width, self.env.keep_terminal_observation, want_saved, mirror or 0)
+        # the C-ABI on the current stream of the state's device (csrc/vf_torch.cpp, EnvStepper)
+        out = (self._stepper or self._make_stepper()).step(state_in, action, self.global_step, 0,
+                                                           self.env.keep_terminal_observation, want_saved, mirror or 0)
         self.global_step += 1
         return out
 
