@@ -10,7 +10,8 @@
 One JSON line on stdout (rank 0).  What is measured
   value     env.step throughput with actions and state resident in HBM (tensor mode): exactly K steps inside
             barrier + synchronize, 16 independent env replicas taking turns so that every step's inputs are evicted
-            from L2 (inputs larger than L2, no flush kernel in the timed region); max over ranks.  Two diagnostics
+            from L2 (inputs larger than L2, no flush kernel in the timed region); max over ranks; the median of five
+            consecutive such brackets (all listed in bracket_ms).  Two diagnostics
             ride along: one env with a 256 MiB flush + CUDA-event pair per step (cold_l2_device_value) and one env
             back to back (hot_l2_bracketed_value).
   e2e       the same env driven like an SB3/numpy training loop: actions arrive in (pinned) host memory every step,
@@ -47,6 +48,7 @@ FLOP_PER_AGENT_STEP = 4100    # SURVEY.md §8(d) lean count, RK4 x 8 sub-steps
 FP32_PEAK_TFLOPS = 74.0       # 148 SM x 128 lanes x 2 x 1.965 GHz (nominal)
 L2_FLUSH_BYTES = 256 << 20
 REPLICAS = 16                 # env copies rotated in the timed loop: 16 x ~17 MB per step > 126 MB L2
+BRACKETS = 5                  # consecutive K-step brackets; value = the median one
 HOT_PREROLL = 600             # untimed back-to-back steps before the bracketed loop (host clock ramp, see run_ours)
 
 
@@ -330,26 +332,33 @@ def run_ours(args):
 
         for i in range(max(W * REPLICAS, HOT_PREROLL)):
             rot_step(i)
-        barrier()
-        r0, r1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
-        t0 = time.perf_counter()
-        r0.record(stream)
-        for i in range(K):
-            rot_step(i)
-        all_returns = gather_episode_returns(env._rewards)
-        r1.record(stream)
-        barrier()
-        wall_rot = time.perf_counter() - t0
-        dev_rot_ms = r0.elapsed_time(r1)
+        # BRACKETS consecutive brackets of exactly K steps, each with barrier + synchronize on both sides and the
+        # max over ranks of max(device time, wall time); the reported value is the MEDIAN bracket (all of them are
+        # listed in the JSON line).  Host enqueue (~10 us) and device time (~12 us) per step are close, so a single
+        # 200-step bracket moves by +-15 % with one scheduler hiccup on the host core.
+        bracket_ms = []
+        for _ in range(BRACKETS):
+            barrier()
+            r0, r1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
+            t0 = time.perf_counter()
+            r0.record(stream)
+            for i in range(K):
+                rot_step(i)
+            all_returns = gather_episode_returns(env._rewards)
+            r1.record(stream)
+            barrier()
+            wall_rot = time.perf_counter() - t0
+            bracket_ms.append(max(r0.elapsed_time(r1), wall_rot * 1e3))
         del envs
     except BaseException:
         clk.__exit__(None, None, None)
         raise
-    tot = th.tensor([sum(per_step), max(dev_hot_ms, wall_hot * 1e3), max(dev_rot_ms, wall_rot * 1e3)], device=dev,
-                    dtype=th.float64)
+    tot = th.tensor([sum(per_step), max(dev_hot_ms, wall_hot * 1e3)] + bracket_ms, device=dev, dtype=th.float64)
     if world > 1:
         dist.all_reduce(tot, op=dist.ReduceOp.MAX)
-    cold_ms, hot_ms, total_ms = float(tot[0]), float(tot[1]), float(tot[2])
+    cold_ms, hot_ms = float(tot[0]), float(tot[1])
+    bracket_ms = [float(x) for x in tot[2:]]
+    total_ms = sorted(bracket_ms)[len(bracket_ms) // 2]
     cold_value = world * n * K / (cold_ms * 1e-3)
     hot_value = world * n * K / (hot_ms * 1e-3)
     value = world * n * K / (total_ms * 1e-3)
@@ -503,13 +512,15 @@ def run_ours(args):
             "config": {"workload": WORKLOAD, "agents_per_gpu": n, "substeps": 8, "actions": "smooth-hover law",
                        "l2": "inputs larger than L2: 16 independent replicas of the 65536-agent env take turns inside the "
                              "bracketed K-step loop (16 x ~17 MB touched per step > 126 MB L2), no flush kernel in the timed "
-                             "region, all host overhead included, after max(16 W, 600) untimed steps; cold_l2_device_value = "
+                             "region, all host overhead included, after max(16 W, 600) untimed steps; value = the median of "
+                             f"{BRACKETS} consecutive K-step brackets (bracket_ms lists them all); cold_l2_device_value = "
                              "one env, 256 MiB flush + one CUDA-event pair per step; hot_l2_bracketed_value = one env back to back",
                        "parallelism": f"agents sharded over {world} GPU(s), one all_gather of episode returns per rollout"},
             "clocks": clk.summary(), "e2e": e2e, "gpu_launches": K * env_launches_per_step(env), "apg": apg,
             "roofline": roofline, "cpu_baseline": cpu, "reference_dynamics_on_gpu": ref_gpu,
             "dynamics_step_value_per_gpu": dynamics_step_value,
             "cold_l2_device_value": cold_value, "hot_l2_bracketed_value": hot_value, "kernel_only_value": n / k_avg,
+            "bracket_ms": bracket_ms,
         }
         emit(line)
     if world > 1:
@@ -580,7 +591,7 @@ def main():
     protect_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--agents", type=int, default=AGENTS, help="agents per GPU")

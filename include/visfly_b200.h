@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define VF_ABI_VERSION 5
+#define VF_ABI_VERSION 6
 
 /* integrator: reference `integrator=` kwarg, utils/maths.py:331 (euler) and :353 (rk4, repaired R1-R3) */
 #define VF_INTEGRATOR_EULER 0
@@ -110,10 +110,14 @@ int vf_device_sm_count(void);
  *   state_out  [5][n][4]  packed state after ctrl_dt = substeps*dt        (device, must not alias state_in)
  *   obs_out    [n][13]    reference `state` property, or NULL             (device, 16B aligned)
  *   ext_out    [n][8]     [acc, 0, thrusts] diagnostics, or NULL          (device, 16B aligned)
+ *   wind       [n][4]     per-agent wind [wx, wy, wz, -] of this control step, or NULL = the constant
+ *                         params->wind.  Carries the reference's time-varying wind functions
+ *                         (dynamics.py:136-165, update_wind :384-388: evaluated by the caller once per control
+ *                         step from t and the previous wind, then frozen over the sub-steps) (device, 16B aligned)
  */
 int vf_step_fwd(const VfParams* params, int n, int substeps, int integrator, int action_type,
                 unsigned flags, const float* state_in, const float* action,
-                float* state_out, float* obs_out, float* ext_out, void* stream);
+                float* state_out, float* obs_out, float* ext_out, const float* wind, void* stream);
 
 /*
  * Reverse-mode gradient of vf_step_fwd: re-runs the substeps from (state_in, action) in registers /
@@ -123,6 +127,8 @@ int vf_step_fwd(const VfParams* params, int n, int substeps, int integrator, int
  *   grad_obs       [n][13]    dL/d obs_out                      (device; NULL = zeros)
  *   grad_state_in  [5][n][4]  dL/d state_in      (written)
  *   grad_action    [n][4]     dL/d action        (written)
+ *   wind           [n][4]     the wind the forward step was given, or NULL (it only decides the gradient gate
+ *                             of the post-step position clamp; wind itself does not depend on the state)
  *
  * torch.autograd conventions are reproduced exactly: clamp passes gradient on the
  * closed interval, d(v|v|)/dv = 2|v|.  substeps must be <= VF_MAX_SUBSTEPS_BWD.
@@ -133,7 +139,7 @@ int vf_step_fwd(const VfParams* params, int n, int substeps, int integrator, int
 int vf_step_bwd(const VfParams* params, int n, int substeps, int integrator, int action_type,
                 unsigned flags, const float* state_in, const float* action,
                 const float* grad_state_out, const float* grad_obs,
-                float* grad_state_in, float* grad_action, void* stream);
+                float* grad_state_in, float* grad_action, const float* wind, void* stream);
 
 /*
  * Host-buffer variant of vf_step_fwd (what a caller that lives in host memory binds, e.g. an SB3/numpy

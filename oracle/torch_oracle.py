@@ -153,8 +153,8 @@ class OracleDynamics:
 
     def __init__(self, num: int = 1, action_type: str = "bodyrate", dt: float = 0.005, ctrl_dt: float = 0.03,
                  ctrl_delay: bool = True, comm_delay: float = 0.06, integrator: str = "euler",
-                 cfg: str = "drone_state", wind: Sequence[float] = (0, 0, 0), device="cpu",
-                 dtype=th.float32, random_reset_time: bool = False):
+                 cfg: str = "drone_state", wind: Sequence = (0, 0, 0), device="cpu",
+                 dtype=th.float32, random_reset_time: bool = False, drag_random: float = 0):
         assert action_type in ("bodyrate", "thrust", "velocity", "position")
         assert integrator in ("euler", "rk4")
         self.num, self.action_type, self.integrator = num, action_type, integrator
@@ -166,10 +166,39 @@ class OracleDynamics:
         self.substeps = int(ctrl_dt / dt)                                          # dynamics.py:74
         self.fifo_depth = int(comm_delay / ctrl_dt)                                # dynamics.py:75
         self.M = OracleModel(cfg, dt, dtype, self.device)
-        self.wind = th.tensor(list(wind), dtype=dtype, device=self.device).reshape(3, 1)
+        self.drag_random = drag_random
+        self.k_lin_mean, self.k_quad_mean = self.M.k_lin, self.M.k_quad            # dynamics.py:129-130
         self.init_thrust = -(self.M.m * self.M.g / 4)[-1]
         self.init_omega = self.M.rotor_omega(self.init_thrust)
+        self._constructing = True      # the reference does not reset (hence does not draw drag) in its constructor
+        self.wind = th.zeros((3, 1), dtype=dtype, device=self.device)
         self.reset()
+        self._constructing = False
+        self._create_wind(wind)
+
+    def _create_wind(self, wind):
+        """dynamics.py:132-174.  Numbers: constant wind.  Six strings: ``wind = f1(t, wind_1) + f2(t, wind_2)``,
+        each component an expression in x (= t, (N,)) and y (= its previous value), re-evaluated at the start of
+        every control step (``update_wind``, :384-388).  (The reference's 3-string form builds 3-argument lambdas that
+        ``update_wind`` calls with two arguments: it raises at construction and is not restated.)"""
+        self.wind_fn = None
+        if isinstance(wind[0], str):
+            if len(wind) != 6:
+                raise ValueError("wind functions: a list of six expression strings")
+            fx = [eval("lambda x,y:" + w) for w in wind]
+            self.wind_fn = (lambda x, y: th.stack([fx[0](x, y[0]), fx[1](x, y[1]), fx[2](x, y[2])]),
+                            lambda x, y: th.stack([fx[3](x, y[0]), fx[4](x, y[1]), fx[5](x, y[2])]))
+            self.wind_1, self.wind_2 = self._zeros(3), self._zeros(3)              # dynamics.py:172-173
+            self.update_wind()                                                     # dynamics.py:174
+        else:
+            self.wind = th.tensor(list(wind), dtype=self.dtype, device=self.device).reshape(3, 1)
+
+    def update_wind(self):                                                         # dynamics.py:384-388
+        if self.wind_fn is None:
+            return
+        self.wind_1 = self.wind_fn[0](self.t, self.wind_1)
+        self.wind_2 = self.wind_fn[1](self.t, self.wind_2)
+        self.wind = self.wind_1 + self.wind_2
 
     # -- state ---------------------------------------------------------------------------------
     def _zeros(self, k, n=None):
@@ -195,6 +224,10 @@ class OracleDynamics:
             self.ang_acc = self._zeros(3) if ang_acc is None else cv(ang_acc).T
             self.acc = self._zeros(3)
             self.fifo: List[th.Tensor] = [self._zeros(4) for _ in range(self.fifo_depth)]
+            if self.drag_random and not self._constructing:                        # dynamics.py:244-246
+                dr = self.drag_random
+                self.M.k_lin = self.k_lin_mean * (((th.rand_like(self.k_lin_mean) - 0.5) * 2 * dr).clamp(-0.5, .5) + 1)
+                self.M.k_quad = self.k_quad_mean * (((th.rand_like(self.k_quad_mean) - 0.5) * 2 * dr).clamp(-0.5, .5) + 1)
         else:
             idx = th.as_tensor(indices, device=self.device)
             m = len(idx)
@@ -367,6 +400,7 @@ class OracleDynamics:
     def step(self, action):
         """``action`` (N,4) in [-1,1]  ->  ``state`` (N,13)                        dynamics.py:319-372"""
         M = self.M
+        self.update_wind()                                                        # dynamics.py:320
         action = th.as_tensor(action, dtype=self.dtype, device=self.device)
         if self.fifo_depth:                                                       # dynamics.py:323-326
             self.fifo.append(action.T.clone())

@@ -46,23 +46,23 @@ def test_abi_version_and_struct_layout():
 def test_argument_validation_needs_no_gpu():
     lib = _lib.load()
     p = vf_params()
-    assert lib.vf_step_fwd(None, 4, 4, 0, 1, 1, None, None, None, None, None, None) != 0
+    assert lib.vf_step_fwd(None, 4, 4, 0, 1, 1, None, None, None, None, None, None, None) != 0
     assert b"params" in lib.vf_last_error()
-    assert lib.vf_step_fwd(ctypes.byref(p), 4, 0, 0, 1, 1, None, None, None, None, None, None) != 0
+    assert lib.vf_step_fwd(ctypes.byref(p), 4, 0, 0, 1, 1, None, None, None, None, None, None, None) != 0
     assert b"substeps" in lib.vf_last_error()
-    assert lib.vf_step_fwd(ctypes.byref(p), 4, 4, 7, 1, 1, None, None, None, None, None, None) != 0
+    assert lib.vf_step_fwd(ctypes.byref(p), 4, 4, 7, 1, 1, None, None, None, None, None, None, None) != 0
     assert b"integrator" in lib.vf_last_error()
-    assert lib.vf_step_fwd(ctypes.byref(p), 4, 4, 0, 4, 1, None, None, None, None, None, None) != 0
+    assert lib.vf_step_fwd(ctypes.byref(p), 4, 4, 0, 4, 1, None, None, None, None, None, None, None) != 0
     assert b"action_type" in lib.vf_last_error()
     # velocity (2) / position (3) run forward only: the adjoint entry points refuse them
-    assert lib.vf_step_bwd(ctypes.byref(p), 4, 4, 0, 3, 1, None, None, None, None, None, None, None) != 0
+    assert lib.vf_step_bwd(ctypes.byref(p), 4, 4, 0, 3, 1, None, None, None, None, None, None, None, None) != 0
     assert b"no gradient for the velocity / position" in lib.vf_last_error()
-    assert lib.vf_step_fwd(ctypes.byref(p), 4, 4, 0, 1, 1, None, None, None, None, None, None) != 0
+    assert lib.vf_step_fwd(ctypes.byref(p), 4, 4, 0, 1, 1, None, None, None, None, None, None, None) != 0
     assert b"NULL" in lib.vf_last_error()
-    assert lib.vf_step_bwd(ctypes.byref(p), 4, 65, 0, 1, 1, None, None, None, None, None, None, None) != 0
+    assert lib.vf_step_bwd(ctypes.byref(p), 4, 65, 0, 1, 1, None, None, None, None, None, None, None, None) != 0
     assert b"VF_MAX_SUBSTEPS_BWD" in lib.vf_last_error()
     # empty batch is a no-op, not an error
-    assert lib.vf_step_fwd(ctypes.byref(p), 0, 4, 0, 1, 1, None, None, None, None, None, None) == 0
+    assert lib.vf_step_fwd(ctypes.byref(p), 0, 4, 0, 1, 1, None, None, None, None, None, None, None) == 0
 
 
 def test_params_match_reference_constants():

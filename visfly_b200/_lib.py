@@ -15,7 +15,7 @@ from .params import VfEnvMirror, VfEnvSpec, VfParams
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvisfly_b200.so")
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 INTEGRATOR_ID = {"euler": 0, "rk4": 1}
 FLAG_CTRL_DELAY = 1
@@ -32,8 +32,8 @@ SIGNATURES = {
     "vf_last_error": (ctypes.c_char_p, []),
     "vf_params_size": (_i, []),
     "vf_device_sm_count": (_i, []),
-    "vf_step_fwd": (_i, [_P(VfParams), _i, _i, _i, _i, _u, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "vf_step_bwd": (_i, [_P(VfParams), _i, _i, _i, _i, _u, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "vf_step_fwd": (_i, [_P(VfParams), _i, _i, _i, _i, _u, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "vf_step_bwd": (_i, [_P(VfParams), _i, _i, _i, _i, _u, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "vf_step_fwd_host": (_i, [_P(VfParams), _i, _i, _i, _i, _u, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "vf_pack_state": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "vf_unpack_state": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
@@ -121,19 +121,20 @@ def _stream(device) -> int:
 
 def step_fwd(params: VfParams, substeps: int, integrator: int, action_type: int, flags: int,
              state_in: th.Tensor, action: th.Tensor, state_out: th.Tensor, obs_out: Optional[th.Tensor],
-             ext_out: Optional[th.Tensor]) -> None:
+             ext_out: Optional[th.Tensor], wind: Optional[th.Tensor] = None) -> None:
     lib = load(require_cuda=True)
     n = state_in.shape[1]
     with th.cuda.device(state_in.device):
         _check(lib.vf_step_fwd(ctypes.byref(params), n, substeps, integrator, action_type, flags,
                                _dev_ptr(state_in, "state_in"), _dev_ptr(action, "action"),
                                _dev_ptr(state_out, "state_out"), _dev_ptr(obs_out, "obs_out"),
-                               _dev_ptr(ext_out, "ext_out"), _stream(state_in.device)))
+                               _dev_ptr(ext_out, "ext_out"), _dev_ptr(wind, "wind"), _stream(state_in.device)))
 
 
 def step_bwd(params: VfParams, substeps: int, integrator: int, action_type: int, flags: int,
              state_in: th.Tensor, action: th.Tensor, g_state_out: Optional[th.Tensor],
-             g_obs: Optional[th.Tensor], g_state_in: th.Tensor, g_action: th.Tensor) -> None:
+             g_obs: Optional[th.Tensor], g_state_in: th.Tensor, g_action: th.Tensor,
+             wind: Optional[th.Tensor] = None) -> None:
     lib = load(require_cuda=True)
     n = state_in.shape[1]
     with th.cuda.device(state_in.device):
@@ -141,7 +142,7 @@ def step_bwd(params: VfParams, substeps: int, integrator: int, action_type: int,
                                _dev_ptr(state_in, "state_in"), _dev_ptr(action, "action"),
                                _dev_ptr(g_state_out, "grad_state_out"), _dev_ptr(g_obs, "grad_obs"),
                                _dev_ptr(g_state_in, "grad_state_in"), _dev_ptr(g_action, "grad_action"),
-                               _stream(state_in.device)))
+                               _dev_ptr(wind, "wind"), _stream(state_in.device)))
 
 
 def step_fwd_host(params: VfParams, substeps: int, integrator: int, action_type: int, flags: int,

@@ -135,7 +135,8 @@ template <int INTEG, int ACT, bool LAG, int BLOCK>
 __global__ void __launch_bounds__(BLOCK)
 vf_step_fwd_kernel(const __grid_constant__ VfParams params, int n, int substeps,
                    const float* __restrict__ state_in, const float* __restrict__ action,
-                   float* __restrict__ state_out, float* __restrict__ obs_out, float* __restrict__ ext_out) {
+                   float* __restrict__ state_out, float* __restrict__ obs_out, float* __restrict__ ext_out,
+                   const float* __restrict__ wind) {
     __shared__ __align__(16) float s_obs[(BLOCK / 32) * kWarpObs];
     const vf::Params<float>& P = reinterpret_cast<const vf::Params<float>&>(params);
     const int i = blockIdx.x * BLOCK + threadIdx.x;
@@ -148,11 +149,16 @@ vf_step_fwd_kernel(const __grid_constant__ VfParams params, int n, int substeps,
 
     vf::State<float> s;
     vf::Wrench<float> k;
+    float wd[3] = {P.wind[0], P.wind[1], P.wind[2]};
     if (live) {
         load_state(state_in, n, i, s);
         const float4 a4 = ldg4(action, size_t(i));
         const float a[4] = {a4.x, a4.y, a4.z, a4.w};
-        vf::step_fwd<float>(P, substeps, INTEG, ACT, LAG, a, s, k);
+        if (wind) {                                  // per-agent wind of this control step (wind functions)
+            const float4 w4 = ldg4(wind, size_t(i));
+            wd[0] = w4.x; wd[1] = w4.y; wd[2] = w4.z;
+        }
+        vf::step_fwd<float>(P, substeps, INTEG, ACT, LAG, a, s, k, wd);
         store_state(state_out, n, i, s);
         if (ext_out) {
             stg4(ext_out, size_t(2) * i, make_float4(k.acc[0], k.acc[1], k.acc[2], 0.f));
@@ -164,7 +170,7 @@ vf_step_fwd_kernel(const __grid_constant__ VfParams params, int n, int substeps,
         if (live) {
             o[0] = s.p[0]; o[1] = s.p[1]; o[2] = s.p[2];
             o[3] = s.q[0]; o[4] = s.q[1]; o[5] = s.q[2]; o[6] = s.q[3];
-            o[7] = s.v[0] + P.wind[0]; o[8] = s.v[1] + P.wind[1]; o[9] = s.v[2] + P.wind[2];
+            o[7] = s.v[0] + wd[0]; o[8] = s.v[1] + wd[1]; o[9] = s.v[2] + wd[2];
             o[10] = s.w[0]; o[11] = s.w[1]; o[12] = s.w[2];
         }
         warp_store_obs(obs_out, s_obs + warp * kWarpObs, n, warp_first, lane, o);
@@ -179,7 +185,7 @@ __global__ void __launch_bounds__(BLOCK)
 vf_step_bwd_kernel(const __grid_constant__ VfParams params, int n, int substeps,
                    const float* __restrict__ state_in, const float* __restrict__ action,
                    const float* __restrict__ g_state_out, const float* __restrict__ g_obs,
-                   float* __restrict__ g_state_in, float* __restrict__ g_action) {
+                   float* __restrict__ g_state_in, float* __restrict__ g_action, const float* __restrict__ wind) {
     __shared__ __align__(16) float s_obs[(BLOCK / 32) * kWarpObs];
     const vf::Params<float>& P = reinterpret_cast<const vf::Params<float>&>(params);
     const int i = blockIdx.x * BLOCK + threadIdx.x;
@@ -215,7 +221,12 @@ vf_step_bwd_kernel(const __grid_constant__ VfParams params, int n, int substeps,
     const float a[4] = {a4.x, a4.y, a4.z, a4.w};
     vf::Tape<float> tape[SMAX];
     float ga[4];
-    vf::step_bwd<float>(P, substeps, INTEG, ACT, LAG, a, s0, g, ga, tape);
+    float wd[3] = {P.wind[0], P.wind[1], P.wind[2]};
+    if (wind) {                                      // only the position clamp's gradient gate depends on it
+        const float4 w4 = ldg4(wind, size_t(i));
+        wd[0] = w4.x; wd[1] = w4.y; wd[2] = w4.z;
+    }
+    vf::step_bwd<float>(P, substeps, INTEG, ACT, LAG, a, s0, g, ga, tape, wd);
     store_state(g_state_in, n, i, g);
     stg4(g_action, size_t(i), make_float4(ga[0], ga[1], ga[2], ga[3]));
 }
@@ -575,27 +586,27 @@ int check_spec(const VfEnvSpec* spec) {
 
 template <int INTEG, int ACT, bool LAG>
 void launch_fwd(const VfParams& p, int n, int substeps, const float* si, const float* a, float* so, float* obs,
-                float* ext, cudaStream_t st) {
+                float* ext, const float* wind, cudaStream_t st) {
     switch (block_override()) {
-        case 32: launch_pdl(vf_step_fwd_kernel<INTEG, ACT, LAG, 32>, (n + 31) / 32, 32, st, p, n, substeps, si, a, so, obs, ext); return;
-        case 128: launch_pdl(vf_step_fwd_kernel<INTEG, ACT, LAG, 128>, (n + 127) / 128, 128, st, p, n, substeps, si, a, so, obs, ext); return;
-        case 256: launch_pdl(vf_step_fwd_kernel<INTEG, ACT, LAG, 256>, (n + 255) / 256, 256, st, p, n, substeps, si, a, so, obs, ext); return;
+        case 32: launch_pdl(vf_step_fwd_kernel<INTEG, ACT, LAG, 32>, (n + 31) / 32, 32, st, p, n, substeps, si, a, so, obs, ext, wind); return;
+        case 128: launch_pdl(vf_step_fwd_kernel<INTEG, ACT, LAG, 128>, (n + 127) / 128, 128, st, p, n, substeps, si, a, so, obs, ext, wind); return;
+        case 256: launch_pdl(vf_step_fwd_kernel<INTEG, ACT, LAG, 256>, (n + 255) / 256, 256, st, p, n, substeps, si, a, so, obs, ext, wind); return;
         default: break;
     }
     const int grid = (n + kBlock - 1) / kBlock;
-    launch_pdl(vf_step_fwd_kernel<INTEG, ACT, LAG, kBlock>, grid, kBlock, st, p, n, substeps, si, a, so, obs, ext);
+    launch_pdl(vf_step_fwd_kernel<INTEG, ACT, LAG, kBlock>, grid, kBlock, st, p, n, substeps, si, a, so, obs, ext, wind);
 }
 
 template <int INTEG, int ACT, bool LAG>
 void launch_bwd(const VfParams& p, int n, int substeps, const float* si, const float* a, const float* gso,
-                const float* gobs, float* gsi, float* ga, cudaStream_t st) {
+                const float* gobs, float* gsi, float* ga, const float* wind, cudaStream_t st) {
     const int grid = (n + kBlock - 1) / kBlock;
     if (substeps <= 8)
-        launch_pdl(vf_step_bwd_kernel<INTEG, ACT, LAG, 8, kBlock>, grid, kBlock, st, p, n, substeps, si, a, gso, gobs, gsi, ga);
+        launch_pdl(vf_step_bwd_kernel<INTEG, ACT, LAG, 8, kBlock>, grid, kBlock, st, p, n, substeps, si, a, gso, gobs, gsi, ga, wind);
     else if (substeps <= 16)
-        launch_pdl(vf_step_bwd_kernel<INTEG, ACT, LAG, 16, kBlock>, grid, kBlock, st, p, n, substeps, si, a, gso, gobs, gsi, ga);
+        launch_pdl(vf_step_bwd_kernel<INTEG, ACT, LAG, 16, kBlock>, grid, kBlock, st, p, n, substeps, si, a, gso, gobs, gsi, ga, wind);
     else
-        launch_pdl(vf_step_bwd_kernel<INTEG, ACT, LAG, VF_MAX_SUBSTEPS_BWD, kBlock>, grid, kBlock, st, p, n, substeps, si, a, gso, gobs, gsi, ga);
+        launch_pdl(vf_step_bwd_kernel<INTEG, ACT, LAG, VF_MAX_SUBSTEPS_BWD, kBlock>, grid, kBlock, st, p, n, substeps, si, a, gso, gobs, gsi, ga, wind);
 }
 
 template <int INTEG, int ACT, bool LAG>
@@ -693,16 +704,16 @@ int vf_device_sm_count(void) {
 
 int vf_step_fwd(const VfParams* params, int n, int substeps, int integrator, int action_type, unsigned flags,
                 const float* state_in, const float* action, float* state_out, float* obs_out, float* ext_out,
-                void* stream) {
+                const float* wind, void* stream) {
     if (check_common(params, n, substeps, integrator, action_type)) return 1;
     if (n == 0) return 0;
     if (!state_in || !action || !state_out) return fail("state_in, action and state_out must not be NULL");
     if (state_in == state_out) return fail("state_out must not alias state_in");
     if (!aligned16(state_in) || !aligned16(action) || !aligned16(state_out) || !aligned16(obs_out) ||
-        !aligned16(ext_out))
+        !aligned16(ext_out) || !aligned16(wind))
         return fail("all buffers must be 16-byte aligned");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    VF_DISPATCH_FWD(launch_fwd, *params, n, substeps, state_in, action, state_out, obs_out, ext_out, st);
+    VF_DISPATCH_FWD(launch_fwd, *params, n, substeps, state_in, action, state_out, obs_out, ext_out, wind, st);
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return fail("vf_step_fwd launch failed", err);
     return 0;
@@ -710,18 +721,18 @@ int vf_step_fwd(const VfParams* params, int n, int substeps, int integrator, int
 
 int vf_step_bwd(const VfParams* params, int n, int substeps, int integrator, int action_type, unsigned flags,
                 const float* state_in, const float* action, const float* grad_state_out, const float* grad_obs,
-                float* grad_state_in, float* grad_action, void* stream) {
+                float* grad_state_in, float* grad_action, const float* wind, void* stream) {
     if (check_common(params, n, substeps, integrator, action_type, true)) return 1;
     if (substeps > VF_MAX_SUBSTEPS_BWD) return fail("substeps exceeds VF_MAX_SUBSTEPS_BWD for the reverse sweep");
     if (n == 0) return 0;
     if (!state_in || !action || !grad_state_in || !grad_action)
         return fail("state_in, action, grad_state_in and grad_action must not be NULL");
     if (!aligned16(state_in) || !aligned16(action) || !aligned16(grad_state_out) || !aligned16(grad_obs) ||
-        !aligned16(grad_state_in) || !aligned16(grad_action))
+        !aligned16(grad_state_in) || !aligned16(grad_action) || !aligned16(wind))
         return fail("all buffers must be 16-byte aligned");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     VF_DISPATCH(launch_bwd, *params, n, substeps, state_in, action, grad_state_out, grad_obs, grad_state_in,
-                grad_action, st);
+                grad_action, wind, st);
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return fail("vf_step_bwd launch failed", err);
     return 0;
@@ -737,7 +748,7 @@ int vf_step_fwd_host(const VfParams* params, int n, int substeps, int integrator
                                       cudaMemcpyHostToDevice, st);
     if (err != cudaSuccess) return fail("vf_step_fwd_host: H2D copy of the actions failed", err);
     if (vf_step_fwd(params, n, substeps, integrator, action_type, flags, state_in, action_dev, state_out, obs_dev,
-                    nullptr, stream))
+                    nullptr, nullptr, stream))
         return 1;
     if (obs_host) {
         err = cudaMemcpyAsync(obs_host, obs_dev, sizeof(float) * VF_OBS_FLOATS * size_t(n),

@@ -591,20 +591,23 @@ VF_HD void attitude_adj(const Params<T>& P, int integrator, const T tau[3], cons
 }
 
 // One full sub-step on the state (rotor lag -> wrench -> translation -> attitude -> renormalise).
+// `wind`: this agent's wind vector for the control step (time-varying wind functions, dynamics.py:136-165,384-388);
+// NULL = the constant P.wind.
 template <class T>
 VF_HD void substep_fwd(const Params<T>& P, int integrator, bool ctrl_delay, const Command<T>& c, State<T>& s,
-                       Wrench<T>& k) {
+                       Wrench<T>& k, const T* wind = nullptr) {
     wrench_fwd(P, ctrl_delay, c, s, k);
     const T h = P.dt;
+    const T* wd = wind ? wind : P.wind;
     if (integrator == VF_INTEGRATOR_RK4) {
         const T h2 = T(0.5) * h * h;
         for (int i = 0; i < 3; ++i) {
-            s.p[i] = s.p[i] + (s.v[i] + P.wind[i]) * h + k.acc[i] * h2;      // maths.py:381 (stage velocities)
+            s.p[i] = s.p[i] + (s.v[i] + wd[i]) * h + k.acc[i] * h2;          // maths.py:381 (stage velocities)
             s.v[i] = s.v[i] + k.acc[i] * h;                                   // maths.py:383
         }
     } else {
         for (int i = 0; i < 3; ++i) {
-            s.p[i] = s.p[i] + (s.v[i] + P.wind[i]) * h;                       // maths.py:344
+            s.p[i] = s.p[i] + (s.v[i] + wd[i]) * h;                           // maths.py:344
             s.v[i] = s.v[i] + k.acc[i] * h;                                   // maths.py:346
         }
     }
@@ -627,10 +630,10 @@ template <class T> VF_HD void clamp_state(const Params<T>& P, State<T>& s) {
 // On return s is the state after substeps*dt; k holds the last sub-step's wrench (acc, thrusts).
 template <class T>
 VF_HD void step_fwd(const Params<T>& P, int substeps, int integrator, int action_type, bool ctrl_delay,
-                    const T a[4], State<T>& s, Wrench<T>& k) {
+                    const T a[4], State<T>& s, Wrench<T>& k, const T* wind = nullptr) {
     Command<T> c;
     command_fwd(P, action_type, a, s, c);
-    for (int it = 0; it < substeps; ++it) substep_fwd(P, integrator, ctrl_delay, c, s, k);
+    for (int it = 0; it < substeps; ++it) substep_fwd(P, integrator, ctrl_delay, c, s, k, wind);
     clamp_state(P, s);
 }
 
@@ -642,7 +645,8 @@ template <class T> struct Tape {
 // Forward re-run for the reverse sweep: records each sub-step's inputs; `s` ends as the UNCLAMPED end state.
 template <class T>
 VF_HD void step_fwd_taped(const Params<T>& P, int substeps, int integrator, int action_type, bool ctrl_delay,
-                          const T a[4], const State<T>& s0, Command<T>& c, State<T>& s, Tape<T>* tape) {
+                          const T a[4], const State<T>& s0, Command<T>& c, State<T>& s, Tape<T>* tape,
+                          const T* wind = nullptr) {
     command_fwd(P, action_type, a, s0, c);
     s = s0;
     Wrench<T> k;
@@ -650,7 +654,7 @@ VF_HD void step_fwd_taped(const Params<T>& P, int substeps, int integrator, int 
         Tape<T>& t = tape[it];
         for (int i = 0; i < 4; ++i) { t.q[i] = s.q[i]; t.mot[i] = s.mot[i]; }
         for (int i = 0; i < 3; ++i) { t.v[i] = s.v[i]; t.w[i] = s.w[i]; }
-        substep_fwd(P, integrator, ctrl_delay, c, s, k);
+        substep_fwd(P, integrator, ctrl_delay, c, s, k, wind);
     }
 }
 
@@ -717,10 +721,11 @@ VF_HD void step_bwd_taped(const Params<T>& P, int substeps, int integrator, int 
 //   tape: scratch of at least `substeps` entries
 template <class T>
 VF_HD void step_bwd(const Params<T>& P, int substeps, int integrator, int action_type, bool ctrl_delay,
-                    const T a[4], const State<T>& s0, State<T>& g, T ga[4], Tape<T>* tape) {
+                    const T a[4], const State<T>& s0, State<T>& g, T ga[4], Tape<T>* tape,
+                    const T* wind = nullptr) {
     Command<T> c;
     State<T> s;
-    step_fwd_taped(P, substeps, integrator, action_type, ctrl_delay, a, s0, c, s, tape);
+    step_fwd_taped(P, substeps, integrator, action_type, ctrl_delay, a, s0, c, s, tape, wind);
     step_bwd_taped(P, substeps, integrator, action_type, ctrl_delay, s0, c, s, tape, g, ga);
 }
 

@@ -23,26 +23,6 @@ inline void check_f32_cuda(const at::Tensor& t, const char* what) {
                 " must be a contiguous float32 CUDA tensor");
 }
 
-// (state', obs) = one control step                                           -> vf_step_fwd
-std::tuple<at::Tensor, at::Tensor> step_fwd(int64_t params, int64_t substeps, int64_t integrator, int64_t action_type,
-                                            int64_t flags, const at::Tensor& state_in, const at::Tensor& action) {
-    check_f32_cuda(state_in, "state_in");
-    check_f32_cuda(action, "action");
-    const int64_t n = state_in.size(1);
-    TORCH_CHECK(state_in.dim() == 3 && state_in.size(0) == VF_STATE_PLANES && state_in.size(2) == 4,
-                "state_in must be (5, n, 4)");
-    TORCH_CHECK(action.numel() == 4 * n, "action must be (n, 4)");
-    c10::cuda::CUDAGuard guard(state_in.device());
-    at::Tensor state_out = at::empty_like(state_in);
-    at::Tensor obs = at::empty({n, VF_OBS_FLOATS}, state_in.options());
-    const int rc = vf_step_fwd(reinterpret_cast<const VfParams*>(params), int(n), int(substeps), int(integrator),
-                               int(action_type), unsigned(flags), state_in.data_ptr<float>(), action.data_ptr<float>(),
-                               state_out.data_ptr<float>(), obs.data_ptr<float>(), nullptr,
-                               c10::cuda::getCurrentCUDAStream(state_in.device().index()).stream());
-    TORCH_CHECK(rc == 0, "visfly_b200: ", vf_last_error());
-    return {state_out, obs};
-}
-
 // A tensor over a byte range of `slab`'s storage, built directly on a TensorImpl: ~0.1 us instead of the ~0.6 us a
 // dispatched view op (as_strided / narrow) costs.  The result shares the slab's storage (keeps it alive) but is an
 // ordinary, non-view tensor as far as autograd is concerned — which is what a fresh kernel output should be.
@@ -53,6 +33,33 @@ inline at::Tensor carve(const at::Tensor& slab, int64_t byte_offset, at::ScalarT
     impl->set_storage_offset(byte_offset / int64_t(c10::elementSize(dtype)));
     impl->set_sizes_contiguous(sizes);
     return t;
+}
+
+// (state', obs) = one control step                                           -> vf_step_fwd
+std::tuple<at::Tensor, at::Tensor> step_fwd(int64_t params, int64_t substeps, int64_t integrator, int64_t action_type,
+                                            int64_t flags, const at::Tensor& state_in, const at::Tensor& action,
+                                            const OptTensor& wind) {
+    check_f32_cuda(state_in, "state_in");
+    check_f32_cuda(action, "action");
+    if (wind.has_value()) {
+        check_f32_cuda(*wind, "wind");
+        TORCH_CHECK(wind->numel() == 4 * state_in.size(1), "wind must be (n, 4)");
+    }
+    const int64_t n = state_in.size(1);
+    TORCH_CHECK(state_in.dim() == 3 && state_in.size(0) == VF_STATE_PLANES && state_in.size(2) == 4,
+                "state_in must be (5, n, 4)");
+    TORCH_CHECK(action.numel() == 4 * n, "action must be (n, 4)");
+    c10::cuda::CUDAGuard guard(state_in.device());
+    const int64_t o_obs = (80 * n + 255) / 256 * 256;
+    at::Tensor slab = at::empty({o_obs + 4 * VF_OBS_FLOATS * n}, state_in.options().dtype(at::kByte));
+    at::Tensor state_out = carve(slab, 0, at::kFloat, {VF_STATE_PLANES, n, 4});
+    at::Tensor obs = carve(slab, o_obs, at::kFloat, {n, VF_OBS_FLOATS});
+    const int rc = vf_step_fwd(reinterpret_cast<const VfParams*>(params), int(n), int(substeps), int(integrator),
+                               int(action_type), unsigned(flags), state_in.data_ptr<float>(), action.data_ptr<float>(),
+                               state_out.data_ptr<float>(), obs.data_ptr<float>(), nullptr,
+                               static_cast<const float*>(ptr(wind)), c10::cuda::getCurrentCUDAStream(state_in.device().index()).stream());
+    TORCH_CHECK(rc == 0, "visfly_b200: ", vf_last_error());
+    return {state_out, obs};
 }
 
 // One fused env step                                                        -> vf_env_step_fwd
@@ -144,7 +151,9 @@ class EnvStepper {
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.doc() = "visfly_b200 host plumbing: output allocation + C-ABI launch in one call";
-    m.def("step_fwd", &step_fwd);
+    m.def("step_fwd", &step_fwd, py::arg("params"), py::arg("substeps"), py::arg("integrator"),
+          py::arg("action_type"), py::arg("flags"), py::arg("state_in"), py::arg("action"),
+          py::arg("wind") = py::none());
     py::class_<EnvStepper>(m, "EnvStepper")
         .def(py::init<int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, at::Tensor, at::Tensor, at::Tensor,
                       OptTensor, OptTensor, OptTensor, int64_t>())

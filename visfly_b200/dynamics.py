@@ -16,8 +16,10 @@ keep working; what is different is where the work happens:
 Deliberate deviations from the reference (documented in DESIGN.md): inputs of ``reset`` are copied (the
 reference aliases and later mutates them); the two per-step device synchronising asserts
 (dynamics.py:333, droneGymEnv.py:144) are opt-in via ``debug_checks``; ``t`` after a partial reset is 0 unless
-``random_reset_time=True`` (reference draws U(0, 2*pi), C9); string wind functions and ``drag_random`` are not
-fused yet and raise ``NotImplementedError``.  Action types ``velocity`` / ``position`` (geometric attitude
+``random_reset_time=True`` (reference draws U(0, 2*pi), C9).  The reference's wind functions (six expression
+strings, dynamics.py:136-151) are evaluated on the device once per control step and reach the kernel as a per-agent
+wind vector; ``drag_random`` re-draws the (shared) drag coefficients on every full reset like dynamics.py:244-246.
+Action types ``velocity`` / ``position`` (geometric attitude
 controller, reference dynamics.py:414-496, per-agent Python loop there) run forward in the same kernel; their
 backward raises, as the reference's own autograd does on that branch.
 """
@@ -40,27 +42,29 @@ _ALIAS = {"thrust": ACTION_TYPE.THRUST, "bodyrate": ACTION_TYPE.BODYRATE,
 class StepConfig:
     """Everything ``vf_step_fwd`` / ``vf_step_bwd`` need besides tensors (immutable per Dynamics object)."""
 
-    __slots__ = ("params", "substeps", "integrator", "action_type", "flags")
+    __slots__ = ("params", "substeps", "integrator", "action_type", "flags", "params_addr")
 
     def __init__(self, params, substeps, integrator, action_type, flags):
+        import ctypes
         self.params, self.substeps, self.integrator = params, substeps, integrator
         self.action_type, self.flags = action_type, flags
+        #: address of the ``VfParams`` struct (owned by this object) for the C++ plumbing
+        self.params_addr = ctypes.addressof(params)
 
-    @property
-    def params_addr(self) -> int:
-        """Address of the ``VfParams`` struct (owned by this object) for the C++ plumbing."""
-        import ctypes
-        return ctypes.addressof(self.params)
+    def __deepcopy__(self, memo):
+        import copy
+        return StepConfig(copy.deepcopy(self.params, memo), self.substeps, self.integrator, self.action_type,
+                          self.flags)
 
 
 class ControlStep(th.autograd.Function):
     """``(state[5,N,4], action[N,4]) -> (state'[5,N,4], obs[N,13])`` — one kernel each way."""
 
     @staticmethod
-    def forward(ctx, state: th.Tensor, action: th.Tensor, cfg: StepConfig):
+    def forward(ctx, state: th.Tensor, action: th.Tensor, cfg: StepConfig, wind: Optional[th.Tensor] = None):
         state_out, obs = _lib.fast().step_fwd(cfg.params_addr, cfg.substeps, cfg.integrator, cfg.action_type,
-                                              cfg.flags, state, action)
-        ctx.cfg = cfg
+                                              cfg.flags, state, action, wind)
+        ctx.cfg, ctx.wind = cfg, wind
         ctx.save_for_backward(state, action)
         ctx.set_materialize_grads(False)
         return state_out, obs
@@ -77,8 +81,8 @@ class ControlStep(th.autograd.Function):
         if g_obs is not None:
             g_obs = g_obs.contiguous()
         _lib.step_bwd(cfg.params, cfg.substeps, cfg.integrator, cfg.action_type, cfg.flags,
-                      state, action, g_state_out, g_obs, g_state, g_action)
-        return g_state, g_action, None
+                      state, action, g_state_out, g_obs, g_state, g_action, ctx.wind)
+        return g_state, g_action, None, None
 
 
 class Dynamics:
@@ -131,8 +135,6 @@ class Dynamics:
         self._rotor_sim = rotor_sim
         self._debug_checks = debug_checks
         self._random_reset_time = random_reset_time
-        if drag_random:
-            raise NotImplementedError("drag_random (per-agent drag coefficients) is not fused yet")
         self._drag_random = drag_random
 
         self.set_seed(seed)
@@ -140,7 +142,7 @@ class Dynamics:
         self.m = self._model.m.to(self.device)
         self.name = self._model.name
         self._normal_params = action_scaling(self._model, self.action_type, action_space)
-        self._wind = self._parse_wind(wind_settings)
+        self._wind, self._wind_fn = self._parse_wind(wind_settings)
         self._params = build_vf_params(self._model, self.action_type, self._normal_params, self._wind)
         for v in self._normal_params.values():
             v.to(self.device)
@@ -150,18 +152,63 @@ class Dynamics:
         self.wind_velocity = th.tensor(self._wind, dtype=th.float32, device=self.device).reshape(3, 1)
         self._cfg = StepConfig(self._params, self._interval_steps, _lib.INTEGRATOR_ID[integrator],
                                self.action_type.value, _lib.FLAG_CTRL_DELAY if ctrl_delay else 0)
+        self._wind_rows = None                    # (N,4) per-agent wind handed to the kernel (wind functions only)
+        self._constructing = True
         self.reset()
+        self._constructing = False
+        if self._wind_fn is not None:             # reference dynamics.py:172-174
+            self._wind_1 = th.zeros((3, num), device=self.device)
+            self._wind_2 = th.zeros((3, num), device=self.device)
+            self.update_wind()
 
     # ------------------------------------------------------------------------------------------
     @staticmethod
-    def _parse_wind(wind_settings) -> Tuple[float, float, float]:
+    def _parse_wind(wind_settings):
+        """``(constant wind, None)`` or ``((0,0,0), (f1, f2))`` for the reference's wind functions
+        (dynamics.py:132-165): six expression strings in ``x`` (= per-agent time ``t``, shape (N,)) and ``y`` (= the
+        previous value of that wind component, shape (N,)); ``wind = f1(t, wind_1) + f2(t, wind_2)`` is re-evaluated
+        once per control step (:384-388).  The expressions are arbitrary Python, evaluated on the engine's device with
+        ordinary tensor ops; the kernel receives the resulting per-agent wind vector."""
         if wind_settings is None:
-            return (0.0, 0.0, 0.0)
+            return (0.0, 0.0, 0.0), None
         if isinstance(wind_settings, (list, tuple)) and len(wind_settings) == 3 and \
                 all(isinstance(w, (int, float)) for w in wind_settings):
-            return tuple(float(w) for w in wind_settings)
-        raise NotImplementedError("only constant wind [wx, wy, wz] is fused; string wind functions "
-                                  "(reference dynamics.py:136-165) are out of scope for now")
+            return tuple(float(w) for w in wind_settings), None
+        if isinstance(wind_settings, (list, tuple)) and len(wind_settings) == 6 and \
+                all(isinstance(w, str) for w in wind_settings):
+            fx = [eval("lambda x,y:" + w) for w in wind_settings]       # noqa: S307 — same contract as the reference
+            f1 = lambda x, y: th.stack([fx[0](x, y[0]), fx[1](x, y[1]), fx[2](x, y[2])])
+            f2 = lambda x, y: th.stack([fx[3](x, y[0]), fx[4](x, y[1]), fx[5](x, y[2])])
+            return (0.0, 0.0, 0.0), (f1, f2)
+        raise ValueError("wind_settings should be [wx, wy, wz] or a list of six expression strings in x (time) and "
+                         "y (previous value); the reference's 3-string form raises at construction "
+                         "(dynamics.py:158-161 builds 3-argument lambdas that update_wind calls with two)")
+
+    def update_wind(self):
+        """Reference dynamics.py:384-388: called at the start of every control step."""
+        if self._wind_fn is None:
+            return
+        t = self.t
+        self._wind_1 = self._wind_fn[0](t, self._wind_1)
+        self._wind_2 = self._wind_fn[1](t, self._wind_2)
+        self.wind_velocity = (self._wind_1 + self._wind_2).to(th.float32)
+        rows = th.zeros((self.num, 4), dtype=th.float32, device=self.device)
+        rows[:, :3] = self.wind_velocity.detach().T
+        self._wind_rows = rows
+        self._obs_t = None            # the reported velocity includes the wind (dynamics.py:750-752)
+
+    def _randomize_drag(self):
+        """Reference dynamics.py:244-246: the drag means are (3,1), so ONE random scale per axis is drawn and shared by
+        all agents; it becomes the k_lin / k_quad of the parameter block the kernels read.  (The reference's partial
+        reset, :265-267, indexes the (3,1) means with agent indices and raises for any index but 0; here a partial
+        reset keeps the coefficients.)"""
+        dr = self._drag_random
+        lin, quad = self._model.linear_drag, self._model.quad_drag
+        lin = lin * (((th.rand_like(lin) - 0.5) * 2 * dr).clamp(-0.5, .5) + 1)
+        quad = quad * (((th.rand_like(quad) - 0.5) * 2 * dr).clamp(-0.5, .5) + 1)
+        for i in range(3):
+            self._params.k_lin[i] = float(lin[i, 0])
+            self._params.k_quad[i] = float(quad[i, 0])
 
     def set_seed(self, seed=42):
         th.manual_seed(seed)
@@ -174,8 +221,9 @@ class Dynamics:
         t = x.detach() if isinstance(x, th.Tensor) else th.as_tensor(x)
         return t.to(device=self.device, dtype=th.float32, copy=True).reshape(-1, cols).contiguous()
 
-    def _assemble(self, n, pos, ori, vel, ori_vel, motor_omega):
-        """Rows of packed state (5,n,4) and observation (n,13) for freshly (re)initialised agents."""
+    def _assemble(self, n, pos, ori, vel, ori_vel, motor_omega, wind_t=None):
+        """Rows of packed state (5,n,4) and observation (n,13) for freshly (re)initialised agents.
+        ``wind_t``: (n,3) wind of exactly these agents when the wind is per-agent (wind functions)."""
         dev = self.device
         pos = th.zeros((n, 3), device=dev) if pos is None else self._f(pos, 3)
         vel = th.zeros((n, 3), device=dev) if vel is None else self._f(vel, 3)
@@ -189,7 +237,7 @@ class Dynamics:
         zero = th.zeros((n, 1), device=dev)       # angular acceleration restarts at 0 (dynamics.py:239,258)
         packed = th.stack([th.cat([pos, zero], 1), quat, th.cat([vel, zero], 1), th.cat([rate, zero], 1),
                            motor.to(th.float32)])
-        obs = th.cat([pos, quat, vel + self.wind_velocity.T, rate], 1)
+        obs = th.cat([pos, quat, vel + (self.wind_velocity.T if wind_t is None else wind_t), rate], 1)
         return packed.contiguous(), obs.contiguous()
 
     def reset(self, pos=None, ori=None, vel=None, ori_vel=None, motor_omega=None, thrusts=None, t=None,
@@ -206,10 +254,13 @@ class Dynamics:
             self._prev, self._ext, self._fresh = None, None, None
             self._t_steps = None
             self._thrusts_given = None if thrusts is None else self._f(thrusts, 4)
+            if self._drag_random and not self._constructing:
+                self._randomize_drag()
         else:
             idx = th.as_tensor(indices, device=dev, dtype=th.int64).reshape(-1)
             m = idx.numel()
-            rows, obs_rows = self._assemble(m, pos, ori, vel, ori_vel, motor_omega)
+            rows, obs_rows = self._assemble(m, pos, ori, vel, ori_vel, motor_omega,
+                                            self.wind_velocity.T[idx] if self.wind_velocity.shape[1] > 1 else None)
             # functional masked overwrite: the reset agents' upstream gradient is cut, the fresh state is a
             # constant — the reference's in-place index_put gives exactly this (dynamics.py:249-263, App. F)
             self._state = self._state.index_copy(1, idx, rows)
@@ -264,15 +315,28 @@ class Dynamics:
         """One control step; ``action`` is (N,4) in ``action_space``; returns ``state`` (reference :319-372)."""
         if not isinstance(action, th.Tensor):
             action = th.from_numpy(np.asarray(action))
-        action = action.to(device=self.device, dtype=th.float32)
+        if action.dtype is not th.float32 or action.device != self.device:
+            action = action.to(device=self.device, dtype=th.float32)
         if action.shape != (self.num, 4):
             raise ValueError(f"action must have shape ({self.num}, 4), got {tuple(action.shape)}")
         if self._comm_delay_steps:                                   # dynamics.py:323-326
             self._pre_action.append(action)
             action = self._pre_action.pop(0)
-        action = action.contiguous()
-        self._prev = (self._state.detach(), action.detach())
-        self._state, self._obs = ControlStep.apply(self._state, action, self._cfg)
+        if not action.is_contiguous():
+            action = action.contiguous()
+        state, cfg = self._state, self._cfg
+        if self._wind_fn is not None:
+            self.update_wind()                                       # dynamics.py:320
+        wind = self._wind_rows
+        if th.is_grad_enabled() and (state.requires_grad or action.requires_grad):
+            self._prev = (state.detach(), action.detach())
+            self._state, self._obs = ControlStep.apply(state, action, cfg, wind)
+        else:
+            # nothing to differentiate: straight to the launch (an autograd.Function costs ~8 us of host time per
+            # call even when no input requires grad; the kernel takes ~11 us at 65 536 agents)
+            self._prev = (state, action)
+            self._state, self._obs = _lib.fast().step_fwd(cfg.params_addr, cfg.substeps, cfg.integrator,
+                                                          cfg.action_type, cfg.flags, state, action, wind)
         self._n_steps += 1
         self._ext, self._fresh, self._thrusts_given = None, None, None
         if self._debug_checks:                                       # dynamics.py:333 (device sync!)
@@ -290,7 +354,7 @@ class Dynamics:
             else:
                 scratch = th.empty_like(self._prev[0])
                 _lib.step_fwd(self._cfg.params, self._cfg.substeps, self._cfg.integrator, self._cfg.action_type,
-                              self._cfg.flags, self._prev[0], self._prev[1], scratch, None, ext)
+                              self._cfg.flags, self._prev[0], self._prev[1], scratch, None, ext, self._wind_rows)
                 if self._fresh is not None:
                     m1 = self._fresh.view(-1, 1)
                     ext = th.cat([th.where(m1, 0.0, ext[:, :4]), th.where(m1, rest, ext[:, 4:])], 1)

@@ -195,6 +195,8 @@ class FusedEnvStep:
             return False
         if not env.envs.dynamics.is_quat_output or "_generate_state" in vars(env.envs):
             return False
+        if env.envs.dynamics._wind_fn is not None:      # per-agent wind functions: generic path (vf_step_fwd + wind)
+            return False
         s.max_episode_steps = int(env.max_episode_steps)
         s.collision_reset = int(bool(env.is_collision_reset))
         table = env.envs._reset_table
