@@ -338,3 +338,43 @@ def test_fused_env_step_runs_velocity_and_position_action_types(action_type):
     for (o1, r1, d1), (o2, r2, d2) in zip(run(True), run(False)):
         assert th.allclose(o1, o2, atol=2e-5, rtol=2e-5) and th.allclose(r1, r2, atol=2e-5) and th.equal(d1, d2)
     assert bool(th.stack([d for _, _, d in run(True)]).any())          # the runs cross auto-resets
+
+
+def test_config5_size_racing_shards_equal_the_whole_batch():
+    """BASELINE config 5 size: RacingEnv semantics, 524 288 agents = 8 shards of 65 536.  The fused env step of the
+    whole batch and of the eight contiguous shards (what eight ranks would run) give bitwise identical
+    observations, rewards and termination flags across auto-resets; unit quaternions, finite rewards, gate indices in
+    range throughout."""
+    from visfly_b200.envs import RacingEnv2
+    n, shards, T = 524288, 8, 7
+    m = n // shards
+    g = th.Generator().manual_seed(91)
+    pos = th.rand(n, 3, generator=g) * th.tensor([6.0, 6.0, 1.5]) + th.tensor([0.5, -3.0, 0.5])
+    quat = th.nn.functional.normalize(th.randn(n, 4, generator=g) * 0.1 + th.tensor([1.0, 0, 0, 0]), dim=1)
+    vel, rate = th.randn(n, 3, generator=g), th.randn(n, 3, generator=g) * 0.3
+    acts = (th.rand(T, n, 4, generator=g) * 2 - 1).cuda()
+
+    def run(lo, hi):
+        env = RacingEnv2(num_agent_per_scene=hi - lo, visual=False, device="cuda", tensor_output=True,
+                         dynamics_kwargs=dict(DYN["rk4"], comm_delay=0.06), max_episode_steps=4)
+        env.envs.set_reset_table(*(x[lo:hi].cuda() for x in (pos, quat, vel, rate)))
+        env.reset()
+        out = []
+        for t in range(T):
+            obs, r, d, info = env.step(acts[t, lo:hi])
+            out.append((obs["state"].clone(), obs["gate"].clone(), r.clone(), d.clone()))
+        assert env._fused.active
+        return out
+
+    whole = run(0, n)
+    for t in range(T):
+        st, gate, r, d = whole[t]
+        assert bool(th.isfinite(st).all() and th.isfinite(r).all())
+        assert float((st[:, 6:10].norm(dim=1) - 1).abs().max()) < 1e-5
+        assert int(gate.min()) >= 0 and int(gate.max()) <= 3
+    assert bool(whole[3][3].all())                      # step 4 truncates everybody: the resets are crossed
+    for k in range(shards):
+        part = run(k * m, (k + 1) * m)
+        for t in range(T):
+            for a, b in zip(whole[t], part[t]):
+                assert th.equal(a[k * m:(k + 1) * m], b), (k, t)

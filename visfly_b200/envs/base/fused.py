@@ -35,6 +35,8 @@ def generator_spec(gen, spec: P.VfEnvSpec) -> bool:
     kinds = set()
     for b, g in enumerate(boxes):
         if isinstance(g, UniformStateRandomizer):
+            if g.heading:                      # yaw towards the box centre: sampled by the generic path
+                return False
             kinds.add(P.GEN_UNIFORM)
             mean, half = g._mean, g._half
         elif isinstance(g, NormalStateRandomizer):

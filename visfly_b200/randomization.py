@@ -59,13 +59,17 @@ class UniformStateRandomizer(StateRandomizer):
     def __init__(self, position=_ZERO3, orientation=_ZERO3, velocity=_ZERO3, angular_velocity=_ZERO3,
                  heading=False, **kw):
         super().__init__(**kw)
-        if heading:
-            raise NotImplementedError("heading=True initial orientation is not supported yet")
         # one (4,3) mean and half-width table: a single rand call covers all four fields
         fields = (position, orientation, velocity, angular_velocity)
         self._mean = th.tensor([list(f["mean"]) for f in fields], dtype=th.float32)
         self._half = th.tensor([list(f["half"]) for f in fields], dtype=th.float32)
         self._deterministic = bool((self._half == 0).all())
+        #: reference :162-165 — the initial yaw points from the drawn position back to the centre of the position
+        #: box (roll = pitch = 0), plus the orientation noise; the orientation mean is not used
+        self.heading = bool(heading)
+        if self.heading and bool((self._half[0, :2] == 0).all()):
+            raise ValueError("heading=True needs a position box with a non-zero x or y half-width (the reference "
+                             "divides by the horizontal offset from the box centre, randomization.py:29)")
 
     def to(self, device):
         super().to(device)
@@ -79,6 +83,12 @@ class UniformStateRandomizer(StateRandomizer):
             s = self._mean.unsqueeze(0).expand(num, 4, 3)
         else:
             s = (2 * th.rand((num, 4, 3), device=self.device) - 1) * self._half + self._mean     # :153-169
+        if self.heading:
+            d = self._mean[0] - s[:, 0]                                   # direction = -half  (:163)
+            yaw = th.arccos(d[:, 0] / d[:, :2].norm(dim=1)) * th.where(d[:, 1].sign() >= 0, 1, -1)   # :27-28
+            ori = s[:, 1] - self._mean[1]                                 # the noise term of :165
+            ori = th.stack([ori[:, 0], ori[:, 1], ori[:, 2] + yaw], dim=1)
+            return s[:, 0], ori, s[:, 2], s[:, 3]
         return s[:, 0], s[:, 1], s[:, 2], s[:, 3]
 
 
