@@ -219,7 +219,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    r = cpu_reference_run(args.steps, args.warmup, budget_s=200.0)
+    r = cpu_reference_run(args.steps, args.warmup, budget_s=90.0)
     sample = f"OracleEnv(hover).step on {r['agents']} agents x {r['steps']} steps, {r['cores']} host threads"
     line = {
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
