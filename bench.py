@@ -262,7 +262,11 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     th.cuda.set_device(local)
     dev = th.device("cuda", local)
+    numa_cpus = None
     if world > 1:
+        # one rank per GPU: keep each rank's host thread and page-locked buffers on its GPU's NUMA node
+        from visfly_b200.distributed import bind_host_to_gpu
+        numa_cpus = bind_host_to_gpu(local)
         dist.init_process_group("nccl", device_id=dev)
     n, K, W = args.agents, args.steps, args.warmup
 
@@ -524,7 +528,8 @@ def run_ours(args):
                              "region, all host overhead included, after max(16 W, 600) untimed steps; value = the median of "
                              f"{BRACKETS} consecutive K-step brackets (bracket_ms lists them all); cold_l2_device_value = "
                              "one env, 256 MiB flush + one CUDA-event pair per step; hot_l2_bracketed_value = one env back to back",
-                       "parallelism": f"agents sharded over {world} GPU(s), one all_gather of episode returns per rollout"},
+                       "parallelism": f"agents sharded over {world} GPU(s), one all_gather of episode returns per rollout",
+                       "host_affinity": None if numa_cpus is None else f"rank 0 pinned to {len(numa_cpus)} CPUs next to its GPU"},
             "clocks": clk.summary(), "e2e": e2e, "gpu_launches": K * env_launches_per_step(env), "apg": apg,
             "roofline": roofline, "cpu_baseline": cpu, "reference_dynamics_on_gpu": ref_gpu,
             "dynamics_step_value_per_gpu": dynamics_step_value,

@@ -56,3 +56,12 @@ def test_gather_episode_returns_world2_gloo(n_total):
 def test_single_process_is_identity():
     x = th.arange(5.0)
     assert gather_episode_returns(x) is x
+
+
+def test_bind_host_to_gpu_degrades_to_a_no_op_without_a_gpu():
+    from visfly_b200.distributed import bind_host_to_gpu
+    before = os.sched_getaffinity(0)
+    got = bind_host_to_gpu(0)
+    assert got is None or set(got) <= before
+    if got is None:
+        assert os.sched_getaffinity(0) == before
