@@ -158,3 +158,26 @@ def test_all_reduce_is_a_no_op_without_a_process_group():
     lin(th.ones(1, 3)).sum().backward()
     g = lin.weight.grad.clone()
     assert all_reduce_gradients(lin.parameters()) == 1 and th.equal(g, lin.weight.grad)
+
+
+@pytest.mark.parametrize("n", [7, 512, 4096, 65536 // 8 + 512])
+def test_wide_batch_linear_equals_nn_linear(n):
+    """Same outputs, same gradients (weight, bias, input) as nn.Linear; sliced weight gradient for large batches."""
+    from visfly_b200.algorithms.policies import WideBatchLinear, _slices
+    th.manual_seed(n)
+    ref = th.nn.Linear(16, 64).double()
+    new = WideBatchLinear(16, 64).double()
+    new.load_state_dict(ref.state_dict())
+    x = th.randn(n, 16, dtype=th.float64)
+    g = th.randn(n, 64, dtype=th.float64)
+    xs = [x.clone().requires_grad_(True) for _ in range(2)]
+    outs = [m(xi) for m, xi in ((ref, xs[0]), (new, xs[1]))]
+    assert th.equal(outs[0], outs[1])
+    for o in outs:
+        (o * g).sum().backward()
+    assert th.allclose(xs[0].grad, xs[1].grad, rtol=1e-12, atol=1e-12)
+    assert th.allclose(ref.weight.grad, new.weight.grad, rtol=1e-11, atol=1e-11)
+    assert th.allclose(ref.bias.grad, new.bias.grad, rtol=1e-11, atol=1e-11)
+    assert _slices(65536) == 128 and _slices(7) == 1 and _slices(512) == 2 and 65536 % _slices(65536) == 0
+    with th.no_grad():
+        assert th.equal(new(x), ref(x))
