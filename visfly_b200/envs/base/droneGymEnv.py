@@ -27,6 +27,9 @@ from ._compat import VecEnv, spaces
 from .droneEnv import DroneEnvsBase
 
 
+_RecordInfo = None          # envs/base/fused.py:RecordInfo, bound on first use
+
+
 class LazyInfo(Sequence):
     """Per-agent info dicts materialised on demand from one snapshot of device tensors."""
 
@@ -233,7 +236,9 @@ class DroneGymEnvsBase(VecEnv):
         return out
 
     def _step_fused(self, host_action=None):
-        from .fused import RecordInfo
+        global _RecordInfo
+        if _RecordInfo is None:                  # resolved once (fused.py imports this module's siblings)
+            from .fused import RecordInfo as _RecordInfo
         if self.requires_grad and not self.tensor_output:
             raise ValueError("requires_grad should be False if tensor_output is False")
         slot = None if self.tensor_output else self._fused.host_slot()
@@ -246,9 +251,13 @@ class DroneGymEnvsBase(VecEnv):
                                                            mirror=None if slot is None else slot["ref"],
                                                            late_action=late)
         self._obs_tensors = self._fused_obs(obs)
-        term_obs = self._fused_obs(term) if term is not None else {}
-        info = RecordInfo(self.num_agent, record, term_obs, self.envs.dynamics.ctrl_dt,
-                          racing=self._fused.gate is not None)
+        if self._fused.gate is None:
+            # the terminal-observation dict is built only if somebody reads a finished agent's info
+            info = _RecordInfo(self.num_agent, record, term, self.envs.dynamics.ctrl_dt, False, self._fused_obs)
+        else:
+            # racing: the observation includes the gate index, a buffer later steps update in place -> build it now
+            info = _RecordInfo(self.num_agent, record, {} if term is None else self._fused_obs(term),
+                               self.envs.dynamics.ctrl_dt, True)
         self._info = info
         if self.tensor_output:                   # kernel outputs never carry autograd history: nothing to detach
             self._observations = self._obs_tensors

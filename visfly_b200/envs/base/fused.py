@@ -60,10 +60,20 @@ class RecordInfo(Sequence):
 
     _IDLE = {"TimeLimit.truncated": False, "episode_done": False}
 
-    def __init__(self, n, record: th.Tensor, term_obs: Dict[str, th.Tensor], ctrl_dt: float, racing: bool):
-        self._n, self._record, self._term, self._ctrl_dt, self._racing = n, record, term_obs, ctrl_dt, racing
+    def __init__(self, n, record: th.Tensor, term_obs, ctrl_dt: float, racing: bool, wrap_obs=None):
+        """``term_obs``: dict of terminal-observation fields, or (with ``wrap_obs``) the kernel's raw terminal-
+        observation tensor — it is turned into the dict only if somebody reads a finished agent's info."""
+        self._n, self._record, self._term_raw, self._ctrl_dt, self._racing = n, record, term_obs, ctrl_dt, racing
+        self._wrap = wrap_obs
         self._host = None
         self._cache: Dict[int, dict] = {}
+
+    @property
+    def _term(self):
+        if self._wrap is not None:
+            self._term_raw = {} if self._term_raw is None else self._wrap(self._term_raw)
+            self._wrap = None
+        return self._term_raw
 
     def _fetch(self):
         if self._host is None:
