@@ -38,12 +38,13 @@ def run(n, steps, replicas):
         wall = time.perf_counter() - t0
         row = (wall / steps * 1e6, t_launch / steps * 1e6, e0.elapsed_time(e1) / steps * 1e3)
         best = row if best is None or row[0] < best[0] else best
-    print(f"pdl={'off' if os.environ.get('VF_NO_PDL') else 'on '} n={n:8d} replicas={replicas:2d} steps={steps}: "
+    print(f"block={os.environ.get('VF_BLOCK', '64'):>3s} pdl={'off' if os.environ.get('VF_NO_PDL') else 'on '} n={n:8d} replicas={replicas:2d} steps={steps}: "
           f"wall {best[0]:6.2f} us/step  host-enqueue {best[1]:6.2f}  device {best[2]:6.2f}", flush=True)
 
 
 if __name__ == "__main__":
     run(65536, 3000, 1)
     run(65536, 3000, 16)
-    run(16384, 3000, 1)      # host-bound: the enqueue cost alone
-    run(1 << 20, 1000, 1)
+    if not os.environ.get("VF_PROBE_SHORT"):
+        run(16384, 3000, 1)      # host-bound: the enqueue cost alone
+        run(1 << 20, 1000, 1)
