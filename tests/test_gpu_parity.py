@@ -478,3 +478,37 @@ def test_habitat_pose_export_matches_reference_transform():
         assert np.array_equal(hp, ref_pos.astype(np.float32)) and np.array_equal(ho, ref_ori.astype(np.float32))
         sp, so = habitat_to_std(hp, ho)                      # round trip
         assert th.equal(sp, d.position.cpu()) and th.equal(so, d.orientation.cpu())
+
+
+def test_comm_delay_fifo_detects_in_place_reuse_of_action_tensors():
+    """The reference clones every action into its FIFO (dynamics.py:324); the engine keeps the caller's tensor and
+    refuses to continue if it was modified in place while it waited there."""
+    n = 64
+    kw = dict(action_type="bodyrate", integrator="euler", dt=0.005, ctrl_dt=0.02, comm_delay=0.06)
+    g = th.Generator().manual_seed(3)
+    acts = (th.rand(8, n, 4, generator=g) * 2 - 1).cuda()
+    ok = make_dynamics(n, **kw)
+    ref = th.stack([ok.step(acts[t]).clone() for t in range(8)])          # fresh tensors: fine
+    same = make_dynamics(n, **kw)
+    const = acts[0].clone()
+    for t in range(8):
+        same.step(const)                                                    # one unmodified tensor every step: fine
+    cloned = make_dynamics(n, **kw)
+    buf = th.empty(n, 4, device="cuda")
+    out = []
+    for t in range(8):
+        buf.copy_(acts[t])
+        out.append(cloned.step(buf.clone()).clone())                        # reused buffer, cloned: fine, same result
+    assert th.equal(th.stack(out), ref)
+    bad = make_dynamics(n, **kw)
+    with pytest.raises(RuntimeError, match="modified in place"):
+        for t in range(8):
+            buf.copy_(acts[t])
+            bad.step(buf)
+    from visfly_b200.envs import HoverEnv
+    env = HoverEnv(num_agent_per_scene=n, visual=False, device="cuda", tensor_output=True, dynamics_kwargs=dict(kw))
+    env.reset()
+    with pytest.raises(RuntimeError, match="modified in place"):
+        for t in range(8):
+            buf.copy_(acts[t])
+            env.step(buf)

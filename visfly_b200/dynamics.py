@@ -251,6 +251,7 @@ class Dynamics:
                 th.as_tensor(t, dtype=th.float32, device=dev).reshape(n).clone()
             self._n_steps = 0
             self._pre_action = [th.zeros((n, 4), device=dev) for _ in range(self._comm_delay_steps)]
+            self._fifo_versions = [None] * self._comm_delay_steps
             self._prev, self._ext, self._fresh = None, None, None
             self._t_steps = None
             self._thrusts_given = None if thrusts is None else self._f(thrusts, 4)
@@ -271,6 +272,7 @@ class Dynamics:
                 t_new = th.as_tensor(t, dtype=th.float32, device=dev).reshape(m)
             self._t_base = self._t_base.index_copy(0, idx, t_new - self._n_steps * self.ctrl_dt)
             self._pre_action = [a.index_fill(0, idx, 0.0) for a in self._pre_action]
+            self._fifo_versions = [None] * len(self._pre_action)
             fresh = th.zeros((self.num,), dtype=th.bool, device=dev).index_fill(0, idx, True)
             self._mark_fresh(fresh)
             if thrusts is not None:
@@ -295,6 +297,7 @@ class Dynamics:
             t_new = th.as_tensor(t, dtype=th.float32, device=self.device).reshape(n)
         self._t_base = th.where(mask, t_new - self._n_steps * self.ctrl_dt, self._t_base)
         self._pre_action = [th.where(m1, 0.0, a) for a in self._pre_action]
+        self._fifo_versions = [None] * len(self._pre_action)
         self._mark_fresh(mask)
         return self.state
 
@@ -308,7 +311,27 @@ class Dynamics:
         """Cut the autograd graph at the current state (reference dynamics.py:176-190)."""
         self._state = self._state.detach()
         self._obs = self._obs.detach()
-        self._pre_action = [a.detach() for a in self._pre_action]
+        self._pre_action = [a.detach() for a in self._pre_action]      # detach() shares the version counter
+
+    # -- comm-delay FIFO (reference dynamics.py:323-328) ----------------------------------------------------
+    # The reference stores a CLONE of every action (`action.T.clone()`); here the caller's tensor itself waits in the
+    # FIFO (a clone is one more launch per step on a path where the whole step is one launch).  The price is a rule
+    # — an action handed to step() must not be modified in place for comm_delay / ctrl_dt further steps — and the
+    # rule is enforced: the tensor's version counter is remembered and checked when the action is finally consumed.
+    def _fifo_push(self, action: th.Tensor):
+        self._pre_action.append(action)
+        self._fifo_versions.append((id(action), action._version))
+
+    def _fifo_pop(self) -> th.Tensor:
+        action = self._pre_action.pop(0)
+        rec = self._fifo_versions.pop(0)         # None: an entry the engine itself wrote (reset rows, zeros)
+        # the identity test skips entries that were re-created since (deepcopy of the env, detach): those are copies
+        # the engine owns, nothing outside can alias them
+        if rec is not None and rec[0] == id(action) and action._version != rec[1]:
+            raise RuntimeError(
+                "an action tensor was modified in place while it was waiting in the comm-delay FIFO "
+                f"({self._comm_delay_steps} control steps): pass a fresh tensor to step() each time, or action.clone()")
+        return action
 
     # ------------------------------------------------------------------------------------------
     def step(self, action) -> th.Tensor:
@@ -320,8 +343,8 @@ class Dynamics:
         if action.shape != (self.num, 4):
             raise ValueError(f"action must have shape ({self.num}, 4), got {tuple(action.shape)}")
         if self._comm_delay_steps:                                   # dynamics.py:323-326
-            self._pre_action.append(action)
-            action = self._pre_action.pop(0)
+            self._fifo_push(action)
+            action = self._fifo_pop()
         if not action.is_contiguous():
             action = action.contiguous()
         state, cfg = self._state, self._cfg

@@ -249,6 +249,7 @@ class FusedEnvStep:
         # FIFO rows the kernel treated as zero (agent younger than the entry) become real zeros again
         d = len(dyn._pre_action)
         dyn._pre_action = [th.where((self.sc < d - j).view(-1, 1), 0.0, a) for j, a in enumerate(dyn._pre_action)]
+        dyn._fifo_versions = [None] * len(dyn._pre_action)
         dyn._t_base = self.sc * dyn.ctrl_dt - dyn._n_steps * dyn.ctrl_dt
         dyn._t_steps = None
         env.envs.update_observation()
@@ -296,10 +297,10 @@ class FusedEnvStep:
         if not self.active:
             self.enter()
         if late_action is not None:
-            action = dyn._pre_action.pop(0)
+            action = dyn._fifo_pop()
         elif dyn._comm_delay_steps:
-            dyn._pre_action.append(action)
-            action = dyn._pre_action.pop(0)
+            dyn._fifo_push(action)
+            action = dyn._fifo_pop()
         if not action.is_contiguous():
             action = action.contiguous()
         state_in = dyn._state
@@ -308,7 +309,7 @@ class FusedEnvStep:
         else:
             state_out, obs, reward, done, record, term, _ = self._launch(state_in, action, False, mirror)
         if late_action is not None:
-            dyn._pre_action.append(late_action())
+            dyn._fifo_push(late_action())
         # keep the Dynamics object coherent (lazy views, diagnostics)
         dyn._prev = (state_in.detach(), action.detach()) if grad else (state_in, action)
         dyn._state = state_out
