@@ -141,3 +141,43 @@ def test_env_step_adjoint_float32_within_tolerance():
     ref_gs, ref_ga, _, _ = oracle_env_grads(task, integ, dt, packed, action, age, gate.long(), g_out, g_obs, g_rew, spec)
     got_gs, got_ga, _, _ = mirror_env(task, integ, dt, packed.float(), action, age, gate, g_out, g_obs, g_rew, spec, dtype=th.float32)
     assert rel_l2(got_gs, ref_gs) < 1e-4 and rel_l2(got_ga, ref_ga) < 1e-4
+
+
+@pytest.mark.parametrize("task", ["hover", "navigation", "racing2"])
+def test_env_reward_adjoint_matches_central_differences(task):
+    """Autograd-free check of the reward adjoints (csrc/vf_env.cuh): d(sum_i g_i * reward_i) / d(state, action) from
+    the reverse sweep against central differences of the forward env step, float64, for agents in smooth flight (not
+    finishing, older than the FIFO, away from the walls' proximity band and from the clamps)."""
+    n, integ, dt, eps = 6, "rk4", 0.0025, 1e-6
+    spec = make_spec(task, max_steps=1000)
+    pos, quat, vel, rate, motor, alpha = random_flight_state(n, seed=23, spread=0.5, dtype=th.float64)
+    pos = pos + th.tensor([2.0, 0.5, 2.0], dtype=th.float64)          # mid-air, metres away from every wall / target
+    vel = vel + th.tensor([0.8, -0.4, 0.3], dtype=th.float64)         # speed well above zero (norms are smooth)
+    packed = pack(pos, quat, vel, rate, motor, alpha)
+    age = th.full((n,), 7, dtype=th.int32)
+    gate = th.arange(n, dtype=th.int32) % 4
+    g = th.Generator().manual_seed(29)
+    action = (th.rand(n, 4, generator=g, dtype=th.float64) * 2 - 1) * 0.4
+    action[:, 0] -= 0.3
+    g_rew = th.randn(n, generator=g, dtype=th.float64)
+    zs, zo = th.zeros(5, n, 4, dtype=th.float64), th.zeros(n, 16 if task == "racing2" else 13, dtype=th.float64)
+
+    def weighted_reward(pk, ac):
+        _, _, rew, done = mirror_env(task, integ, dt, pk, ac, age, gate, zs, zo, g_rew, spec)
+        assert not bool(done.any())
+        return rew * g_rew                                            # per agent (agents are independent)
+
+    gs, ga, _, _ = mirror_env(task, integ, dt, packed, action, age, gate, zs, zo, g_rew, spec)
+    fd_s, fd_a = th.zeros_like(packed), th.zeros_like(action)
+    for plane in range(5):
+        for lane in range(4):
+            d = th.zeros_like(packed)
+            d[plane, :, lane] = eps
+            fd_s[plane, :, lane] = (weighted_reward(packed + d, action) - weighted_reward(packed - d, action)) / (2 * eps)
+    for j in range(4):
+        d = th.zeros_like(action)
+        d[:, j] = eps
+        fd_a[:, j] = (weighted_reward(packed, action + d) - weighted_reward(packed, action - d)) / (2 * eps)
+    assert float(fd_s.abs().max()) > 1e-4                             # the reward really depends on the state
+    assert rel_l2(gs, fd_s) < 1e-6, rel_l2(gs, fd_s)
+    assert rel_l2(ga, fd_a) < 1e-6, rel_l2(ga, fd_a)
