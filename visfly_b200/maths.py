@@ -57,7 +57,7 @@ class Quaternion:
         return self._q.shape[1]
 
     def __getitem__(self, idx):
-        return Quaternion.from_tensor(th.atleast_2d(self._q[:, idx].T).T)
+        return Quaternion.from_tensor(self._q[:, idx].reshape(4, -1))
 
     def __repr__(self):
         return f"Quaternion(wxyz={self._q.T})"
