@@ -47,3 +47,47 @@ def test_heading_needs_a_horizontal_extent():
         UniformStateRandomizer(heading=True, device="cpu",
                                position={"mean": [0.0, 0.0, 1.0], "half": [0.0, 0.0, 1.0]})
     assert math.isfinite(1.0)
+
+
+@pytest.mark.skipif(not reference_available(), reason="reference tree not mounted")
+def test_euler_to_quaternion_equals_the_reference_conversion():
+    load_reference()
+    from VisFly.utils.maths import Quaternion as RefQuaternion
+    g = th.Generator().manual_seed(5)
+    eul = (th.rand(500, 3, generator=g) * 2 - 1) * th.tensor([3.1, 1.5, 3.1])
+    ref = RefQuaternion.from_euler(*eul.T).toTensor().T                       # randomization.py:95
+    assert th.allclose(euler_zyx_to_quat(eul), ref, rtol=0, atol=1e-7)
+
+
+@pytest.mark.skipif(not reference_available(), reason="reference tree not mounted")
+def test_generators_draw_from_the_reference_distributions():
+    """Same families and moments as the reference classes (the random streams differ: one (num,4,3) draw here, four
+    (num,3) draws there), incl. the reference's `(2*randn - 1) * std + mean` for the normal generator (:201-204)."""
+    load_reference()
+    from VisFly.utils import randomization as R
+    from visfly_b200.randomization import NormalStateRandomizer, UnionRandomizer
+    n = 200_000
+    box = dict(position={"mean": [1.0, -2.0, 1.5], "half": [3.0, 2.0, 0.5]},
+               orientation={"mean": [0.0, 0.1, 0.2], "half": [0.1, 0.2, 0.3]},
+               velocity={"mean": [0.5, 0.0, -0.5], "half": [1.0, 2.0, 0.5]},
+               angular_velocity={"mean": [0.0, 0.0, 0.0], "half": [0.5, 0.5, 0.5]})
+    th.manual_seed(0)
+    ours = UniformStateRandomizer(device="cpu", **box).generate(n)
+    ref = R.UniformStateRandomizer(**box)._generate(n)
+    for a, b in zip(ours, ref):
+        assert th.allclose(a.mean(0), b.mean(0), atol=0.02) and th.allclose(a.std(0), b.std(0), atol=0.02)
+        assert th.allclose(a.amin(0), b.amin(0), atol=0.01) and th.allclose(a.amax(0), b.amax(0), atol=0.01)
+    nbox = {k: {"mean": v["mean"], "std": v["half"]} for k, v in box.items()}
+    # the reference's NormalStateRandomizer converts only `position` to a Normal (:196) and raises AttributeError on
+    # the orientation line of _generate (:200); the formula it writes for all four fields is what is implemented here
+    with pytest.raises(AttributeError):
+        R.NormalStateRandomizer(**nbox)._generate(4)
+    ours = NormalStateRandomizer(device="cpu", **nbox).generate(n)
+    for a, k in zip(ours, nbox):
+        mean, std = th.tensor(nbox[k]["mean"]), th.tensor(nbox[k]["std"])
+        assert th.allclose(a.mean(0), mean - std, atol=0.03) and th.allclose(a.std(0), 2 * std, atol=0.03)
+    two = [{"class": "Uniform", "kwargs": {"position": {"mean": [10.0, 0, 1], "half": [0.1, 0.1, 0.1]}}},
+           {"class": "Uniform", "kwargs": {"position": {"mean": [-10.0, 0, 1], "half": [0.1, 0.1, 0.1]}}}]
+    pos = UnionRandomizer(two, device="cpu").generate(20_000)[0]
+    assert abs(float((pos[:, 0] > 0).float().mean()) - 0.5) < 0.02                # each agent picks a box uniformly
+    assert float((pos[:, 0].abs() - 10).abs().max()) <= 0.1 + 1e-6
