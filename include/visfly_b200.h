@@ -13,7 +13,12 @@
  *     NULL = legacy default stream) and are CUDA-graph capturable; only the *_host entry points
  *     synchronise (they have to: they hand results back in host memory);
  *   - return value 0 = success, non-zero = error; `vf_last_error()` describes the last failure of
- *     the calling thread.
+ *     the calling thread;
+ *   - the four step kernels (vf_step_fwd/bwd, vf_env_step_fwd/bwd) are launched with programmatic stream
+ *     serialization (sm_90+): their CTAs may become resident while the preceding kernel on `stream` is still
+ *     running, but they touch no memory before that kernel has completed and its writes are visible
+ *     (griddepcontrol.wait), so stream order is what a caller observes.  Kernels of other libraries
+ *     before or after them need nothing special.  VF_NO_PDL=1 in the environment turns the attribute off.
  *
  * HBM layout of the agent state ("packed state", float32):
  *
