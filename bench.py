@@ -146,32 +146,52 @@ def hover_actions(n, count, device, seed=0):
 
 
 # ---------------------------------------------------------------------------------------------------------
-# reference arm / cpu baseline: the oracle port on the host cores
+# reference arm / cpu baseline: the UNMODIFIED reference (baseline/_ref copy or the live tree, runtime monkeypatches
+# R1-R3 + signature shims only, baseline/REF_PATCHES.md) on the host cores; the oracle port rides along
 # ---------------------------------------------------------------------------------------------------------
-def cpu_reference_run(steps: int, warmup: int, budget_s: float, agents: int = AGENTS):
-    """Times OracleEnv.step (hover task, same dynamics kwargs) on the CPU.  The agent count of the sample is
-    reduced (power of two) until `steps` steps fit the time budget."""
-    from oracle.env_oracle import OracleEnv
-    from oracle.torch_oracle import OracleDynamics
+def base_config(world: int) -> dict:
+    """`config` of the JSON line — identical in both arms."""
+    return {"workload": WORKLOAD, "agents_per_gpu": AGENTS, "substeps": 8, "actions": "smooth-hover law",
+            "l2": "inputs larger than L2 (16 rotating replicas of the 65536-agent env, no flush kernel in the timed region)",
+            "parallelism": f"agents sharded over {world} GPU(s), one all_gather of episode returns per rollout"}
+
+
+def _time_steps(step, acts, steps, warmup):
+    for i in range(warmup):
+        step(acts[i % len(acts)])
+    t0 = time.perf_counter()
+    for i in range(steps):
+        step(acts[i % len(acts)])
+    return time.perf_counter() - t0
+
+
+def reference_env_run(steps: int, warmup: int, budget_s: float, agents: int = AGENTS, with_port: bool = True):
+    """Times the real reference's HoverEnv.step (same dynamics kwargs; C4 shim + RK4 repairs as monkeypatches) on
+    the CPU.  The agent count of the sample is halved until `warmup + steps` steps fit the time budget.  Falls back
+    to the oracle port (kind "port") only where no reference tree is present."""
+    import warnings
+    warnings.filterwarnings("ignore")
+    from baseline.ref_loader import reference_available, reference_origin
     th.set_num_threads(os.cpu_count() or 1)
     cores = th.get_num_threads()
+    kind = "reference" if reference_available() else "port"
 
     def build(n):
-        table = None
-
-        def generate(indices=None):      # initial placement vectorised: reset is not part of the timed step
-            m = n if indices is None else len(indices)
-            pos = th.tensor([1., 0., 1.5]) + (th.rand(m, 3) * 2 - 1) * th.tensor([1.0, 1.0, 0.5])
-            quat = th.zeros(m, 4)
-            quat[:, 0] = 1
-            return pos, quat, th.zeros(m, 3), th.zeros(m, 3)
-        env = OracleEnv("hover", n, dict(DYN), max_episode_steps=256, generate_state=generate)
+        if kind == "reference":
+            from baseline.ref_loader import load_reference_envs
+            env = load_reference_envs()["HoverEnv"](num_agent_per_scene=n, visual=False, device="cpu",
+                                                    dynamics_kwargs=dict(DYN), max_episode_steps=256,
+                                                    tensor_output=True)
+        else:
+            env = port_env(n)
         env.reset()
         return env
 
     n = agents
     while True:
+        t0 = time.perf_counter()
         env = build(n)
+        reset_s = time.perf_counter() - t0
         acts = hover_actions(n, 4, "cpu")
         t0 = time.perf_counter()
         env.step(acts[0])
@@ -179,59 +199,117 @@ def cpu_reference_run(steps: int, warmup: int, budget_s: float, agents: int = AG
         if probe * (steps + warmup) <= budget_s or n <= 1024:
             break
         n //= 2
-    for i in range(warmup):
-        env.step(acts[i % 4])
-    t0 = time.perf_counter()
-    for i in range(steps):
-        env.step(acts[i % 4])
-    dt = time.perf_counter() - t0
-    # the dynamics alone (no wrapper loops), a few steps
-    dyn = OracleDynamics(n, **{k: v for k, v in DYN.items()})
-    dyn.step(acts[0])
+    dt = _time_steps(env.step, acts, steps, warmup)
+    out = {"value": n * steps / dt, "ms_per_step": 1e3 * dt / steps, "agents": n, "cores": cores, "steps": steps,
+           "kind": kind, "origin": reference_origin(), "reset_s": reset_s,
+           "what": ("VisFly HoverEnv.step, unmodified source + runtime patches R1-R3/C4" if kind == "reference"
+                    else "oracle/env_oracle.py OracleEnv(hover).step (op-by-op port)")}
     k = max(1, min(5, steps))
-    t1 = time.perf_counter()
-    for i in range(k):
-        dyn.step(acts[i % 4])
-    dyn_dt = (time.perf_counter() - t1) / k
-    return {"value": n * steps / dt, "ms_per_step": 1e3 * dt / steps, "agents": n, "cores": cores,
-            "dynamics_only_value": n / dyn_dt, "steps": steps}
+    if kind == "reference":
+        from baseline.ref_loader import load_reference_envs, make_reference_dynamics
+        dyn = make_reference_dynamics(n, **DYN)
+        dyn.reset()
+        out["dynamics_only_value"] = n * k / _time_steps(dyn.step, acts, k, 1)
+        # the one task env whose signatures match the base class as shipped: no shim at all
+        nav = load_reference_envs()["NavigationEnv"](num_agent_per_scene=min(n, 8192), visual=False, device="cpu",
+                                                     dynamics_kwargs=dict(DYN), max_episode_steps=256)
+        nav.reset()
+        nav_acts = hover_actions(min(n, 8192), 4, "cpu")
+        out["navigation_env_value"] = min(n, 8192) * k / _time_steps(nav.step, nav_acts, k, 1)
+        out["navigation_env_agents"] = min(n, 8192)
+    if with_port or kind == "port":
+        from oracle.torch_oracle import OracleDynamics
+        m = min(n, 16384)
+        pacts = hover_actions(m, 4, "cpu")
+        penv = port_env(m)
+        penv.reset()
+        out["port_value"] = m * k / _time_steps(penv.step, pacts, k, 1)
+        pdyn = OracleDynamics(m, **{kk: v for kk, v in DYN.items()})
+        out["port_dynamics_only_value"] = m * k / _time_steps(pdyn.step, pacts, k, 1)
+        out["port_agents"] = m
+        if kind == "port":
+            out["dynamics_only_value"] = out["port_dynamics_only_value"]
+    return out
+
+
+def port_env(n):
+    """oracle/env_oracle.py hover env with a vectorised initial placement (reset is not part of the timed step)."""
+    from oracle.env_oracle import OracleEnv
+
+    def generate(indices=None):
+        m = n if indices is None else len(indices)
+        pos = th.tensor([1., 0., 1.5]) + (th.rand(m, 3) * 2 - 1) * th.tensor([1.0, 1.0, 0.5])
+        quat = th.zeros(m, 4)
+        quat[:, 0] = 1
+        return pos, quat, th.zeros(m, 3), th.zeros(m, 3)
+    return OracleEnv("hover", n, dict(DYN), max_episode_steps=256, generate_state=generate)
 
 
 def reference_dynamics_on_gpu(n, dev, steps=5):
-    """north_star's second baseline: the reference's PyTorch dynamics executed on the B200 — the oracle port of
-    Dynamics.step (same aten-op sequence, ~8 200 launches per RK4x8 control step) with its tensors on the device."""
-    try:
-        from oracle.torch_oracle import OracleDynamics
-        dyn = OracleDynamics(n, device=dev, **{k: v for k, v in DYN.items()})
-        acts = hover_actions(n, 4, dev)
+    """north_star's second baseline: the reference's PyTorch dynamics executed on the B200.  The real reference
+    `Dynamics.step` (RK4 repairs R1-R3; device hygiene D1-D3 = run under torch.set_default_device, see
+    baseline/ref_loader.py) — ~8 200 aten launches per RK4x8 control step; the oracle port with its tensors on the
+    device is the fallback where the reference tree is absent or the reference raises on CUDA."""
+    acts = hover_actions(n, 4, dev)
+
+    def timed(step):
         with th.no_grad():
             for i in range(2):
-                dyn.step(acts[i])
+                step(acts[i])
             th.cuda.synchronize()
             t0 = time.perf_counter()
             for i in range(steps):
-                dyn.step(acts[i % 4])
+                step(acts[i % 4])
             th.cuda.synchronize()
-        dt = (time.perf_counter() - t0) / steps
-        return {"value": n / dt, "unit": UNIT, "ms_per_step": dt * 1e3, "agents": n, "kind": "port",
-                "what": "OracleDynamics.step (Dynamics.step only, no env wrapper) with all tensors on cuda"}
+        return (time.perf_counter() - t0) / steps
+
+    out = {}
+    try:
+        from baseline.ref_loader import make_reference_dynamics, reference_available, reference_on_device
+        if reference_available():
+            with reference_on_device(dev):
+                dyn = make_reference_dynamics(n, device=dev, **DYN)
+                dyn.reset()
+                dt = timed(dyn.step)
+            out = {"value": n / dt, "unit": UNIT, "ms_per_step": dt * 1e3, "agents": n, "kind": "reference",
+                   "what": "VisFly Dynamics.step (no env wrapper), unmodified source + runtime patches R1-R3, "
+                           "D1-D3 via torch.set_default_device(cuda)"}
     except Exception as e:  # noqa: BLE001 - a baseline must never take the bench down
-        return {"error": repr(e)[:200]}
+        out = {"reference_error": repr(e)[:300]}
+    if "value" not in out:
+        try:
+            from oracle.torch_oracle import OracleDynamics
+            dyn = OracleDynamics(n, device=dev, **{k: v for k, v in DYN.items()})
+            dt = timed(dyn.step)
+            out.update({"value": n / dt, "unit": UNIT, "ms_per_step": dt * 1e3, "agents": n, "kind": "port",
+                        "what": "OracleDynamics.step (Dynamics.step only, no env wrapper) with all tensors on cuda"})
+        except Exception as e:  # noqa: BLE001
+            out["error"] = repr(e)[:200]
+    return out
+
+
+def cpu_baseline_record(r):
+    sample = (f"{r['what']} on {r['agents']} agents x {r['steps']} steps ({r['ms_per_step']:.0f} ms/step), "
+              f"{r['cores']} host threads, reference tree: {r['origin']}")
+    rec = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": sample}
+    for k in ("dynamics_only_value", "navigation_env_value", "navigation_env_agents", "port_value",
+              "port_dynamics_only_value", "port_agents", "reset_s"):
+        if k in r:
+            rec[k] = r[k]
+    return rec
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    r = cpu_reference_run(args.steps, args.warmup, budget_s=90.0)
-    sample = f"OracleEnv(hover).step on {r['agents']} agents x {r['steps']} steps, {r['cores']} host threads"
+    r = reference_env_run(args.steps, args.warmup, budget_s=150.0, with_port=False)
     line = {
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "agents_in_sample": r["agents"], "device": "cpu"},
-        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": sample,
-                         "dynamics_only_value": r["dynamics_only_value"]},
+        "config": base_config(args.gpus),
+        "cpu_baseline": cpu_baseline_record(r),
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -255,10 +333,80 @@ def timed_steps(step_fn, steps, flush, stream):
     return [s.elapsed_time(e) for s, e in zip(starts, ends)]       # ms
 
 
+def rotating_brackets(envs, act_list, K, preroll, brackets, stream, barrier, collective=None):
+    """The contract's bracket over a set of independent env replicas that take turns (so that every step finds its
+    inputs evicted from L2 while launches stay back to back): after `preroll` untimed steps, `brackets` consecutive
+    brackets of exactly K steps (+ the rollout's one collective, if given), each opened behind barrier + synchronize
+    and closed by synchronising on the bracket's last CUDA event — no barrier, no other collective inside the
+    timed region.  Returns per bracket the device time (CUDA events on the launching stream) and the wall time."""
+    R, pool = len(envs), len(act_list)
+    for i in range(preroll):
+        envs[i % R].step(act_list[i % pool])
+    dev_ms, wall_ms = [], []
+    for _ in range(brackets):
+        barrier()
+        r0, r1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        r0.record(stream)
+        for i in range(K):
+            envs[i % R].step(act_list[i % pool])
+        if collective is not None:
+            collective()
+        r1.record(stream)
+        r1.synchronize()
+        wall_ms.append((time.perf_counter() - t0) * 1e3)
+        dev_ms.append(r0.elapsed_time(r1))
+    return dev_ms, wall_ms
+
+
+def median(xs):
+    return sorted(xs)[len(xs) // 2]
+
+
+def max_over_ranks(values, dev, world):
+    import torch.distributed as dist
+    t = th.tensor(list(values), device=dev, dtype=th.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return [float(x) for x in t]
+
+
+def racing_leg(n_weak, dev, rank, world, K, W, stream, barrier):
+    """BASELINE configs[4]: RacingEnv semantics (gates, radius 0.3, hover-style reward + 20 per gate, 16-wide
+    observation; reference envs/RacingEnv.py:87-98,142-148,203-215,250-267), RK4 x8, agents sharded over the GPUs:
+    weak scaling (65 536 agents per GPU) and strong scaling (524 288 agents in total, rank r owns shard_range(r))."""
+    from visfly_b200.distributed import EpisodeReturnsGather, shard_range, shard_seed
+    from visfly_b200.envs import RacingEnv2
+    out = {"workload": "RacingEnv2 visual=False RK4 dt=0.0025 ctrl_dt=0.02 bodyrate (BASELINE configs[4])"}
+    total_strong = 524288
+    lo, hi = shard_range(total_strong, rank, world)
+    for name, n, n_total in (("weak", n_weak, n_weak * world), ("strong", hi - lo, total_strong)):
+        replicas = max(2, -(-16 * 65536 // n))          # keep >= ~280 MB of per-step traffic in rotation (> L2)
+        envs = [RacingEnv2(num_agent_per_scene=n, visual=False, device=dev, dynamics_kwargs=dict(DYN),
+                           seed=shard_seed(42 + 1000 * j, rank), max_episode_steps=256, tensor_output=True)
+                for j in range(replicas)]
+        for e in envs:
+            e.reset()
+        pool = 4
+        act_list = list(hover_actions(n, pool, dev, seed=rank).unbind(0))
+        gather = EpisodeReturnsGather(n_total, rank, world, dev)
+        dev_ms, wall_ms = rotating_brackets(envs, act_list, K, max(W * replicas, HOT_PREROLL), BRACKETS, stream, barrier,
+                                            collective=lambda: gather(envs[0]._rewards))
+        ms = max_over_ranks([max(d, w) for d, w in zip(dev_ms, wall_ms)], dev, world)
+        t = median(ms)
+        out[name] = {"value": n_total * K / (t * 1e-3), "unit": UNIT, "agents_total": n_total, "agents_this_gpu": n,
+                     "ms_per_step": t / K, "bracket_ms": ms, "replicas": replicas,
+                     "fused": bool(envs[0]._fused is not None and envs[0]._fused.active),
+                     "scaling": name}
+        del envs, gather
+        th.cuda.empty_cache()
+    return out
+
+
 def run_ours(args):
     import torch.distributed as dist
     from visfly_b200 import _lib
-    from visfly_b200.distributed import gather_episode_returns
+    from visfly_b200.distributed import EpisodeReturnsGather
     from visfly_b200.envs import HoverEnv
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -295,6 +443,11 @@ def run_ours(args):
 
     for i in range(W):
         env_step(i)
+    # the one collective of the path: episode returns of all shards, once per rollout (a no-op at world 1); buffers
+    # and shard sizes are fixed ahead of the rollout, the call is one asynchronous all_gather_into_tensor
+    gather = EpisodeReturnsGather(n * world, rank, world, dev)
+    for _ in range(3):
+        gather(env._rewards)              # NCCL communicator set-up happens here, not in a timed bracket
     # long-lived objects (modules, the envs) leave the garbage collector's working set: a full collection walking
     # them costs ~1 ms, which is 50 env steps on this path
     import gc
@@ -307,67 +460,43 @@ def run_ours(args):
         # (A) cold L2: one CUDA-event pair per step, 256 MiB flush before every timed step
         per_step = timed_steps(env_step, K, flush, stream)
         barrier()
-        # the back-to-back loop gets its own warm-up: the host thread slept in the barrier above while the GPU drained
-        # the flush-heavy cold pass, and its core needs a few ms of work to clock back up (measured: 19.8 -> 17.1 ->
-        # 14.5 us/step over three consecutive 200-step loops); max(W, HOT_PREROLL) untimed steps bring it to steady state
-        for i in range(max(W, HOT_PREROLL)):
-            env_step(i)
-        barrier()
-        # (B) hot L2, the contract's bracket: barrier + synchronize, K steps back to back, events at both ends;
-        #     includes every host-side microsecond between launches and the rollout's one collective
-        e0, e1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
-        t0 = time.perf_counter()
-        e0.record(stream)
-        for i in range(K):
-            env_step(i)
-        # the one collective of the path: episode returns of all shards, once per rollout (no-op at world 1)
-        all_returns = gather_episode_returns(env._rewards)
-        e1.record(stream)
-        barrier()
-        wall_hot = time.perf_counter() - t0
-        dev_hot_ms = e0.elapsed_time(e1)
+        # (B) hot L2: one env back to back (its 12 MB working set stays in L2), same bracket as (C).  The host thread
+        #     slept in the barrier above while the GPU drained the flush-heavy cold pass and its core needs a few ms of
+        #     work to clock back up (measured: 19.8 -> 17.1 -> 14.5 us/step over three consecutive 200-step loops),
+        #     hence the untimed pre-roll
+        hot_dev, hot_wall = rotating_brackets([env], act_list, K, max(W, HOT_PREROLL), 1, stream, barrier,
+                                              collective=lambda: gather(env._rewards))
         # (C) THE reported value: the contract's bracket with inputs larger than L2 and no flush kernel inside it —
         #     REPLICAS independent copies of the 65 536-agent env take turns, so every step finds its state, actions
-        #     and env status evicted (REPLICAS x ~17 MB per step >> 126 MB L2) while launches stay back to back
+        #     and env status evicted (REPLICAS x ~17 MB per step >> 126 MB L2) while launches stay back to back.
+        #     BRACKETS consecutive brackets of exactly K steps + the rollout's collective; per bracket the max over
+        #     ranks of max(device time, wall time); the reported value is the MEDIAN bracket (all are listed).
         envs = [env] + [HoverEnv(num_agent_per_scene=n, visual=False, device=dev, dynamics_kwargs=dict(DYN),
                                  seed=42 + rank + 1000 * j, max_episode_steps=256, tensor_output=True)
                         for j in range(1, REPLICAS)]
         for e in envs[1:]:
             e.reset()
-
-        def rot_step(i):
-            envs[i % REPLICAS].step(act_list[i % pool])
-
-        for i in range(max(W * REPLICAS, HOT_PREROLL)):
-            rot_step(i)
-        # BRACKETS consecutive brackets of exactly K steps, each with barrier + synchronize on both sides and the
-        # max over ranks of max(device time, wall time); the reported value is the MEDIAN bracket (all of them are
-        # listed in the JSON line).  Host enqueue (~10 us) and device time (~12 us) per step are close, so a single
-        # 200-step bracket moves by +-15 % with one scheduler hiccup on the host core.
-        bracket_ms, bracket_dev_ms = [], []
-        for _ in range(BRACKETS):
-            barrier()
-            r0, r1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
-            t0 = time.perf_counter()
-            r0.record(stream)
-            for i in range(K):
-                rot_step(i)
-            all_returns = gather_episode_returns(env._rewards)
-            r1.record(stream)
-            barrier()
-            wall_rot = time.perf_counter() - t0
-            bracket_dev_ms.append(r0.elapsed_time(r1))
-            bracket_ms.append(max(bracket_dev_ms[-1], wall_rot * 1e3))
+        preroll = max(W * REPLICAS, HOT_PREROLL)
+        bracket_dev_ms, bracket_wall_ms = rotating_brackets(envs, act_list, K, preroll, BRACKETS, stream, barrier,
+                                                            collective=lambda: gather(env._rewards))
+        # (D) the same loop WITHOUT the collective: the step kernel's own launch-to-launch time (roofline.kernel_us)
+        nocoll_dev_ms, _ = rotating_brackets(envs, act_list, K, 50, BRACKETS, stream, barrier)
+        # (E) the collective alone, back to back
+        c0, c1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
+        barrier()
+        c0.record(stream)
+        for _ in range(10):
+            gather(env._rewards)
+        c1.record(stream)
+        c1.synchronize()
+        collective_us = c0.elapsed_time(c1) * 1e3 / 10 if world > 1 else 0.0
         del envs
     except BaseException:
         clk.__exit__(None, None, None)
         raise
-    tot = th.tensor([sum(per_step), max(dev_hot_ms, wall_hot * 1e3)] + bracket_ms, device=dev, dtype=th.float64)
-    if world > 1:
-        dist.all_reduce(tot, op=dist.ReduceOp.MAX)
-    cold_ms, hot_ms = float(tot[0]), float(tot[1])
-    bracket_ms = [float(x) for x in tot[2:]]
-    total_ms = sorted(bracket_ms)[len(bracket_ms) // 2]
+    bracket_ms = max_over_ranks([max(d, w) for d, w in zip(bracket_dev_ms, bracket_wall_ms)], dev, world)
+    cold_ms, hot_ms = max_over_ranks([sum(per_step), max(hot_dev[0], hot_wall[0])], dev, world)
+    total_ms = median(bracket_ms)
     cold_value = world * n * K / (cold_ms * 1e-3)
     hot_value = world * n * K / (hot_ms * 1e-3)
     value = world * n * K / (total_ms * 1e-3)
@@ -398,14 +527,13 @@ def run_ours(args):
     # the kernel env.step launches: the fused env step (control step + wrapper tail) on a private copy of the
     # per-agent env status, so that timing it does not disturb the env
     fz = env._fused
-    sc, ret, eb = fz.sc.clone(), fz.ret.clone(), fz.eb.clone()
+    status, status_o = fz.status.clone(), th.empty_like(fz.status)
     rew_o, done_o = th.empty(n, device=dev), th.empty(n, dtype=th.bool, device=dev)
     rec_o = th.empty((n, 4), device=dev)
 
     def kernel_only(i):
         _lib.env_step_fwd(cfg.params, fz.spec, cfg.substeps, cfg.integrator, cfg.action_type, cfg.flags, 0, 10_000 + i,
-                          st_in, acts[i % pool], None, sc, ret, eb, None, None, st_out, obs_out, rew_o, done_o, rec_o,
-                          None, None)
+                          st_in, acts[i % pool], None, status, st_out, status_o, obs_out, rew_o, done_o, rec_o, None)
 
     for i in range(5):
         kernel_only(i)
@@ -415,7 +543,7 @@ def run_ours(args):
     # of it (one per env.step, nothing else on the stream), CUDA events on the launching stream at both ends — an
     # upper bound of the kernel time (inter-launch gaps included), inputs cold (16 rotating replicas).  k_iso is the
     # same kernel launched alone behind a 256 MiB L2 flush with one event pair per launch (event overhead included).
-    k_avg = sorted(bracket_dev_ms)[len(bracket_dev_ms) // 2] * 1e-3 / K
+    k_avg = median(nocoll_dev_ms) * 1e-3 / K
     peak, peak_src = measured_peaks()
     achieved = ALGO_BYTES_FWD * n / k_avg / 1e9
     traffic = None
@@ -424,10 +552,13 @@ def run_ours(args):
         with open(tpath) as f:
             traffic = json.load(f).get("vf_env_step_fwd_kernel_bytes_per_launch")
     roofline = {"bound": "hbm", "kernel": "vf_env_step_fwd_kernel<RK4,BODYRATE,LAG>", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "traffic_source": "static: dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture "
+                                  "named in profiles/roofline_traffic.json (not re-measured in this run)",
+                "peak_source": peak_src,
                 "kernel_us": k_avg * 1e6, "kernel_us_isolated_cold_event_pair": k_iso * 1e6,
-                "timing": "device time of the median K-step bracket / K launches (CUDA events on the launching stream, "
-                          "cold inputs, one launch of this kernel per step)",
+                "timing": "device time of the median collective-free K-step bracket / K launches (CUDA events on the "
+                          "launching stream, cold inputs, one launch of this kernel per step, nothing else on the stream)",
                 "algorithmic_bytes_per_launch": ALGO_BYTES_FWD * n,
                 "bytes_moved_per_launch": MOVED_BYTES_FWD * n,
                 "fp32": {"achieved_tflops": FLOP_PER_AGENT_STEP * n / k_avg / 1e12, "peak_tflops": FP32_PEAK_TFLOPS,
@@ -441,14 +572,15 @@ def run_ours(args):
         b_in = st_in.repeat(1, big // n, 1).contiguous()
         b_out, b_obs = th.empty_like(b_in), th.empty((big, 13), device=dev)
         b_act = acts[0].repeat(big // n, 1).contiguous()
-        b_sc, b_ret, b_eb = sc.repeat(big // n), ret.repeat(big // n), eb.repeat(big // n)
+        b_status = status.repeat(big // n, 1).contiguous()
+        b_status_o = th.empty_like(b_status)
         b_rew, b_done = th.empty(big, device=dev), th.empty(big, dtype=th.bool, device=dev)
         b_rec = th.empty((big, 4), device=dev)
 
         def kernel_big(i):
             _lib.env_step_fwd(cfg.params, fz.spec, cfg.substeps, cfg.integrator, cfg.action_type, cfg.flags, 0,
-                              30_000 + i, b_in, b_act, None, b_sc, b_ret, b_eb, None, None, b_out, b_obs, b_rew, b_done,
-                              b_rec, None, None)
+                              30_000 + i, b_in, b_act, None, b_status, b_out, b_status_o, b_obs, b_rew, b_done, b_rec,
+                              None)
 
         for i in range(3):
             kernel_big(i)
@@ -457,7 +589,7 @@ def run_ours(args):
             "kernel_us": kb * 1e6, "achieved": ALGO_BYTES_FWD * big / kb / 1e9, "frac": ALGO_BYTES_FWD * big / kb / 1e9 / peak,
             "moved_gbs": MOVED_BYTES_FWD * big / kb / 1e9, "fp32_tflops": FLOP_PER_AGENT_STEP * big / kb / 1e12,
             "fp32_frac": FLOP_PER_AGENT_STEP * big / kb / 1e12 / FP32_PEAK_TFLOPS, "agent_steps_per_s": big / kb}
-        del b_in, b_out, b_obs, b_act, b_sc, b_ret, b_eb, b_rew, b_done, b_rec
+        del b_in, b_out, b_obs, b_act, b_status, b_status_o, b_rew, b_done, b_rec
     except Exception as e:  # noqa: BLE001 - a diagnostic must never take the bench down
         roofline["asymptote_4194304_agents"] = {"error": repr(e)[:200]}
 
@@ -465,12 +597,12 @@ def run_ours(args):
     from visfly_b200.params import VfEnvMirror
     m_obs, m_rew = th.empty((n, 13), pin_memory=True), th.empty(n, pin_memory=True)
     m_done = th.empty(n, dtype=th.int32, pin_memory=True)
-    mirror = VfEnvMirror(m_obs.data_ptr(), m_rew.data_ptr(), m_done.data_ptr())
+    mirror = VfEnvMirror(m_obs.data_ptr(), m_rew.data_ptr(), m_done.data_ptr(), None, None, 0)
 
     def kernel_mirror(i):
         _lib.env_step_fwd(cfg.params, fz.spec, cfg.substeps, cfg.integrator, cfg.action_type, cfg.flags, 0, 20_000 + i,
-                          st_in, acts[i % pool], None, sc, ret, eb, None, None, st_out, obs_out, rew_o, done_o, rec_o,
-                          None, None, mirror)
+                          st_in, acts[i % pool], None, status, st_out, status_o, obs_out, rew_o, done_o, rec_o, None,
+                          mirror)
 
     for i in range(5):
         kernel_mirror(i)
@@ -515,7 +647,9 @@ def run_ours(args):
                         "straight into page-locked host memory (zero-copy over PCIe), one stream sync per step"}
 
     # ---- config[2]: APG-style analytic policy gradient through NavigationEnv (requires_grad=True) -----------------
-    apg = apg_benchmark(n, dev, rank, world, barrier)
+    apg = None if args.no_apg else apg_benchmark(n, dev, rank, world, barrier)
+
+    racing = None if args.no_racing else racing_leg(n, dev, rank, world, K, W, stream, barrier)
     clk.__exit__(None, None, None)
 
     ref_gpu = None
@@ -524,25 +658,25 @@ def run_ours(args):
     if rank == 0:
         cpu = None
         if not args.no_cpu_baseline:
-            r = cpu_reference_run(steps=20, warmup=1, budget_s=25.0)
-            cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
-                   "sample": f"OracleEnv(hover).step on {r['agents']} agents x {r['steps']} steps "
-                             f"({r['ms_per_step']:.0f} ms/step), {r['cores']} host threads",
-                   "dynamics_only_value": r["dynamics_only_value"]}
+            cpu = cpu_baseline_record(reference_env_run(steps=10, warmup=1, budget_s=20.0, agents=16384))
+        cfg_line = base_config(world)
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K,
+            # untimed env.step calls that really precede the first timed bracket (the requested W is kept beside it)
+            "warmup": W + max(W, HOT_PREROLL) + preroll, "warmup_requested": W,
             "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "agents_per_gpu": n, "substeps": 8, "actions": "smooth-hover law",
-                       "l2": "inputs larger than L2: 16 independent replicas of the 65536-agent env take turns inside the "
-                             "bracketed K-step loop (16 x ~17 MB touched per step > 126 MB L2), no flush kernel in the timed "
-                             "region, all host overhead included, after max(16 W, 600) untimed steps; value = the median of "
-                             f"{BRACKETS} consecutive K-step brackets (bracket_ms lists them all); cold_l2_device_value = "
-                             "one env, 256 MiB flush + one CUDA-event pair per step; hot_l2_bracketed_value = one env back to back",
-                       "parallelism": f"agents sharded over {world} GPU(s), one all_gather of episode returns per rollout",
-                       "host_affinity": None if numa_cpus is None else f"rank 0 pinned to {len(numa_cpus)} CPUs next to its GPU"},
+            "dtype": "f32", "data": "synthetic", "config": cfg_line,
+            "measurement": {
+                "value": f"median of {BRACKETS} consecutive brackets of exactly K env.step calls + the rollout's one "
+                         "all_gather; each bracket opens behind barrier + synchronize and closes by synchronising on its "
+                         "last CUDA event (no barrier / extra collective inside); per bracket max over ranks of "
+                         "max(device time, wall time); bracket_ms lists them all",
+                "cold_l2_device_value": "one env, 256 MiB flush + one CUDA-event pair per step",
+                "hot_l2_bracketed_value": "one env back to back (12 MB working set resident in L2)",
+                "host_affinity": None if numa_cpus is None else f"rank 0 pinned to {len(numa_cpus)} CPUs next to its GPU"},
             "clocks": clk.summary(), "e2e": e2e, "gpu_launches": K * env_launches_per_step(env), "apg": apg,
-            "roofline": roofline, "cpu_baseline": cpu, "reference_dynamics_on_gpu": ref_gpu,
+            "racing": racing, "roofline": roofline, "cpu_baseline": cpu, "reference_dynamics_on_gpu": ref_gpu,
+            "rollout_collective_us": collective_us,
             "dynamics_step_value_per_gpu": dynamics_step_value,
             "cold_l2_device_value": cold_value, "hot_l2_bracketed_value": hot_value, "kernel_only_value": n / k_avg,
             "bracket_ms": bracket_ms,
@@ -621,6 +755,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--agents", type=int, default=AGENTS, help="agents per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-apg", action="store_true", help="skip the BASELINE configs[2] leg")
+    ap.add_argument("--no-racing", action="store_true", help="skip the BASELINE configs[4] leg")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

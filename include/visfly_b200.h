@@ -45,7 +45,7 @@
 extern "C" {
 #endif
 
-#define VF_ABI_VERSION 6
+#define VF_ABI_VERSION 7
 
 /* integrator: reference `integrator=` kwarg, utils/maths.py:331 (euler) and :353 (rk4, repaired R1-R3) */
 #define VF_INTEGRATOR_EULER 0
@@ -119,10 +119,16 @@ int vf_device_sm_count(void);
  *                         params->wind.  Carries the reference's time-varying wind functions
  *                         (dynamics.py:136-165, update_wind :384-388: evaluated by the caller once per control
  *                         step from t and the previous wind, then frozen over the sub-steps) (device, 16B aligned)
+ *   fifo_push  [n][4]     the action the caller handed to step() THIS control step, or NULL     (device, 16B aligned)
+ *   fifo_copy  [n][4]     receives a copy of fifo_push: the engine-owned comm-delay FIFO entry that will be consumed
+ *                         comm_delay/ctrl_dt steps later — the reference's `action.T.clone()` (dynamics.py:324) done by
+ *                         the same launch (+32 B per agent), so the caller may overwrite its action buffer right away.
+ *                         NULL together with fifo_push.                                         (device, 16B aligned)
  */
 int vf_step_fwd(const VfParams* params, int n, int substeps, int integrator, int action_type,
                 unsigned flags, const float* state_in, const float* action,
-                float* state_out, float* obs_out, float* ext_out, const float* wind, void* stream);
+                float* state_out, float* obs_out, float* ext_out, const float* wind,
+                const float* fifo_push, float* fifo_copy, void* stream);
 
 /*
  * Reverse-mode gradient of vf_step_fwd: re-runs the substeps from (state_in, action) in registers /
@@ -208,7 +214,7 @@ int vf_export_pose_habitat(const VfParams* params, int n, const float* state, fl
 
 #define VF_ENV_FLAG_NO_RESET 1u   /* is_test=True: report done but do not re-initialise (droneGymEnv.py:207)        */
 
-/* per-agent env status bits (in/out) */
+/* per-agent env status bits (low byte of VfEnvStatus word 2) */
 #define VF_EBIT_EPISODE_DONE  1u
 #define VF_EBIT_ONCE_COLLIDED 2u
 /* bits of the per-step episode record */
@@ -217,6 +223,16 @@ int vf_export_pose_habitat(const VfParams* params, int n, const float* state, fl
 #define VF_RBIT_SUCCESS       4u
 #define VF_RBIT_TRUNCATED     8u
 #define VF_RBIT_COLLIDED     16u
+
+/* Per-agent env status: ONE 16-byte record per agent (one 128-bit load and store), int32 status[n][4]:
+ *   word 0  step_count   steps since the agent's last reset                         (droneGymEnv.py:163)
+ *   word 1  returns      accumulated episode reward, float32 bit pattern            (droneGymEnv.py:185)
+ *   word 2  VF_EBIT_* in bits 0..7, next gate index in bits 8..15 (racing)          (RacingEnv.py:142-148)
+ *   word 3  gates passed this episode (racing)
+ * The step reads status_in and writes status_out; the two may be the same buffer (in place) or different ones
+ * (the start-of-step record then stays intact: it is what vf_env_step_bwd needs, and what a caller that runs
+ * steps ahead of its consumer rewinds to). */
+#define VF_STATUS_WORDS 4
 
 typedef struct VfEnvSpec {
     int   task;               /* VF_TASK_*                                                                        */
@@ -236,6 +252,8 @@ typedef struct VfEnvSpec {
     int   gen_boxes;          /* 1, or the number of boxes of a Union generator                                   */
     float gen_mean[VF_GEN_MAX_BOXES][4][3];   /* [box][position, euler orientation, velocity, body rate][xyz]     */
     float gen_half[VF_GEN_MAX_BOXES][4][3];   /* half width (uniform) or std (normal)                             */
+    int   gen_heading[VF_GEN_MAX_BOXES];      /* Uniform(heading=True): yaw points from the drawn position to the  */
+                                              /* centre of the position box, randomization.py:27-29,162-165       */
     float init_motor_omega;   /* hover rotor speed after reset, dynamics.py:86                                    */
     unsigned long long seed;  /* Philox key of the reset sampler                                                  */
 } VfEnvSpec;
@@ -246,53 +264,68 @@ int vf_env_spec_size(void);
  * numpy output mode, envs/base/droneGymEnv.py:218).  The pointers are page-locked host buffers (cudaHostAlloc /
  * cudaHostRegister; the library resolves their device alias with cudaHostGetDevicePointer): the kernel stores
  * observation, reward and done flag there directly (zero-copy over PCIe, overlapped with the arithmetic of the other
- * warps) in addition to the device outputs, so the step needs no device->host copy afterwards — only a stream
- * synchronisation before the host reads.  Any member may be NULL. */
+ * warps) in addition to the device outputs, so the step needs no device->host copy afterwards.  Any of obs / reward /
+ * done may be NULL.
+ * Completion word: if `flag` is set, the LAST thread block of the launch to finish stores `flag_value` into the
+ * page-locked word `flag` after every block's host stores are visible system-wide (each block: fence.sys, then one
+ * atomic on the device word `counter`, which must be zero before the launch and is zero again after it).  A host
+ * thread that spins on `*flag == flag_value` (vf_wait_flag) may then read the mirror without a stream
+ * synchronisation — and without waiting for whatever else was queued on the stream behind this launch. */
 typedef struct VfEnvMirror {
-    float* obs;      /* [n][13|16]                                                          */
-    float* reward;   /* [n]                                                                 */
-    int*   done;     /* [n]  0/1 as int32 (the reference returns done.astype(np.int32))     */
+    float*    obs;         /* [n][13|16]                                                          */
+    float*    reward;      /* [n]                                                                 */
+    int*      done;        /* [n]  0/1 as int32 (the reference returns done.astype(np.int32))     */
+    unsigned* flag;        /* page-locked host word, or NULL                                      */
+    unsigned* counter;     /* device word (zero), required with flag                              */
+    unsigned  flag_value;  /* what the last block stores into *flag                               */
 } VfEnvMirror;
+
+/* Spin until the page-locked word *flag equals value (see VfEnvMirror).  Returns 0, or 1 after timeout_us
+ * microseconds (timeout_us <= 0: wait forever). */
+int vf_wait_flag(const volatile unsigned* flag, unsigned value, long long timeout_us);
 
 /*
  * One env step for n agents.
- *   state_in/action/state_out   as vf_step_fwd (action = output of the caller's comm-delay FIFO)
- *   step_count  int32[n]  in/out   steps since the agent's last reset                 (droneGymEnv.py:163)
- *   returns     float[n]  in/out   accumulated episode reward                         (droneGymEnv.py:185)
- *   ebits       uint8[n]  in/out   VF_EBIT_*
- *   gate        int32[n]  in/out   next gate index (racing; NULL otherwise)           (RacingEnv.py:142-148)
- *   gates_passed int32[n] in/out   (racing; NULL otherwise)
- *   step_index             counter mixed into the reset sampler (use the env's global step number)
+ *   state_in/action/state_out, wind, fifo_push/fifo_copy   as vf_step_fwd (action = output of the comm-delay FIFO);
+ *                 the reported velocity, the rewards and the observation use v + wind of this step like the reference
+ *   status_in   int32[n][4]   VfEnvStatus records at the start of the step (see above)
+ *   status_out  int32[n][4]   records after the step (and after the auto-reset); may alias status_in
+ *   step_index              counter mixed into the reset sampler (the env's global step number) ...
+ *   step_base   device uint64*, or NULL: ... plus *step_base, read by the kernel — a caller that replays a captured
+ *                 CUDA graph bumps this word between replays so that every replay draws fresh restarts
  *   reset_table float[n][13]  rows [p q v w] for VF_GEN_TABLE, else NULL
  *   obs_out     float[n][13|16]  observation AFTER the auto-reset (what env.step returns)
  *   reward_out  float[n], done_out uint8[n]
  *   record_out  float[n][4]   [episode return, episode length, VF_RBIT_* as float, gates passed] of this step
  *   term_obs_out float[n][13|16] or NULL: observation BEFORE the reset, written only for finished agents
- *   saved_out   int32[n][2] or NULL: [step_count, gate] at the START of the step — what vf_env_step_bwd needs
  *   host_mirror NULL, or page-locked host destinations written in addition to obs_out / reward_out / done_out
  */
 int vf_env_step_fwd(const VfParams* params, const VfEnvSpec* spec, int n, int substeps, int integrator,
                     int action_type, unsigned flags, unsigned env_flags, unsigned long long step_index,
-                    const float* state_in, const float* action, const float* reset_table,
-                    int* step_count, float* returns, unsigned char* ebits, int* gate, int* gates_passed,
-                    float* state_out, float* obs_out, float* reward_out, unsigned char* done_out,
-                    float* record_out, float* term_obs_out, int* saved_out, const VfEnvMirror* host_mirror,
-                    void* stream);
+                    const unsigned long long* step_base,
+                    const float* state_in, const float* action, const float* wind, const float* fifo_push,
+                    const float* reset_table, const int* status_in,
+                    float* state_out, int* status_out, float* fifo_copy, float* obs_out, float* reward_out,
+                    unsigned char* done_out, float* record_out, float* term_obs_out,
+                    const VfEnvMirror* host_mirror, void* stream);
 
 /*
  * Reverse mode of vf_env_step_fwd with respect to (state_in, action), given the gradients of its differentiable
  * outputs: the packed state, the returned observation and the reward.  Re-runs the step from its inputs (nothing
- * else was stored), folds in the adjoint of the task reward (torch.autograd conventions, see csrc/vf_env.cuh) and of
- * the observation layout, then the adjoint of the control step.  An agent that finished in this step was
- * re-initialised inside it: its returned state/observation are constants, only its reward carries gradient — the
- * same graph the reference builds by overwriting rows in place (dynamics.py:249-263).
- *   saved        int32[n][2]  from vf_env_step_fwd        grad_state_out [5][n][4] or NULL
- *   grad_obs     float[n][13|16] or NULL                   grad_reward    float[n] or NULL
+ * else was stored: status_in is the forward's own input buffer, kept intact by an out-of-place status_out), folds in
+ * the adjoint of the task reward (torch.autograd conventions, see csrc/vf_env.cuh) and of the observation layout, then
+ * the adjoint of the control step.  An agent that finished in this step was re-initialised inside it: its returned
+ * state/observation are constants, only its reward carries gradient — the same graph the reference builds by
+ * overwriting rows in place (dynamics.py:249-263).
+ *   status_in    int32[n][4]  the forward's status_in          grad_state_out [5][n][4] or NULL
+ *   grad_obs     float[n][13|16] or NULL                        grad_reward    float[n] or NULL
+ *   wind         [n][4] the forward's per-agent wind, or NULL
  */
 int vf_env_step_bwd(const VfParams* params, const VfEnvSpec* spec, int n, int substeps, int integrator,
                     int action_type, unsigned flags, unsigned env_flags, const float* state_in,
-                    const float* action, const int* saved, const float* grad_state_out, const float* grad_obs,
-                    const float* grad_reward, float* grad_state_in, float* grad_action, void* stream);
+                    const float* action, const float* wind, const int* status_in, const float* grad_state_out,
+                    const float* grad_obs, const float* grad_reward, float* grad_state_in, float* grad_action,
+                    void* stream);
 
 #ifdef __cplusplus
 }

@@ -109,7 +109,7 @@ void env_fwd(const VfParams* params, const VfEnvSpec* E, int n, int substeps, in
         vf::Wrench<T> k;
         vf::step_fwd<T>(P, substeps, integrator, action_type, lag, a, s, k);
         vf::EnvEval<T> ev;
-        vf::env_eval<T>(P, *E, s, saved[2 * i] + 1, saved[2 * i + 1], false, ev);
+        vf::env_eval<T>(P, *E, s, P.wind, saved[2 * i] + 1, saved[2 * i + 1], false, ev);
         store_state(state_out, n, i, s);
         reward[i] = ev.reward;
         done[i] = ev.done ? 1 : 0;

@@ -41,28 +41,42 @@ def test_abi_version_and_struct_layout():
     body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
     fields = re.findall(r"float\s+([A-Za-z_]+)", body)
     assert fields == [f[0] for f in VfParams._fields_]
+    from visfly_b200.params import VfEnvMirror, VfEnvSpec
+    assert lib.vf_env_spec_size() == ctypes.sizeof(VfEnvSpec)
+    for name, cls in (("VfEnvSpec", VfEnvSpec), ("VfEnvMirror", VfEnvMirror)):
+        body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (name, name), hdr, flags=re.S).group(1)
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        fields = re.findall(r"(?:float|int|unsigned long long|unsigned)\s*\*?\s+([A-Za-z_]+)", body)
+        assert fields == [f[0] for f in cls._fields_], name
 
 
 def test_argument_validation_needs_no_gpu():
     lib = _lib.load()
     p = vf_params()
-    assert lib.vf_step_fwd(None, 4, 4, 0, 1, 1, None, None, None, None, None, None, None) != 0
+    assert lib.vf_step_fwd(None, 4, 4, 0, 1, 1, None, None, None, None, None, None, None, None, None) != 0
     assert b"params" in lib.vf_last_error()
-    assert lib.vf_step_fwd(ctypes.byref(p), 4, 0, 0, 1, 1, None, None, None, None, None, None, None) != 0
+    assert lib.vf_step_fwd(ctypes.byref(p), 4, 0, 0, 1, 1, None, None, None, None, None, None, None, None, None) != 0
     assert b"substeps" in lib.vf_last_error()
-    assert lib.vf_step_fwd(ctypes.byref(p), 4, 4, 7, 1, 1, None, None, None, None, None, None, None) != 0
+    assert lib.vf_step_fwd(ctypes.byref(p), 4, 4, 7, 1, 1, None, None, None, None, None, None, None, None, None) != 0
     assert b"integrator" in lib.vf_last_error()
-    assert lib.vf_step_fwd(ctypes.byref(p), 4, 4, 0, 4, 1, None, None, None, None, None, None, None) != 0
+    assert lib.vf_step_fwd(ctypes.byref(p), 4, 4, 0, 4, 1, None, None, None, None, None, None, None, None, None) != 0
     assert b"action_type" in lib.vf_last_error()
     # velocity (2) / position (3) run forward only: the adjoint entry points refuse them
     assert lib.vf_step_bwd(ctypes.byref(p), 4, 4, 0, 3, 1, None, None, None, None, None, None, None, None) != 0
     assert b"no gradient for the velocity / position" in lib.vf_last_error()
-    assert lib.vf_step_fwd(ctypes.byref(p), 4, 4, 0, 1, 1, None, None, None, None, None, None, None) != 0
+    assert lib.vf_step_fwd(ctypes.byref(p), 4, 4, 0, 1, 1, None, None, None, None, None, None, None, None, None) != 0
     assert b"NULL" in lib.vf_last_error()
     assert lib.vf_step_bwd(ctypes.byref(p), 4, 65, 0, 1, 1, None, None, None, None, None, None, None, None) != 0
     assert b"VF_MAX_SUBSTEPS_BWD" in lib.vf_last_error()
+    x = ctypes.c_void_p(16)
+    assert lib.vf_step_fwd(ctypes.byref(p), 4, 4, 0, 1, 1, x, x, ctypes.c_void_p(32), None, None, None, x, None, None) != 0
+    assert b"fifo_push and fifo_copy" in lib.vf_last_error()
+    assert lib.vf_wait_flag(None, 1, 10) != 0
+    flag = ctypes.c_uint(7)
+    assert lib.vf_wait_flag(ctypes.byref(flag), 7, 10) == 0                 # already raised
+    assert lib.vf_wait_flag(ctypes.byref(flag), 8, 2000) != 0 and b"timed out" in lib.vf_last_error()
     # empty batch is a no-op, not an error
-    assert lib.vf_step_fwd(ctypes.byref(p), 0, 4, 0, 1, 1, None, None, None, None, None, None, None) == 0
+    assert lib.vf_step_fwd(ctypes.byref(p), 0, 4, 0, 1, 1, None, None, None, None, None, None, None, None, None) == 0
 
 
 def test_params_match_reference_constants():

@@ -35,8 +35,10 @@ def _worker(rank, world, port, n_total, out):
     try:
         lo, hi = shard_range(n_total, rank, world)
         local = th.arange(lo, hi, dtype=th.float32) * 0.5          # "episode return" of agent i is i/2
-        full = gather_episode_returns(local)
-        ok = th.equal(full, th.arange(n_total, dtype=th.float32) * 0.5)
+        full = gather_episode_returns(local, n_total=n_total).clone()
+        again = gather_episode_returns(local + 1.0, n_total=n_total)      # cached gather object, buffers reused
+        ref = th.arange(n_total, dtype=th.float32) * 0.5
+        ok = th.equal(full, ref) and th.equal(again, ref + 1.0)
         mean_r, mean_l, cnt = rollout_stats(local.sum(), th.tensor(float(hi - lo) * 10), th.tensor(float(hi - lo)))
         ok = ok and cnt == n_total and abs(mean_l - 10.0) < 1e-9 and abs(mean_r - 0.5 * (n_total - 1) / 2) < 1e-6
         out[rank] = bool(ok)

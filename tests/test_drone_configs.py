@@ -62,7 +62,7 @@ def test_engine_matches_oracle_per_config(cfg, integ, dt):
     action = th.rand(n, 4, generator=g) * 2 - 1
     g_out, g_obs = th.randn(5, n, 4, generator=g), th.randn(n, 13, generator=g)
     st, ac = packed.cuda().requires_grad_(True), action.cuda().requires_grad_(True)
-    out, obs = ControlStep.apply(st, ac, eng._cfg)
+    out, obs, _ = ControlStep.apply(st, ac, None, eng._cfg)
     ((out * g_out.cuda()).sum() + (obs * g_obs.cuda()).sum()).backward()
     ref_gs, ref_ga = oracle_grads(make_oracle(n, "bodyrate", integ, dt, cfg=cfg, dtype=th.float64), packed.double(),
                                   action.double(), g_out.double(), g_obs.double())

@@ -480,35 +480,79 @@ def test_habitat_pose_export_matches_reference_transform():
         assert th.equal(sp, d.position.cpu()) and th.equal(so, d.orientation.cpu())
 
 
-def test_comm_delay_fifo_detects_in_place_reuse_of_action_tensors():
-    """The reference clones every action into its FIFO (dynamics.py:324); the engine keeps the caller's tensor and
-    refuses to continue if it was modified in place while it waited there."""
+def test_comm_delay_fifo_owns_a_copy_of_every_action_like_the_reference():
+    """The reference clones every action into its FIFO (`action.T.clone()`, dynamics.py:323-328), so a caller may
+    refill ONE preallocated action buffer in place every step.  Here the step launch itself makes that copy
+    (`fifo_push` -> `fifo_copy`): the in-place-reuse loop must fly exactly the trajectory of fresh tensors and of the
+    reference golden, through `Dynamics.step`, the fused env step and the generic env path; gradients reach the
+    action through the copy, and actions still waiting in the FIFO at the end of a rollout get exactly zero."""
+    from _util import make_oracle
     n = 64
     kw = dict(action_type="bodyrate", integrator="euler", dt=0.005, ctrl_dt=0.02, comm_delay=0.06)
     g = th.Generator().manual_seed(3)
     acts = (th.rand(8, n, 4, generator=g) * 2 - 1).cuda()
     ok = make_dynamics(n, **kw)
-    ref = th.stack([ok.step(acts[t]).clone() for t in range(8)])          # fresh tensors: fine
-    same = make_dynamics(n, **kw)
-    const = acts[0].clone()
-    for t in range(8):
-        same.step(const)                                                    # one unmodified tensor every step: fine
-    cloned = make_dynamics(n, **kw)
+    ref = th.stack([ok.step(acts[t]).clone() for t in range(8)])          # fresh tensors
+    orc = make_oracle(n, **kw)                                             # the reference's own FIFO (clone per step)
+    ref_cpu = th.stack([orc.step(acts[t].cpu()).clone() for t in range(8)])
+    assert rel_l2(ref.cpu(), ref_cpu) < TRAJ_TOL
+    reuse = make_dynamics(n, **kw)
     buf = th.empty(n, 4, device="cuda")
     out = []
     for t in range(8):
-        buf.copy_(acts[t])
-        out.append(cloned.step(buf.clone()).clone())                        # reused buffer, cloned: fine, same result
+        buf.copy_(acts[t])                                                  # legal with the reference: same buffer
+        out.append(reuse.step(buf).clone())
+        assert all(a.data_ptr() != buf.data_ptr() for a in reuse._pre_action)
     assert th.equal(th.stack(out), ref)
-    bad = make_dynamics(n, **kw)
-    with pytest.raises(RuntimeError, match="modified in place"):
-        for t in range(8):
-            buf.copy_(acts[t])
-            bad.step(buf)
+    # host actions (numpy) are converted on the way in: already private, no second copy
+    host = make_dynamics(n, **kw)
+    out = [host.step(acts[t].cpu().numpy()).clone() for t in range(8)]
+    assert th.equal(th.stack(out), ref)
     from visfly_b200.envs import HoverEnv
-    env = HoverEnv(num_agent_per_scene=n, visual=False, device="cuda", tensor_output=True, dynamics_kwargs=dict(kw))
-    env.reset()
+    runs = {}
+    for fused in (True, False):
+        for mode in ("fresh", "reuse"):
+            env = HoverEnv(num_agent_per_scene=n, visual=False, device="cuda", tensor_output=True, seed=5,
+                           dynamics_kwargs=dict(kw))
+            env.use_fused_step = fused
+            env.reset()
+            states = []
+            for t in range(8):
+                if mode == "reuse":
+                    buf.copy_(acts[t])
+                states.append(env.step(buf if mode == "reuse" else acts[t])[0]["state"].clone())
+            assert env._fused.active == fused
+            runs[fused, mode] = th.stack(states)
+        assert th.equal(runs[fused, "fresh"], runs[fused, "reuse"])
+    assert rel_l2(runs[True, "fresh"].cpu(), runs[False, "fresh"].cpu()) < 1e-6
+    # gradients: through the copy to the action that was pushed; nothing for actions that never left the FIFO
+    d = make_dynamics(n, **kw)
+    a = acts.clone().requires_grad_(True)
+    loss = 0.0
+    for t in range(8):
+        loss = loss + d.step(a[t]).pow(2).sum()
+    ga, = th.autograd.grad(loss, a)
+    assert float(ga[:5].abs().sum()) > 0 and float(ga[5:].abs().sum()) == 0.0       # depth 3: a[5:] were never flown
+    o = make_oracle(n, dtype=th.float64, **kw)
+    a64 = acts.cpu().double().requires_grad_(True)
+    lo = 0.0
+    for t in range(8):
+        lo = lo + o.step(a64[t]).pow(2).sum()
+    go, = th.autograd.grad(lo, a64)
+    assert rel_l2(ga.cpu(), go) < GRAD_TOL
+
+
+def test_diagnostics_notice_an_overwritten_action_without_a_fifo():
+    """comm_delay=0 keeps no copy of the action; the on-demand diagnostics re-run the step on its inputs and must
+    refuse if the caller has overwritten the action buffer in the meantime (instead of reporting a different step)."""
+    n = 32
+    d = make_dynamics(n, action_type="bodyrate", integrator="euler", dt=0.005, ctrl_dt=0.02, comm_delay=0.0)
+    buf = th.zeros(n, 4, device="cuda")
+    d.step(buf)
+    acc = d.acceleration.clone()
+    d.step(buf)
+    buf.add_(0.5)
     with pytest.raises(RuntimeError, match="modified in place"):
-        for t in range(8):
-            buf.copy_(acts[t])
-            env.step(buf)
+        d.acceleration
+    d.step(buf)
+    assert d.acceleration.shape == acc.shape

@@ -91,3 +91,27 @@ def test_generators_draw_from_the_reference_distributions():
     pos = UnionRandomizer(two, device="cpu").generate(20_000)[0]
     assert abs(float((pos[:, 0] > 0).float().mean()) - 0.5) < 0.02                # each agent picks a box uniformly
     assert float((pos[:, 0].abs() - 10).abs().max()) <= 0.1 + 1e-6
+
+
+@pytest.mark.skipif(not reference_available(), reason="reference tree not mounted")
+def test_evaluation_grid_walks_the_box_like_the_reference():
+    """`test=True` (reference randomization.py:141-160): start positions walk over a regular grid of the position box,
+    one grid point per generated agent.  The reference is called agent by agent (droneEnv.py:243-249); the vectorised
+    generator must hand agent k the same grid point (the U(-1,1)*xyz_half jitter is switched off to compare)."""
+    load_reference()
+    from VisFly.utils import randomization as R
+    box = dict(position={"mean": [1.0, -2.0, 1.5], "half": [3.0, 2.0, 0.5]})
+    kw = dict(test=True, xyz_num=[3, 2, 2], xyz_half=[0.0, 0.0, 0.0])
+    ref = R.UniformStateRandomizer(**box, **kw)
+    ref_pos = th.cat([ref._generate(1)[0] for _ in range(30)])
+    ours = UniformStateRandomizer(device="cpu", **box, **kw)
+    pos = th.cat([ours.generate(17)[0], ours.generate(13)[0]])            # two batches continue the walk
+    assert th.allclose(pos, ref_pos, atol=1e-6)
+    jit = UniformStateRandomizer(device="cpu", **box, test=True, xyz_num=[3, 2, 2], xyz_half=[0.0, 2.0, 0.0])
+    p2 = jit.generate(30)[0]
+    assert float((p2 - ref_pos)[:, [0, 2]].abs().max()) < 1e-6 and 0.5 < float((p2 - ref_pos)[:, 1].abs().max()) <= 2.0
+
+
+def test_unknown_generator_kwargs_are_rejected():
+    with pytest.raises(TypeError, match="unknown keyword"):
+        UniformStateRandomizer(device="cpu", positon={"mean": [0, 0, 0], "half": [1, 1, 1]})     # typo

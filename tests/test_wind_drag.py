@@ -120,7 +120,7 @@ def test_engine_wind_function_gradient_matches_autograd_through_the_oracle():
     g_out, g_obs = th.randn(5, n, 4, generator=g), th.randn(n, 13, generator=g)
     st, ac = packed.cuda().requires_grad_(True), action.cuda().requires_grad_(True)
     wind4 = th.cat([wind, th.zeros(n, 1)], 1).cuda().contiguous()
-    out, obs = ControlStep.apply(st, ac, dyn._cfg, wind4)
+    out, obs, _ = ControlStep.apply(st, ac, None, dyn._cfg, wind4)
     ((out * g_out.cuda()).sum() + (obs * g_obs.cuda()).sum()).backward()
     orc = OracleDynamics(n, "bodyrate", dt=dt, ctrl_dt=0.02, integrator="rk4", comm_delay=0.0, dtype=th.float64)
     orc.wind = wind.double().T.contiguous()
@@ -148,15 +148,49 @@ def test_engine_drag_random_matches_reference_golden():
 
 
 @pytest.mark.gpu
-def test_env_with_wind_functions_takes_the_generic_path_and_runs():
-    from visfly_b200.envs import HoverEnv
+def test_env_with_wind_functions_runs_the_one_kernel_path_and_matches_the_generic_one():
+    """Per-agent wind (the reference's wind functions, dynamics.py:136-165,384-388) inside the fused env step: the
+    wind is evaluated with tensor ops from the per-agent time, the kernel takes it as a (N,4) vector.  Same env through
+    the generic tensor-op path must give the same observations / rewards / dones, across an auto-reset; the gradient of
+    a short rollout agrees as well."""
+    from visfly_b200.envs import HoverEnv, NavigationEnv
     fn = ["0.5*th.sin(2*x)", "0.3*th.cos(x)", "0*x", "0.9*y+0.05", "0.8*y-0.02", "0*y"]
-    env = HoverEnv(num_agent_per_scene=64, visual=False, device="cuda", max_episode_steps=8, tensor_output=True,
-                   dynamics_kwargs=dict(action_type="bodyrate", integrator="rk4", dt=0.0025, ctrl_dt=0.02,
-                                        wind_settings=fn))
-    env.reset()
-    for _ in range(12):                                       # crosses an auto-reset
-        obs, reward, done, info = env.step(th.zeros(64, 4, device="cuda"))
-    assert env._fused is None or not env._fused.active
-    assert th.isfinite(obs["state"]).all() and env.envs.dynamics.wind_velocity.shape == (3, 64)
-    assert float(env.envs.dynamics.wind_velocity.abs().max()) > 0.1
+    n = 64
+    g = th.Generator().manual_seed(11)
+    pos = th.tensor([1.0, 0.0, 1.5]) + (th.rand(n, 3, generator=g) * 2 - 1) * 0.5
+    quat = th.tensor([[1.0, 0, 0, 0]]).repeat(n, 1)
+    acts = ((th.rand(12, n, 4, generator=g) * 2 - 1) * 0.2).cuda()
+    acts[..., 0] -= 1.0 / 3.0
+    runs = {}
+    for fused in (True, False):
+        env = HoverEnv(num_agent_per_scene=n, visual=False, device="cuda", max_episode_steps=8, tensor_output=True,
+                       dynamics_kwargs=dict(action_type="bodyrate", integrator="rk4", dt=0.0025, ctrl_dt=0.02,
+                                            wind_settings=fn))
+        env.envs.set_reset_table(pos.cuda(), quat.cuda())
+        env.use_fused_step = fused
+        env.reset()
+        out = []
+        for t in range(12):                                   # crosses an auto-reset at step 8
+            obs, reward, done, info = env.step(acts[t])
+            out.append((obs["state"].clone(), reward.clone(), done.clone()))
+        assert (env._fused is not None and env._fused.active) == fused
+        assert env.envs.dynamics.wind_velocity.shape == (3, n)
+        assert float(env.envs.dynamics.wind_velocity.abs().max()) > 0.1
+        runs[fused] = out
+    for (o1, r1, d1), (o2, r2, d2) in zip(runs[True], runs[False]):
+        assert rel_l2(o1.cpu(), o2.cpu()) < 1e-5 and th.allclose(r1, r2, atol=1e-5) and th.equal(d1, d2)
+    grads = {}
+    for fused in (True, False):
+        env = NavigationEnv(num_agent_per_scene=n, visual=False, device="cuda", max_episode_steps=5, requires_grad=True,
+                            dynamics_kwargs=dict(action_type="bodyrate", integrator="rk4", dt=0.0025, ctrl_dt=0.02,
+                                                 wind_settings=fn))
+        env.envs.set_reset_table(pos.cuda(), quat.cuda())
+        env.use_fused_step = fused
+        env.reset()
+        a = acts[:8].clone().requires_grad_(True)
+        loss = 0.0
+        for t in range(8):
+            obs, reward, done, info = env.step(a[t])
+            loss = loss - reward.mean() + 1e-3 * obs["state"].pow(2).mean()
+        grads[fused], = th.autograd.grad(loss, a)
+    assert rel_l2(grads[True].cpu(), grads[False].cpu()) < 1e-4

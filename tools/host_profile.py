@@ -34,13 +34,13 @@ stepper = fz._stepper or fz._make_stepper()
 st, ac = env.envs.dynamics._state, acts[0]
 t0 = time.perf_counter()
 for i in range(steps):
-    out = stepper.step(st, ac, i, 0, True, False, 0)
+    out = stepper.step(st, ac, fz.status, i, 0, True, 0)
 t1 = time.perf_counter()
 th.cuda.synchronize()
 print(f"EnvStepper.step alone (alloc + carve + launch + 7-tuple): {(t1 - t0) / steps * 1e6:.2f} us/call")
 t0 = time.perf_counter()
 for i in range(steps):
-    out = stepper.step(st, ac, i, 0, False, False, 0)
+    out = stepper.step(st, ac, fz.status, i, 0, False, 0)
 t1 = time.perf_counter()
 th.cuda.synchronize()
 print(f"EnvStepper.step alone, no terminal obs: {(t1 - t0) / steps * 1e6:.2f} us/call")

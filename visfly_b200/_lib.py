@@ -15,7 +15,7 @@ from .params import VfEnvMirror, VfEnvSpec, VfParams
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvisfly_b200.so")
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 INTEGRATOR_ID = {"euler": 0, "rk4": 1}
 FLAG_CTRL_DELAY = 1
@@ -32,18 +32,20 @@ SIGNATURES = {
     "vf_last_error": (ctypes.c_char_p, []),
     "vf_params_size": (_i, []),
     "vf_device_sm_count": (_i, []),
-    "vf_step_fwd": (_i, [_P(VfParams), _i, _i, _i, _i, _u, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "vf_step_fwd": (_i, [_P(VfParams), _i, _i, _i, _i, _u, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "vf_step_bwd": (_i, [_P(VfParams), _i, _i, _i, _i, _u, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "vf_step_fwd_host": (_i, [_P(VfParams), _i, _i, _i, _i, _u, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "vf_pack_state": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "vf_unpack_state": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "vf_export_pose_habitat": (_i, [_P(VfParams), _i, _vp, _vp, _vp, _vp]),
     "vf_env_spec_size": (_i, []),
-    "vf_env_step_fwd": (_i, [_P(VfParams), _P(VfEnvSpec), _i, _i, _i, _i, _u, _u, ctypes.c_ulonglong,
-                             _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+    "vf_wait_flag": (_i, [_vp, _u, ctypes.c_longlong]),
+    "vf_env_step_fwd": (_i, [_P(VfParams), _P(VfEnvSpec), _i, _i, _i, _i, _u, _u, ctypes.c_ulonglong, _vp,
+                             _vp, _vp, _vp, _vp, _vp, _vp,
+                             _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                              _P(VfEnvMirror), _vp]),
     "vf_env_step_bwd": (_i, [_P(VfParams), _P(VfEnvSpec), _i, _i, _i, _i, _u, _u,
-                             _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+                             _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
 }
 
 _lib: Optional[ctypes.CDLL] = None
@@ -121,14 +123,17 @@ def _stream(device) -> int:
 
 def step_fwd(params: VfParams, substeps: int, integrator: int, action_type: int, flags: int,
              state_in: th.Tensor, action: th.Tensor, state_out: th.Tensor, obs_out: Optional[th.Tensor],
-             ext_out: Optional[th.Tensor], wind: Optional[th.Tensor] = None) -> None:
+             ext_out: Optional[th.Tensor], wind: Optional[th.Tensor] = None, fifo_push: Optional[th.Tensor] = None,
+             fifo_copy: Optional[th.Tensor] = None) -> None:
     lib = load(require_cuda=True)
     n = state_in.shape[1]
     with th.cuda.device(state_in.device):
         _check(lib.vf_step_fwd(ctypes.byref(params), n, substeps, integrator, action_type, flags,
                                _dev_ptr(state_in, "state_in"), _dev_ptr(action, "action"),
                                _dev_ptr(state_out, "state_out"), _dev_ptr(obs_out, "obs_out"),
-                               _dev_ptr(ext_out, "ext_out"), _dev_ptr(wind, "wind"), _stream(state_in.device)))
+                               _dev_ptr(ext_out, "ext_out"), _dev_ptr(wind, "wind"),
+                               _dev_ptr(fifo_push, "fifo_push"), _dev_ptr(fifo_copy, "fifo_copy"),
+                               _stream(state_in.device)))
 
 
 def step_bwd(params: VfParams, substeps: int, integrator: int, action_type: int, flags: int,
@@ -197,42 +202,70 @@ def _any_ptr(t: Optional[th.Tensor], what: str, dtype) -> Optional[int]:
     return t.data_ptr()
 
 
+def pack_status(step_count: th.Tensor, returns: th.Tensor, ebits: th.Tensor, gate: Optional[th.Tensor] = None,
+                gates_passed: Optional[th.Tensor] = None) -> th.Tensor:
+    """Per-agent env status records ``int32[n][4]`` (``VfEnvStatus`` in include/visfly_b200.h) from its fields."""
+    n = step_count.numel()
+    st = th.zeros((n, 4), dtype=th.int32, device=step_count.device)
+    st[:, 0] = step_count.to(th.int32)
+    st[:, 1] = returns.detach().to(th.float32).contiguous().view(th.int32)
+    st[:, 2] = ebits.to(th.int32) & 0xFF
+    if gate is not None:
+        st[:, 2] |= gate.to(th.int32) << 8
+    if gates_passed is not None:
+        st[:, 3] = gates_passed.to(th.int32)
+    return st
+
+
+def unpack_status(status: th.Tensor):
+    """``(step_count int32, returns float32, ebits int32, gate int32, gates_passed int32)`` views / copies."""
+    return (status[:, 0], status[:, 1].view(th.float32), status[:, 2] & 0xFF, (status[:, 2] >> 8) & 0xFF,
+            status[:, 3])
+
+
 def env_step_fwd(params: VfParams, spec: VfEnvSpec, substeps: int, integrator: int, action_type: int, flags: int,
                  env_flags: int, step_index: int, state_in: th.Tensor, action: th.Tensor,
-                 reset_table: Optional[th.Tensor], step_count: th.Tensor, returns: th.Tensor, ebits: th.Tensor,
-                 gate: Optional[th.Tensor], gates_passed: Optional[th.Tensor], state_out: th.Tensor,
+                 reset_table: Optional[th.Tensor], status_in: th.Tensor, state_out: th.Tensor, status_out: th.Tensor,
                  obs_out: th.Tensor, reward_out: th.Tensor, done_out: th.Tensor, record_out: th.Tensor,
-                 term_obs_out: Optional[th.Tensor], saved_out: Optional[th.Tensor] = None,
-                 host_mirror: Optional[VfEnvMirror] = None) -> None:
+                 term_obs_out: Optional[th.Tensor], host_mirror: Optional[VfEnvMirror] = None,
+                 wind: Optional[th.Tensor] = None, fifo_push: Optional[th.Tensor] = None,
+                 fifo_copy: Optional[th.Tensor] = None, step_base: Optional[th.Tensor] = None) -> None:
     """Binding of ``vf_env_step_fwd`` (fused control step + env wrapper tail, one launch)."""
     lib = load(require_cuda=True)
     n = state_in.shape[1]
     with th.cuda.device(state_in.device):
         _check(lib.vf_env_step_fwd(
             ctypes.byref(params), ctypes.byref(spec), n, substeps, integrator, action_type, flags, env_flags,
-            step_index, _dev_ptr(state_in, "state_in"), _dev_ptr(action, "action"),
-            _dev_ptr(reset_table, "reset_table"), _any_ptr(step_count, "step_count", th.int32),
-            _dev_ptr(returns, "returns"), _any_ptr(ebits, "ebits", th.uint8), _any_ptr(gate, "gate", th.int32),
-            _any_ptr(gates_passed, "gates_passed", th.int32), _dev_ptr(state_out, "state_out"),
-            _dev_ptr(obs_out, "obs_out"), _dev_ptr(reward_out, "reward_out"),
+            step_index, _any_ptr(step_base, "step_base", th.int64),
+            _dev_ptr(state_in, "state_in"), _dev_ptr(action, "action"), _dev_ptr(wind, "wind"),
+            _dev_ptr(fifo_push, "fifo_push"), _dev_ptr(reset_table, "reset_table"),
+            _any_ptr(status_in, "status_in", th.int32),
+            _dev_ptr(state_out, "state_out"), _any_ptr(status_out, "status_out", th.int32),
+            _dev_ptr(fifo_copy, "fifo_copy"), _dev_ptr(obs_out, "obs_out"), _dev_ptr(reward_out, "reward_out"),
             _any_ptr(done_out, "done_out", th.bool), _dev_ptr(record_out, "record_out"),
-            _dev_ptr(term_obs_out, "term_obs_out"), _any_ptr(saved_out, "saved_out", th.int32),
+            _dev_ptr(term_obs_out, "term_obs_out"),
             None if host_mirror is None else ctypes.byref(host_mirror), _stream(state_in.device)))
 
 
 def env_step_bwd(params: VfParams, spec: VfEnvSpec, substeps: int, integrator: int, action_type: int, flags: int,
-                 env_flags: int, state_in: th.Tensor, action: th.Tensor, saved: th.Tensor,
+                 env_flags: int, state_in: th.Tensor, action: th.Tensor, status_in: th.Tensor,
                  g_state_out: Optional[th.Tensor], g_obs: Optional[th.Tensor], g_reward: Optional[th.Tensor],
-                 g_state_in: th.Tensor, g_action: th.Tensor) -> None:
+                 g_state_in: th.Tensor, g_action: th.Tensor, wind: Optional[th.Tensor] = None) -> None:
     """Binding of ``vf_env_step_bwd`` (adjoint of the fused env step, one launch)."""
     lib = load(require_cuda=True)
     n = state_in.shape[1]
     with th.cuda.device(state_in.device):
         _check(lib.vf_env_step_bwd(
             ctypes.byref(params), ctypes.byref(spec), n, substeps, integrator, action_type, flags, env_flags,
-            _dev_ptr(state_in, "state_in"), _dev_ptr(action, "action"), _any_ptr(saved, "saved", th.int32),
+            _dev_ptr(state_in, "state_in"), _dev_ptr(action, "action"), _dev_ptr(wind, "wind"),
+            _any_ptr(status_in, "status_in", th.int32),
             _dev_ptr(g_state_out, "grad_state_out"), _dev_ptr(g_obs, "grad_obs"), _dev_ptr(g_reward, "grad_reward"),
             _dev_ptr(g_state_in, "grad_state_in"), _dev_ptr(g_action, "grad_action"), _stream(state_in.device)))
+
+
+def wait_flag(flag_addr: int, value: int, timeout_us: int = 10_000_000) -> None:
+    """Spin (in C, no GIL games needed: microseconds) until the page-locked completion word equals ``value``."""
+    _check(load().vf_wait_flag(flag_addr, value, timeout_us))
 
 
 def export_pose_habitat(params: VfParams, state: th.Tensor, pose_out: th.Tensor, vel_out: Optional[th.Tensor]) -> None:

@@ -225,10 +225,11 @@ template <class T> struct EnvEval {
     T reward;
 };
 
+// `wd`: this agent's wind of the control step (the constant P.wind, or the per-agent vector of the wind functions)
 template <class T>
-VF_HD void env_eval(const Params<T>& P, const VfEnvSpec& E, const State<T>& s, int sc, int gate_in, bool ep_done_in,
-                    EnvEval<T>& ev) {
-    for (int j = 0; j < 3; ++j) ev.vel[j] = s.v[j] + P.wind[j];
+VF_HD void env_eval(const Params<T>& P, const VfEnvSpec& E, const State<T>& s, const T wd[3], int sc, int gate_in,
+                    bool ep_done_in, EnvEval<T>& ev) {
+    for (int j = 0; j < 3; ++j) ev.vel[j] = s.v[j] + wd[j];
     ev.hit = box_hit<T>(s.p, E.bbox_lo, E.bbox_hi);
     ev.is_col = ev.hit.dis < T(E.uav_radius);
     ev.success = false;
@@ -263,14 +264,15 @@ VF_HD void env_eval(const Params<T>& P, const VfEnvSpec& E, const State<T>& s, i
 template <class T>
 VF_HD void env_step_bwd_agent(const Params<T>& P, const VfEnvSpec& E, int substeps, int integrator, int action_type,
                               bool ctrl_delay, bool no_reset, const T a[4], const State<T>& s0, int age_in,
-                              int gate_in, const T* gobs, T gr, State<T>& g, T ga[4], Tape<T>* tape) {
+                              int gate_in, const T* gobs, T gr, State<T>& g, T ga[4], Tape<T>* tape,
+                              const T* wind = nullptr) {
     Command<T> c;
     State<T> s_raw;
-    step_fwd_taped(P, substeps, integrator, action_type, ctrl_delay, a, s0, c, s_raw, tape);
+    step_fwd_taped(P, substeps, integrator, action_type, ctrl_delay, a, s0, c, s_raw, tape, wind);
     State<T> s = s_raw;
     clamp_state(P, s);
     EnvEval<T> ev;
-    env_eval(P, E, s, age_in + 1, gate_in, false, ev);
+    env_eval(P, E, s, wind ? wind : P.wind, age_in + 1, gate_in, false, ev);
     if (ev.done && !no_reset) {
         for (int j = 0; j < 3; ++j) g.p[j] = g.v[j] = g.w[j] = g.al[j] = T(0);
         for (int j = 0; j < 4; ++j) g.q[j] = g.mot[j] = T(0);
@@ -341,12 +343,22 @@ VF_HD void sample_reset(const VfEnvSpec& E, unsigned agent, unsigned long long s
     } else {
         for (int j = 0; j < 12; ++j) f[j] = 2.0f * u01(r[j]) - 1.0f;
     }
-    float e[3];
+    float e[3], off[3];
     for (int j = 0; j < 3; ++j) {
-        p[j] = f[j] * E.gen_half[box][0][j] + E.gen_mean[box][0][j];
+        off[j] = f[j] * E.gen_half[box][0][j];
+        p[j] = off[j] + E.gen_mean[box][0][j];
         e[j] = f[3 + j] * E.gen_half[box][1][j] + E.gen_mean[box][1][j];
         v[j] = f[6 + j] * E.gen_half[box][2][j] + E.gen_mean[box][2][j];
         w[j] = f[9 + j] * E.gen_half[box][3][j] + E.gen_mean[box][3][j];
+    }
+    if (E.gen_heading[box]) {
+        // randomization.py:162-165 with calculate_yaw_pitch (:27-28): the yaw points from the drawn position back to
+        // the centre of the position box, roll = pitch = 0, plus the orientation noise (the orientation mean is unused)
+        const float dx = -off[0], dy = -off[1];
+        const float yaw = acosf(dx / sqrtf(dx * dx + dy * dy)) * (dy >= 0.f ? 1.f : -1.f);
+        e[0] = f[3] * E.gen_half[box][1][0];
+        e[1] = f[4] * E.gen_half[box][1][1];
+        e[2] = yaw + f[5] * E.gen_half[box][1][2];
     }
     euler_to_quat(e, q);
 }

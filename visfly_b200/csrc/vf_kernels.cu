@@ -11,6 +11,7 @@
 // memory so its global stores/loads are 128-bit and coalesced as well.
 #include <cuda_runtime.h>
 
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <string>
@@ -136,7 +137,8 @@ __global__ void __launch_bounds__(BLOCK)
 vf_step_fwd_kernel(const __grid_constant__ VfParams params, int n, int substeps,
                    const float* __restrict__ state_in, const float* __restrict__ action,
                    float* __restrict__ state_out, float* __restrict__ obs_out, float* __restrict__ ext_out,
-                   const float* __restrict__ wind) {
+                   const float* __restrict__ wind, const float* __restrict__ fifo_push,
+                   float* __restrict__ fifo_copy) {
     __shared__ __align__(16) float s_obs[(BLOCK / 32) * kWarpObs];
     const vf::Params<float>& P = reinterpret_cast<const vf::Params<float>&>(params);
     const int i = blockIdx.x * BLOCK + threadIdx.x;
@@ -158,6 +160,8 @@ vf_step_fwd_kernel(const __grid_constant__ VfParams params, int n, int substeps,
             const float4 w4 = ldg4(wind, size_t(i));
             wd[0] = w4.x; wd[1] = w4.y; wd[2] = w4.z;
         }
+        // comm-delay FIFO: the engine-owned copy of the action that arrived this step (dynamics.py:324 `clone()`)
+        if (fifo_copy) stg4(fifo_copy, size_t(i), ldg4(fifo_push, size_t(i)));
         vf::step_fwd<float>(P, substeps, INTEG, ACT, LAG, a, s, k, wd);
         store_state(state_out, n, i, s);
         if (ext_out) {
@@ -238,13 +242,14 @@ template <int INTEG, int ACT, bool LAG, int BLOCK>
 __global__ void __launch_bounds__(BLOCK)
 vf_env_step_fwd_kernel(const __grid_constant__ VfParams params, const __grid_constant__ VfEnvSpec E, int n,
                        int substeps, unsigned env_flags, unsigned long long step_index,
+                       const unsigned long long* __restrict__ step_base,
                        const float* __restrict__ state_in, const float* __restrict__ action,
-                       const float* __restrict__ reset_table, int* __restrict__ step_count,
-                       float* __restrict__ returns, unsigned char* __restrict__ ebits, int* __restrict__ gate,
-                       int* __restrict__ gates_passed, float* __restrict__ state_out, float* __restrict__ obs_out,
-                       float* __restrict__ reward_out, unsigned char* __restrict__ done_out,
-                       float* __restrict__ record_out, float* __restrict__ term_obs_out,
-                       int* __restrict__ saved_out, const VfEnvMirror mirror) {
+                       const float* __restrict__ wind, const float* __restrict__ fifo_push,
+                       const float* __restrict__ reset_table, const int* __restrict__ status_in,
+                       float* __restrict__ state_out, int* __restrict__ status_out, float* __restrict__ fifo_copy,
+                       float* __restrict__ obs_out, float* __restrict__ reward_out,
+                       unsigned char* __restrict__ done_out, float* __restrict__ record_out,
+                       float* __restrict__ term_obs_out, const VfEnvMirror mirror) {
     __shared__ __align__(16) float s_obs[(BLOCK / 32) * kWarpObs];
     const vf::Params<float>& P = reinterpret_cast<const vf::Params<float>&>(params);
     const int i = blockIdx.x * BLOCK + threadIdx.x;
@@ -256,27 +261,32 @@ vf_env_step_fwd_kernel(const __grid_constant__ VfParams params, const __grid_con
     pdl_wait();
 
     vf::State<float> s;
+    float wd[3] = {P.wind[0], P.wind[1], P.wind[2]};
     int g = 0;
     if (live) {
-        // every input of the step is requested up front: the env status words are only needed after the sub-step
-        // loop, but fetching them there would put a second (cold) HBM round trip on each warp's critical path
+        // every input of the step is requested up front: the env status record is only needed after the sub-step
+        // loop, but fetching it there would put a second (cold) HBM round trip on each warp's critical path
         load_state(state_in, n, i, s);
-        const int age = step_count[i];
+        const int4 st4 = __ldg(reinterpret_cast<const int4*>(status_in) + i);
         float4 a4 = ldg4(action, size_t(i));
-        const unsigned eb = ebits[i];
-        const float ret_in = returns[i];
-        int passed = 0;
-        int g_in = 0;
-        if (E.task == VF_TASK_RACING) { g_in = gate[i]; passed = gates_passed[i]; }
+        if (wind) {
+            const float4 w4 = ldg4(wind, size_t(i));
+            wd[0] = w4.x; wd[1] = w4.y; wd[2] = w4.z;
+        }
+        if (fifo_copy) stg4(fifo_copy, size_t(i), ldg4(fifo_push, size_t(i)));
+        const int age = st4.x;
+        const float ret_in = __int_as_float(st4.y);
+        const unsigned eb = unsigned(st4.z) & 0xFFu;
+        const int g_in = (st4.z >> 8) & 0xFF;
+        int passed = st4.w;
         if (age < E.fifo_depth) a4 = make_float4(0.f, 0.f, 0.f, 0.f);   // FIFO rows of a reset agent read as zero
         const float a[4] = {a4.x, a4.y, a4.z, a4.w};
         vf::Wrench<float> k;
-        vf::step_fwd<float>(P, substeps, INTEG, ACT, LAG, a, s, k);
+        vf::step_fwd<float>(P, substeps, INTEG, ACT, LAG, a, s, k, wd);
 
         int sc = age + 1;
-        if (saved_out) reinterpret_cast<int2*>(saved_out)[i] = make_int2(age, g_in);
         vf::EnvEval<float> ev;
-        vf::env_eval<float>(P, E, s, sc, g_in, (eb & VF_EBIT_EPISODE_DONE) != 0, ev);
+        vf::env_eval<float>(P, E, s, wd, sc, g_in, (eb & VF_EBIT_EPISODE_DONE) != 0, ev);
         float vel[3] = {ev.vel[0], ev.vel[1], ev.vel[2]};
         g = ev.gate;
         passed += ev.pass ? 1 : 0;
@@ -318,18 +328,17 @@ vf_env_step_fwd_kernel(const __grid_constant__ VfParams params, const __grid_con
                 g = vf::racing_first_gate<float>(s.p);
                 passed = 0;
             }
-            vf::sample_reset(E, unsigned(i), step_index, reset_table ? reset_table + size_t(i) * 13 : nullptr,
+            const unsigned long long step = step_index + (step_base ? *step_base : 0ull);
+            vf::sample_reset(E, unsigned(i), step, reset_table ? reset_table + size_t(i) * 13 : nullptr,
                              s.p, s.q, s.v, s.w);
             for (int j = 0; j < 4; ++j) s.mot[j] = E.init_motor_omega;
             s.al[0] = s.al[1] = s.al[2] = 0.f;
             sc = 0; ret = 0.f; ep_done = false; once = false;
-            vel[0] = s.v[0] + P.wind[0]; vel[1] = s.v[1] + P.wind[1]; vel[2] = s.v[2] + P.wind[2];
+            vel[0] = s.v[0] + wd[0]; vel[1] = s.v[1] + wd[1]; vel[2] = s.v[2] + wd[2];
         }
         store_state(state_out, n, i, s);
-        step_count[i] = sc;
-        returns[i] = ret;
-        ebits[i] = (unsigned char)((ep_done ? VF_EBIT_EPISODE_DONE : 0u) | (once ? VF_EBIT_ONCE_COLLIDED : 0u));
-        if (E.task == VF_TASK_RACING) { gate[i] = g; gates_passed[i] = passed; }
+        const int ebo = int((ep_done ? VF_EBIT_EPISODE_DONE : 0u) | (once ? VF_EBIT_ONCE_COLLIDED : 0u));
+        reinterpret_cast<int4*>(status_out)[i] = make_int4(sc, __float_as_int(ret), ebo | (g << 8), passed);
 
         if (E.obs_kind == VF_OBS_RACING16) {
             float o[16];
@@ -349,10 +358,24 @@ vf_env_step_fwd_kernel(const __grid_constant__ VfParams params, const __grid_con
         if (live) {
             o[0] = s.p[0]; o[1] = s.p[1]; o[2] = s.p[2];
             o[3] = s.q[0]; o[4] = s.q[1]; o[5] = s.q[2]; o[6] = s.q[3];
-            o[7] = s.v[0] + P.wind[0]; o[8] = s.v[1] + P.wind[1]; o[9] = s.v[2] + P.wind[2];
+            o[7] = s.v[0] + wd[0]; o[8] = s.v[1] + wd[1]; o[9] = s.v[2] + wd[2];
             o[10] = s.w[0]; o[11] = s.w[1]; o[12] = s.w[2];
         }
         warp_store_obs(obs_out, s_obs + warp * kWarpObs, n, warp_first, lane, o, mirror.obs);
+    }
+    if (mirror.flag) {
+        // completion word for a host that spins instead of synchronising the stream: every thread makes its host
+        // stores visible system-wide, the block counts itself in, and the last block of the grid raises the flag
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned arrived = atomicAdd(mirror.counter, 1u);
+            if (arrived == gridDim.x - 1) {
+                *mirror.counter = 0u;               // ready for the next launch (stream-ordered behind this one)
+                __threadfence_system();
+                *reinterpret_cast<volatile unsigned*>(mirror.flag) = mirror.flag_value;
+            }
+        }
     }
 }
 
@@ -363,7 +386,8 @@ template <int INTEG, int ACT, bool LAG, int SMAX, int BLOCK>
 __global__ void __launch_bounds__(BLOCK)
 vf_env_step_bwd_kernel(const __grid_constant__ VfParams params, const __grid_constant__ VfEnvSpec E, int n,
                        int substeps, unsigned env_flags, const float* __restrict__ state_in,
-                       const float* __restrict__ action, const int* __restrict__ saved,
+                       const float* __restrict__ action, const float* __restrict__ wind,
+                       const int* __restrict__ status_in,
                        const float* __restrict__ g_state_out, const float* __restrict__ g_obs,
                        const float* __restrict__ g_reward, float* __restrict__ g_state_in,
                        float* __restrict__ g_action) {
@@ -403,16 +427,22 @@ vf_env_step_bwd_kernel(const __grid_constant__ VfParams params, const __grid_con
     }
     vf::State<float> s0;
     load_state(state_in, n, i, s0);
-    const int2 sv = __ldg(reinterpret_cast<const int2*>(saved) + i);
+    const int4 st4 = __ldg(reinterpret_cast<const int4*>(status_in) + i);
+    const int age_in = st4.x, gate_in = (st4.z >> 8) & 0xFF;
     float4 a4 = ldg4(action, size_t(i));
-    const bool masked = sv.x < E.fifo_depth;          // the forward replaced the delayed action by zero
+    const bool masked = age_in < E.fifo_depth;        // the forward replaced the delayed action by zero
     if (masked) a4 = make_float4(0.f, 0.f, 0.f, 0.f);
     const float a[4] = {a4.x, a4.y, a4.z, a4.w};
     const float gr = g_reward ? __ldg(g_reward + i) : 0.f;
+    float wd[3] = {P.wind[0], P.wind[1], P.wind[2]};
+    if (wind) {
+        const float4 w4 = ldg4(wind, size_t(i));
+        wd[0] = w4.x; wd[1] = w4.y; wd[2] = w4.z;
+    }
     vf::Tape<float> tape[SMAX];
     float ga[4];
     vf::env_step_bwd_agent<float>(P, E, substeps, INTEG, ACT, LAG, (env_flags & VF_ENV_FLAG_NO_RESET) != 0, a, s0,
-                                  sv.x, sv.y, have_obs ? o : nullptr, gr, g, ga, tape);
+                                  age_in, gate_in, have_obs ? o : nullptr, gr, g, ga, tape, wd);
     store_state(g_state_in, n, i, g);
     stg4(g_action, size_t(i), masked ? make_float4(0.f, 0.f, 0.f, 0.f) : make_float4(ga[0], ga[1], ga[2], ga[3]));
 }
@@ -586,15 +616,15 @@ int check_spec(const VfEnvSpec* spec) {
 
 template <int INTEG, int ACT, bool LAG>
 void launch_fwd(const VfParams& p, int n, int substeps, const float* si, const float* a, float* so, float* obs,
-                float* ext, const float* wind, cudaStream_t st) {
+                float* ext, const float* wind, const float* push, float* copy, cudaStream_t st) {
     switch (block_override()) {
-        case 32: launch_pdl(vf_step_fwd_kernel<INTEG, ACT, LAG, 32>, (n + 31) / 32, 32, st, p, n, substeps, si, a, so, obs, ext, wind); return;
-        case 128: launch_pdl(vf_step_fwd_kernel<INTEG, ACT, LAG, 128>, (n + 127) / 128, 128, st, p, n, substeps, si, a, so, obs, ext, wind); return;
-        case 256: launch_pdl(vf_step_fwd_kernel<INTEG, ACT, LAG, 256>, (n + 255) / 256, 256, st, p, n, substeps, si, a, so, obs, ext, wind); return;
+        case 32: launch_pdl(vf_step_fwd_kernel<INTEG, ACT, LAG, 32>, (n + 31) / 32, 32, st, p, n, substeps, si, a, so, obs, ext, wind, push, copy); return;
+        case 128: launch_pdl(vf_step_fwd_kernel<INTEG, ACT, LAG, 128>, (n + 127) / 128, 128, st, p, n, substeps, si, a, so, obs, ext, wind, push, copy); return;
+        case 256: launch_pdl(vf_step_fwd_kernel<INTEG, ACT, LAG, 256>, (n + 255) / 256, 256, st, p, n, substeps, si, a, so, obs, ext, wind, push, copy); return;
         default: break;
     }
     const int grid = (n + kBlock - 1) / kBlock;
-    launch_pdl(vf_step_fwd_kernel<INTEG, ACT, LAG, kBlock>, grid, kBlock, st, p, n, substeps, si, a, so, obs, ext, wind);
+    launch_pdl(vf_step_fwd_kernel<INTEG, ACT, LAG, kBlock>, grid, kBlock, st, p, n, substeps, si, a, so, obs, ext, wind, push, copy);
 }
 
 template <int INTEG, int ACT, bool LAG>
@@ -611,26 +641,27 @@ void launch_bwd(const VfParams& p, int n, int substeps, const float* si, const f
 
 template <int INTEG, int ACT, bool LAG>
 void launch_env_fwd(const VfParams& p, const VfEnvSpec& e, int n, int substeps, unsigned env_flags,
-                    unsigned long long step_index, const float* si, const float* a, const float* table, int* sc,
-                    float* ret, unsigned char* eb, int* gate, int* passed, float* so, float* obs, float* rew,
-                    unsigned char* done, float* rec, float* tobs, int* saved, const VfEnvMirror& mirror,
-                    cudaStream_t st) {
+                    unsigned long long step_index, const unsigned long long* step_base, const float* si,
+                    const float* a, const float* wind, const float* push, const float* table, const int* status_in,
+                    float* so, int* status_out, float* copy, float* obs, float* rew, unsigned char* done, float* rec,
+                    float* tobs, const VfEnvMirror& mirror, cudaStream_t st) {
     const int grid = (n + kBlock - 1) / kBlock;
-    launch_pdl(vf_env_step_fwd_kernel<INTEG, ACT, LAG, kBlock>, grid, kBlock, st, p, e, n, substeps, env_flags, step_index, si, a, table, sc, ret, eb, gate, passed, so, obs, rew, done, rec, tobs,
-        saved, mirror);
+    launch_pdl(vf_env_step_fwd_kernel<INTEG, ACT, LAG, kBlock>, grid, kBlock, st, p, e, n, substeps, env_flags,
+               step_index, step_base, si, a, wind, push, table, status_in, so, status_out, copy, obs, rew, done, rec,
+               tobs, mirror);
 }
 
 template <int INTEG, int ACT, bool LAG>
 void launch_env_bwd(const VfParams& p, const VfEnvSpec& e, int n, int substeps, unsigned env_flags, const float* si,
-                    const float* a, const int* saved, const float* gso, const float* gobs, const float* gr, float* gsi,
-                    float* ga, cudaStream_t st) {
+                    const float* a, const float* wind, const int* status_in, const float* gso, const float* gobs,
+                    const float* gr, float* gsi, float* ga, cudaStream_t st) {
     const int grid = (n + kBlock - 1) / kBlock;
     if (substeps <= 8)
-        launch_pdl(vf_env_step_bwd_kernel<INTEG, ACT, LAG, 8, kBlock>, grid, kBlock, st, p, e, n, substeps, env_flags, si, a, saved, gso, gobs, gr, gsi, ga);
+        launch_pdl(vf_env_step_bwd_kernel<INTEG, ACT, LAG, 8, kBlock>, grid, kBlock, st, p, e, n, substeps, env_flags, si, a, wind, status_in, gso, gobs, gr, gsi, ga);
     else if (substeps <= 16)
-        launch_pdl(vf_env_step_bwd_kernel<INTEG, ACT, LAG, 16, kBlock>, grid, kBlock, st, p, e, n, substeps, env_flags, si, a, saved, gso, gobs, gr, gsi, ga);
+        launch_pdl(vf_env_step_bwd_kernel<INTEG, ACT, LAG, 16, kBlock>, grid, kBlock, st, p, e, n, substeps, env_flags, si, a, wind, status_in, gso, gobs, gr, gsi, ga);
     else
-        launch_pdl(vf_env_step_bwd_kernel<INTEG, ACT, LAG, VF_MAX_SUBSTEPS_BWD, kBlock>, grid, kBlock, st, p, e, n, substeps, env_flags, si, a, saved, gso, gobs, gr, gsi, ga);
+        launch_pdl(vf_env_step_bwd_kernel<INTEG, ACT, LAG, VF_MAX_SUBSTEPS_BWD, kBlock>, grid, kBlock, st, p, e, n, substeps, env_flags, si, a, wind, status_in, gso, gobs, gr, gsi, ga);
 }
 
 // forward-only dispatch: all four action types
@@ -704,16 +735,19 @@ int vf_device_sm_count(void) {
 
 int vf_step_fwd(const VfParams* params, int n, int substeps, int integrator, int action_type, unsigned flags,
                 const float* state_in, const float* action, float* state_out, float* obs_out, float* ext_out,
-                const float* wind, void* stream) {
+                const float* wind, const float* fifo_push, float* fifo_copy, void* stream) {
     if (check_common(params, n, substeps, integrator, action_type)) return 1;
     if (n == 0) return 0;
     if (!state_in || !action || !state_out) return fail("state_in, action and state_out must not be NULL");
     if (state_in == state_out) return fail("state_out must not alias state_in");
+    if ((fifo_push == nullptr) != (fifo_copy == nullptr)) return fail("fifo_push and fifo_copy must be given together");
+    if (fifo_copy && fifo_copy == action) return fail("fifo_copy must not alias the consumed action");
     if (!aligned16(state_in) || !aligned16(action) || !aligned16(state_out) || !aligned16(obs_out) ||
-        !aligned16(ext_out) || !aligned16(wind))
+        !aligned16(ext_out) || !aligned16(wind) || !aligned16(fifo_push) || !aligned16(fifo_copy))
         return fail("all buffers must be 16-byte aligned");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    VF_DISPATCH_FWD(launch_fwd, *params, n, substeps, state_in, action, state_out, obs_out, ext_out, wind, st);
+    VF_DISPATCH_FWD(launch_fwd, *params, n, substeps, state_in, action, state_out, obs_out, ext_out, wind, fifo_push,
+                    fifo_copy, st);
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return fail("vf_step_fwd launch failed", err);
     return 0;
@@ -748,7 +782,7 @@ int vf_step_fwd_host(const VfParams* params, int n, int substeps, int integrator
                                       cudaMemcpyHostToDevice, st);
     if (err != cudaSuccess) return fail("vf_step_fwd_host: H2D copy of the actions failed", err);
     if (vf_step_fwd(params, n, substeps, integrator, action_type, flags, state_in, action_dev, state_out, obs_dev,
-                    nullptr, nullptr, stream))
+                    nullptr, nullptr, nullptr, nullptr, stream))
         return 1;
     if (obs_host) {
         err = cudaMemcpyAsync(obs_host, obs_dev, sizeof(float) * VF_OBS_FLOATS * size_t(n),
@@ -762,27 +796,47 @@ int vf_step_fwd_host(const VfParams* params, int n, int substeps, int integrator
 
 int vf_env_spec_size(void) { return int(sizeof(VfEnvSpec)); }
 
+int vf_wait_flag(const volatile unsigned* flag, unsigned value, long long timeout_us) {
+    if (!flag) return fail("vf_wait_flag: flag is NULL");
+    if (*flag == value) return 0;
+    const auto t0 = std::chrono::steady_clock::now();
+    for (unsigned spins = 1;; ++spins) {
+        if (*flag == value) return 0;
+#if defined(__x86_64__) || defined(__i386__)
+        __builtin_ia32_pause();
+#endif
+        if (timeout_us > 0 && (spins & 1023u) == 0) {
+            const auto dt = std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0);
+            if (dt.count() > timeout_us) return fail("vf_wait_flag: timed out waiting for the kernel's completion word");
+        }
+    }
+}
+
 int vf_env_step_fwd(const VfParams* params, const VfEnvSpec* spec, int n, int substeps, int integrator,
                     int action_type, unsigned flags, unsigned env_flags, unsigned long long step_index,
-                    const float* state_in, const float* action, const float* reset_table, int* step_count,
-                    float* returns, unsigned char* ebits, int* gate, int* gates_passed, float* state_out,
-                    float* obs_out, float* reward_out, unsigned char* done_out, float* record_out,
-                    float* term_obs_out, int* saved_out, const VfEnvMirror* host_mirror, void* stream) {
+                    const unsigned long long* step_base,
+                    const float* state_in, const float* action, const float* wind, const float* fifo_push,
+                    const float* reset_table, const int* status_in,
+                    float* state_out, int* status_out, float* fifo_copy, float* obs_out, float* reward_out,
+                    unsigned char* done_out, float* record_out, float* term_obs_out,
+                    const VfEnvMirror* host_mirror, void* stream) {
     if (check_common(params, n, substeps, integrator, action_type)) return 1;
     if (check_spec(spec)) return 1;
     if (n == 0) return 0;
-    if (!state_in || !action || !state_out || !step_count || !returns || !ebits || !obs_out || !reward_out ||
-        !done_out || !record_out)
+    if (!state_in || !action || !state_out || !status_in || !status_out || !obs_out || !reward_out || !done_out ||
+        !record_out)
         return fail("vf_env_step_fwd: a required buffer is NULL");
-    if (spec->task == VF_TASK_RACING && (!gate || !gates_passed)) return fail("racing needs gate and gates_passed buffers");
     if (spec->gen_kind == VF_GEN_TABLE && !reset_table) return fail("VF_GEN_TABLE needs reset_table");
     if (state_in == state_out) return fail("state_out must not alias state_in");
+    if ((fifo_push == nullptr) != (fifo_copy == nullptr)) return fail("fifo_push and fifo_copy must be given together");
+    if (fifo_copy && fifo_copy == action) return fail("fifo_copy must not alias the consumed action");
     if (!aligned16(state_in) || !aligned16(action) || !aligned16(state_out) || !aligned16(obs_out) ||
-        !aligned16(record_out))
-        return fail("all float4 buffers must be 16-byte aligned");
+        !aligned16(record_out) || !aligned16(status_in) || !aligned16(status_out) || !aligned16(wind) ||
+        !aligned16(fifo_push) || !aligned16(fifo_copy))
+        return fail("all float4 / int4 buffers must be 16-byte aligned");
     // page-locked host destinations -> their device aliases (identity under unified addressing; an error here means
     // the caller passed pageable memory)
-    VfEnvMirror mirror = {nullptr, nullptr, nullptr};
+    VfEnvMirror mirror = {nullptr, nullptr, nullptr, nullptr, nullptr, 0u};
     if (host_mirror) {
         void* d = nullptr;
         if (host_mirror->obs) {
@@ -806,11 +860,21 @@ int vf_env_step_fwd(const VfParams* params, const VfEnvSpec* spec, int n, int su
             }
             mirror.done = static_cast<int*>(d);
         }
+        if (host_mirror->flag) {
+            if (!host_mirror->counter) return fail("host_mirror.flag needs host_mirror.counter (a zeroed device word)");
+            if (cudaHostGetDevicePointer(&d, host_mirror->flag, 0) != cudaSuccess) {
+                (void)cudaGetLastError();
+                return fail("host_mirror.flag must be page-locked host memory");
+            }
+            mirror.flag = static_cast<unsigned*>(d);
+            mirror.counter = host_mirror->counter;
+            mirror.flag_value = host_mirror->flag_value;
+        }
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    VF_DISPATCH_FWD(launch_env_fwd, *params, *spec, n, substeps, env_flags, step_index, state_in, action, reset_table,
-                step_count, returns, ebits, gate, gates_passed, state_out, obs_out, reward_out, done_out, record_out,
-                term_obs_out, saved_out, mirror, st);
+    VF_DISPATCH_FWD(launch_env_fwd, *params, *spec, n, substeps, env_flags, step_index, step_base, state_in, action,
+                    wind, fifo_push, reset_table, status_in, state_out, status_out, fifo_copy, obs_out, reward_out,
+                    done_out, record_out, term_obs_out, mirror, st);
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return fail("vf_env_step_fwd launch failed", err);
     return 0;
@@ -818,20 +882,20 @@ int vf_env_step_fwd(const VfParams* params, const VfEnvSpec* spec, int n, int su
 
 int vf_env_step_bwd(const VfParams* params, const VfEnvSpec* spec, int n, int substeps, int integrator,
                     int action_type, unsigned flags, unsigned env_flags, const float* state_in, const float* action,
-                    const int* saved, const float* grad_state_out, const float* grad_obs, const float* grad_reward,
-                    float* grad_state_in, float* grad_action, void* stream) {
+                    const float* wind, const int* status_in, const float* grad_state_out, const float* grad_obs,
+                    const float* grad_reward, float* grad_state_in, float* grad_action, void* stream) {
     if (check_common(params, n, substeps, integrator, action_type, true)) return 1;
     if (check_spec(spec)) return 1;
     if (substeps > VF_MAX_SUBSTEPS_BWD) return fail("substeps exceeds VF_MAX_SUBSTEPS_BWD for the reverse sweep");
     if (n == 0) return 0;
-    if (!state_in || !action || !saved || !grad_state_in || !grad_action)
+    if (!state_in || !action || !status_in || !grad_state_in || !grad_action)
         return fail("vf_env_step_bwd: a required buffer is NULL");
     if (!aligned16(state_in) || !aligned16(action) || !aligned16(grad_state_out) || !aligned16(grad_obs) ||
-        !aligned16(grad_state_in) || !aligned16(grad_action) || (reinterpret_cast<size_t>(saved) & 7u))
-        return fail("all buffers must be 16-byte aligned (saved: 8-byte)");
+        !aligned16(grad_state_in) || !aligned16(grad_action) || !aligned16(status_in) || !aligned16(wind))
+        return fail("all buffers must be 16-byte aligned");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    VF_DISPATCH(launch_env_bwd, *params, *spec, n, substeps, env_flags, state_in, action, saved, grad_state_out,
-                grad_obs, grad_reward, grad_state_in, grad_action, st);
+    VF_DISPATCH(launch_env_bwd, *params, *spec, n, substeps, env_flags, state_in, action, wind, status_in,
+                grad_state_out, grad_obs, grad_reward, grad_state_in, grad_action, st);
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return fail("vf_env_step_bwd launch failed", err);
     return 0;

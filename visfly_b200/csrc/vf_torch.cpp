@@ -35,105 +35,123 @@ inline at::Tensor carve(const at::Tensor& slab, int64_t byte_offset, at::ScalarT
     return t;
 }
 
-// (state', obs) = one control step                                           -> vf_step_fwd
-std::tuple<at::Tensor, at::Tensor> step_fwd(int64_t params, int64_t substeps, int64_t integrator, int64_t action_type,
-                                            int64_t flags, const at::Tensor& state_in, const at::Tensor& action,
-                                            const OptTensor& wind) {
+// (state', obs, fifo copy | None) = one control step                          -> vf_step_fwd
+// `push`: the action that arrived this step; the kernel leaves an engine-owned copy of it in the step's slab (the
+// comm-delay FIFO entry, reference dynamics.py:324 `action.T.clone()`), returned as the third element.
+std::tuple<at::Tensor, at::Tensor, OptTensor> step_fwd(int64_t params, int64_t substeps, int64_t integrator,
+                                                       int64_t action_type, int64_t flags, const at::Tensor& state_in,
+                                                       const at::Tensor& action, const OptTensor& wind,
+                                                       const OptTensor& push) {
     check_f32_cuda(state_in, "state_in");
     check_f32_cuda(action, "action");
+    const int64_t n = state_in.size(1);
     if (wind.has_value()) {
         check_f32_cuda(*wind, "wind");
-        TORCH_CHECK(wind->numel() == 4 * state_in.size(1), "wind must be (n, 4)");
+        TORCH_CHECK(wind->numel() == 4 * n, "wind must be (n, 4)");
     }
-    const int64_t n = state_in.size(1);
+    if (push.has_value()) {
+        check_f32_cuda(*push, "fifo_push");
+        TORCH_CHECK(push->numel() == 4 * n, "fifo_push must be (n, 4)");
+    }
     TORCH_CHECK(state_in.dim() == 3 && state_in.size(0) == VF_STATE_PLANES && state_in.size(2) == 4,
                 "state_in must be (5, n, 4)");
     TORCH_CHECK(action.numel() == 4 * n, "action must be (n, 4)");
     c10::cuda::CUDAGuard guard(state_in.device());
-    const int64_t o_obs = (80 * n + 255) / 256 * 256;
-    at::Tensor slab = at::empty({o_obs + 4 * VF_OBS_FLOATS * n}, state_in.options().dtype(at::kByte));
+    auto pad = [](int64_t bytes) { return (bytes + 255) / 256 * 256; };
+    const int64_t o_obs = pad(80 * n);
+    const int64_t o_copy = o_obs + pad(4 * VF_OBS_FLOATS * n);
+    at::Tensor slab = at::empty({push.has_value() ? o_copy + 16 * n : o_copy}, state_in.options().dtype(at::kByte));
     at::Tensor state_out = carve(slab, 0, at::kFloat, {VF_STATE_PLANES, n, 4});
     at::Tensor obs = carve(slab, o_obs, at::kFloat, {n, VF_OBS_FLOATS});
+    OptTensor copy;
+    if (push.has_value()) copy = carve(slab, o_copy, at::kFloat, {n, 4});
     const int rc = vf_step_fwd(reinterpret_cast<const VfParams*>(params), int(n), int(substeps), int(integrator),
                                int(action_type), unsigned(flags), state_in.data_ptr<float>(), action.data_ptr<float>(),
                                state_out.data_ptr<float>(), obs.data_ptr<float>(), nullptr,
-                               static_cast<const float*>(ptr(wind)), c10::cuda::getCurrentCUDAStream(state_in.device().index()).stream());
+                               static_cast<const float*>(ptr(wind)), static_cast<const float*>(ptr(push)),
+                               static_cast<float*>(ptr(copy)),
+                               c10::cuda::getCurrentCUDAStream(state_in.device().index()).stream());
     TORCH_CHECK(rc == 0, "visfly_b200: ", vf_last_error());
-    return {state_out, obs};
+    return {state_out, obs, copy};
 }
 
 // One fused env step                                                        -> vf_env_step_fwd
-// Everything that stays the same from step to step (parameter blocks, kernel variant, the in-place env status
-// buffers) is bound once; the per-step call carries four arguments.  At 65 536 agents the kernel runs ~11 us, so
-// every microsecond of host work per step shows up in the step rate.
+// Everything that stays the same from step to step (parameter blocks, kernel variant, reset table, the device word
+// of the Philox step base) is bound once; the per-step call carries the tensors that change.  At 65 536 agents the
+// kernel runs ~11 us, so every microsecond of host work per step shows up in the step rate.
 class EnvStepper {
   public:
     EnvStepper(int64_t params, int64_t spec, int64_t substeps, int64_t integrator, int64_t action_type, int64_t flags,
-               int64_t n, at::Tensor step_count, at::Tensor returns, at::Tensor ebits, OptTensor gate,
-               OptTensor gates_passed, OptTensor reset_table, int64_t obs_width)
+               int64_t n, OptTensor reset_table, int64_t obs_width, OptTensor step_base)
         : params_(reinterpret_cast<const VfParams*>(params)), spec_(reinterpret_cast<const VfEnvSpec*>(spec)),
           substeps_(int(substeps)), integrator_(int(integrator)), action_type_(int(action_type)),
-          flags_(unsigned(flags)), n_(n), obs_width_(obs_width), step_count_(std::move(step_count)),
-          returns_(std::move(returns)), ebits_(std::move(ebits)), gate_(std::move(gate)),
-          gates_passed_(std::move(gates_passed)), reset_table_(std::move(reset_table)) {
+          flags_(unsigned(flags)), n_(n), obs_width_(obs_width), reset_table_(std::move(reset_table)),
+          step_base_(std::move(step_base)) {
         TORCH_CHECK(params_ && spec_ && n_ >= 0 && (obs_width_ == 13 || obs_width_ == 16), "EnvStepper: bad arguments");
-        check_f32_cuda(returns_, "returns");
-        TORCH_CHECK(returns_.numel() == n_, "returns must have n elements");
-        TORCH_CHECK(step_count_.is_cuda() && step_count_.scalar_type() == at::kInt && step_count_.is_contiguous() &&
-                        step_count_.numel() == n_, "step_count must be a contiguous int32 CUDA tensor of n elements");
-        TORCH_CHECK(ebits_.is_cuda() && ebits_.scalar_type() == at::kByte && ebits_.is_contiguous() &&
-                        ebits_.numel() == n_, "ebits must be a contiguous uint8 CUDA tensor of n elements");
-        for (const OptTensor* t : {&gate_, &gates_passed_})
-            TORCH_CHECK(!t->has_value() || ((*t)->is_cuda() && (*t)->scalar_type() == at::kInt &&
-                                            (*t)->is_contiguous() && (*t)->numel() == n_),
-                        "gate / gates_passed must be contiguous int32 CUDA tensors of n elements");
         if (reset_table_.has_value()) {
             check_f32_cuda(*reset_table_, "reset_table");
             TORCH_CHECK(reset_table_->numel() == 13 * n_, "reset_table must be (n, 13)");
         }
+        if (step_base_.has_value())
+            TORCH_CHECK(step_base_->is_cuda() && step_base_->scalar_type() == at::kLong && step_base_->numel() == 1,
+                        "step_base must be a one-element int64 CUDA tensor");
         // segments of the per-step output slab, each on a 256-byte boundary
         auto pad = [](int64_t bytes) { return (bytes + 255) / 256 * 256; };
-        o_obs_ = pad(80 * n_);
+        o_status_ = pad(80 * n_);
+        o_obs_ = o_status_ + pad(16 * n_);
         o_rew_ = o_obs_ + pad(4 * obs_width_ * n_);
         o_rec_ = o_rew_ + pad(4 * n_);
         o_done_ = o_rec_ + pad(16 * n_);
-        o_saved_ = o_done_ + pad(n_);
-        o_term_ = o_saved_ + pad(8 * n_);
-        total_ = o_term_ + pad(4 * obs_width_ * n_);
+        o_copy_ = o_done_ + pad(n_);
+        sz_copy_ = pad(16 * n_);
+        sz_term_ = pad(4 * obs_width_ * n_);
     }
 
-    // returns (state', obs, reward, done, record, terminal obs | None, saved | None)
-    std::tuple<at::Tensor, at::Tensor, at::Tensor, at::Tensor, at::Tensor, OptTensor, OptTensor>
-    step(const at::Tensor& state_in, const at::Tensor& action, int64_t step_index, int64_t env_flags, bool want_term,
-         bool want_saved, int64_t host_mirror) {
+    // returns (state', status', obs, reward, done, record, terminal obs | None, fifo copy | None)
+    std::tuple<at::Tensor, at::Tensor, at::Tensor, at::Tensor, at::Tensor, at::Tensor, OptTensor, OptTensor>
+    step(const at::Tensor& state_in, const at::Tensor& action, const at::Tensor& status_in, int64_t step_index,
+         int64_t env_flags, bool want_term, int64_t host_mirror, const OptTensor& wind, const OptTensor& push) {
         check_f32_cuda(state_in, "state_in");
         check_f32_cuda(action, "action");
         TORCH_CHECK(state_in.dim() == 3 && state_in.size(0) == VF_STATE_PLANES && state_in.size(1) == n_ &&
                         state_in.size(2) == 4, "state_in must be (5, n, 4)");
         TORCH_CHECK(action.numel() == 4 * n_, "action must be (n, 4)");
+        TORCH_CHECK(status_in.is_cuda() && status_in.scalar_type() == at::kInt && status_in.is_contiguous() &&
+                        status_in.numel() == VF_STATUS_WORDS * n_, "status_in must be a contiguous int32 (n, 4) CUDA tensor");
+        if (wind.has_value()) {
+            check_f32_cuda(*wind, "wind");
+            TORCH_CHECK(wind->numel() == 4 * n_, "wind must be (n, 4)");
+        }
+        if (push.has_value()) {
+            check_f32_cuda(*push, "fifo_push");
+            TORCH_CHECK(push->numel() == 4 * n_, "fifo_push must be (n, 4)");
+        }
         c10::cuda::CUDAGuard guard(state_in.device());
         // one trip to the caching allocator for every output of the step
-        at::Tensor slab = at::empty({want_term ? total_ : o_term_}, state_in.options().dtype(at::kByte));
+        const int64_t o_term = o_copy_ + (push.has_value() ? sz_copy_ : 0);
+        at::Tensor slab = at::empty({o_term + (want_term ? sz_term_ : 0)}, state_in.options().dtype(at::kByte));
         at::Tensor state_out = carve(slab, 0, at::kFloat, {VF_STATE_PLANES, n_, 4});
+        at::Tensor status = carve(slab, o_status_, at::kInt, {n_, VF_STATUS_WORDS});
         at::Tensor obs = carve(slab, o_obs_, at::kFloat, {n_, obs_width_});
         at::Tensor reward = carve(slab, o_rew_, at::kFloat, {n_});
         at::Tensor record = carve(slab, o_rec_, at::kFloat, {n_, 4});
         at::Tensor done = carve(slab, o_done_, at::kBool, {n_});
-        OptTensor term, saved;
-        if (want_saved) saved = carve(slab, o_saved_, at::kInt, {n_, 2});
-        if (want_term) term = carve(slab, o_term_, at::kFloat, {n_, obs_width_});
+        OptTensor term, copy;
+        if (push.has_value()) copy = carve(slab, o_copy_, at::kFloat, {n_, 4});
+        if (want_term) term = carve(slab, o_term, at::kFloat, {n_, obs_width_});
         const int rc = vf_env_step_fwd(
             params_, spec_, int(n_), substeps_, integrator_, action_type_, flags_, unsigned(env_flags),
-            (unsigned long long)step_index, state_in.data_ptr<float>(), action.data_ptr<float>(),
-            static_cast<const float*>(ptr(reset_table_)), step_count_.data_ptr<int>(), returns_.data_ptr<float>(),
-            ebits_.data_ptr<uint8_t>(), static_cast<int*>(ptr(gate_)), static_cast<int*>(ptr(gates_passed_)),
-            state_out.data_ptr<float>(), obs.data_ptr<float>(), reward.data_ptr<float>(),
+            (unsigned long long)step_index,
+            step_base_.has_value() ? reinterpret_cast<const unsigned long long*>(step_base_->data_ptr<int64_t>()) : nullptr,
+            state_in.data_ptr<float>(), action.data_ptr<float>(), static_cast<const float*>(ptr(wind)),
+            static_cast<const float*>(ptr(push)), static_cast<const float*>(ptr(reset_table_)),
+            status_in.data_ptr<int>(), state_out.data_ptr<float>(), status.data_ptr<int>(),
+            static_cast<float*>(ptr(copy)), obs.data_ptr<float>(), reward.data_ptr<float>(),
             reinterpret_cast<unsigned char*>(done.data_ptr<bool>()), record.data_ptr<float>(),
-            static_cast<float*>(ptr(term)), static_cast<int*>(ptr(saved)),
-            reinterpret_cast<const VfEnvMirror*>(host_mirror),
+            static_cast<float*>(ptr(term)), reinterpret_cast<const VfEnvMirror*>(host_mirror),
             c10::cuda::getCurrentCUDAStream(state_in.device().index()).stream());
         TORCH_CHECK(rc == 0, "visfly_b200: ", vf_last_error());
-        return {state_out, obs, reward, done, record, term, saved};
+        return {state_out, status, obs, reward, done, record, term, copy};
     }
 
   private:
@@ -142,10 +160,19 @@ class EnvStepper {
     int substeps_, integrator_, action_type_;
     unsigned flags_;
     int64_t n_, obs_width_;
-    at::Tensor step_count_, returns_, ebits_;
-    OptTensor gate_, gates_passed_, reset_table_;
-    int64_t o_obs_ = 0, o_rew_ = 0, o_rec_ = 0, o_done_ = 0, o_saved_ = 0, o_term_ = 0, total_ = 0;
+    OptTensor reset_table_, step_base_;
+    int64_t o_status_ = 0, o_obs_ = 0, o_rew_ = 0, o_rec_ = 0, o_done_ = 0, o_copy_ = 0, sz_copy_ = 0, sz_term_ = 0;
 };
+
+// Spin on the kernel's completion word (VfEnvMirror.flag) with the GIL released.
+void wait_flag(int64_t flag_addr, int64_t value, int64_t timeout_us) {
+    int rc;
+    {
+        py::gil_scoped_release release;
+        rc = vf_wait_flag(reinterpret_cast<const volatile unsigned*>(flag_addr), unsigned(value), (long long)timeout_us);
+    }
+    TORCH_CHECK(rc == 0, "visfly_b200: ", vf_last_error());
+}
 
 }  // namespace
 
@@ -153,10 +180,12 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.doc() = "visfly_b200 host plumbing: output allocation + C-ABI launch in one call";
     m.def("step_fwd", &step_fwd, py::arg("params"), py::arg("substeps"), py::arg("integrator"),
           py::arg("action_type"), py::arg("flags"), py::arg("state_in"), py::arg("action"),
-          py::arg("wind") = py::none());
+          py::arg("wind") = py::none(), py::arg("push") = py::none());
     py::class_<EnvStepper>(m, "EnvStepper")
-        .def(py::init<int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, at::Tensor, at::Tensor, at::Tensor,
-                      OptTensor, OptTensor, OptTensor, int64_t>())
-        .def("step", &EnvStepper::step);
+        .def(py::init<int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, OptTensor, int64_t, OptTensor>())
+        .def("step", &EnvStepper::step, py::arg("state_in"), py::arg("action"), py::arg("status_in"),
+             py::arg("step_index"), py::arg("env_flags"), py::arg("want_term"), py::arg("host_mirror"),
+             py::arg("wind") = py::none(), py::arg("push") = py::none());
+    m.def("wait_flag", &wait_flag, py::arg("flag_addr"), py::arg("value"), py::arg("timeout_us") = 10000000);
     m.def("abi_version", []() { return vf_abi_version(); });
 }

@@ -68,22 +68,65 @@ def shard_seed(seed: int, rank: int) -> int:
     return int(seed) + 1_000_003 * int(rank)
 
 
-def gather_episode_returns(returns: th.Tensor, group=None) -> th.Tensor:
-    """All-gather the per-agent episode returns of every shard: ``(n_local,) -> (sum of n_local over ranks,)`` in
-    rank order.  Shards may differ in size by one (see ``shard_range``); single-process runs return the input."""
+class EpisodeReturnsGather:
+    """The one collective of the path: all-gather of the per-agent episode returns of every shard,
+    once per rollout, ``(n_local,) -> (n_total,)`` in rank order.
+
+    Everything that can be decided ahead of the rollout is decided here: shard sizes follow from ``shard_range``
+    (no size exchange, no ``.item()``), the receive buffer is allocated once, and ``__call__`` is ONE
+    ``all_gather_into_tensor`` enqueued on the current stream — it never synchronises with the host, so the launches
+    queued behind it keep flowing.  The returned tensor is valid in stream order and is overwritten by the next call.
+    Shards that differ in size by one (``n_total % world != 0``) go through a ``base+1``-wide staging row and one
+    precomputed ``index_select``; equal shards take the direct path with no extra kernel."""
+
+    def __init__(self, n_total: int, rank: int, world: int, device, dtype=th.float32, group=None):
+        self.n_total, self.rank, self.world, self.group = int(n_total), int(rank), int(world), group
+        lo, hi = shard_range(n_total, rank, world)
+        self.n_local = hi - lo
+        base, extra = divmod(self.n_total, self.world)
+        self.ragged = extra != 0
+        if not self.ragged:
+            self.out = th.empty((self.n_total,), device=device, dtype=dtype)
+        else:
+            self.width = base + 1
+            self.stage = th.zeros((self.width,), device=device, dtype=dtype)
+            self.wide = th.empty((self.world * self.width,), device=device, dtype=dtype)
+            idx = [r * self.width + k for r in range(world) for k in range(base + (1 if r < extra else 0))]
+            self.index = th.tensor(idx, device=device, dtype=th.int64)
+            self.out = th.empty((self.n_total,), device=device, dtype=dtype)
+
+    def __call__(self, returns: th.Tensor) -> th.Tensor:
+        if returns.numel() != self.n_local:
+            raise ValueError(f"rank {self.rank} owns {self.n_local} agents, got {returns.numel()} returns")
+        src = returns.detach().reshape(-1)
+        if self.world == 1:
+            return src
+        if not self.ragged:
+            dist.all_gather_into_tensor(self.out, src.contiguous(), group=self.group)
+            return self.out
+        self.stage[:self.n_local].copy_(src)
+        dist.all_gather_into_tensor(self.wide, self.stage, group=self.group)
+        th.index_select(self.wide, 0, self.index, out=self.out)
+        return self.out
+
+
+_GATHERS = {}
+
+
+def gather_episode_returns(returns: th.Tensor, n_total: Optional[int] = None, group=None) -> th.Tensor:
+    """All-gather the per-agent episode returns of every shard: ``(n_local,) -> (n_total,)`` in rank order, one
+    asynchronous ``all_gather_into_tensor`` (see ``EpisodeReturnsGather``; the gather object is cached per shape).
+    ``n_total`` = number of agents over all ranks; ``None`` means equal shards (``n_local * world``).  Shards must
+    follow ``shard_range``.  Single-process runs return the input."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return returns
-    world = dist.get_world_size(group)
-    n_local = th.tensor([returns.numel()], device=returns.device, dtype=th.int64)
-    sizes = [th.zeros_like(n_local) for _ in range(world)]
-    dist.all_gather(sizes, n_local, group=group)
-    sizes = [int(s) for s in sizes]
-    width = max(sizes)
-    padded = returns.new_zeros(width)
-    padded[:returns.numel()] = returns.reshape(-1)
-    parts = [returns.new_empty(width) for _ in range(world)]
-    dist.all_gather(parts, padded, group=group)
-    return th.cat([p[:k] for p, k in zip(parts, sizes)])
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    n_total = returns.numel() * world if n_total is None else int(n_total)
+    key = (n_total, rank, world, returns.device, returns.dtype, id(group))
+    g = _GATHERS.get(key)
+    if g is None:
+        g = _GATHERS[key] = EpisodeReturnsGather(n_total, rank, world, returns.device, returns.dtype, group)
+    return g(returns)
 
 
 def rollout_stats(ep_return_sum: th.Tensor, ep_len_sum: th.Tensor, ep_count: th.Tensor, group=None):

@@ -58,20 +58,25 @@ class StepConfig:
 
 
 class ControlStep(th.autograd.Function):
-    """``(state[5,N,4], action[N,4]) -> (state'[5,N,4], obs[N,13])`` — one kernel each way."""
+    """``(state[5,N,4], action[N,4], push[N,4] | None) -> (state'[5,N,4], obs[N,13], copy[N,4] | None)`` — one kernel
+    each way.  ``action`` is the (comm-delayed) action the step consumes; ``push`` is the action that arrived this
+    step: the kernel leaves an engine-owned copy of it next to its other outputs — the reference's
+    ``action.T.clone()`` (dynamics.py:324) — which is what waits in the FIFO.  Its gradient passes straight through to
+    ``push``, exactly like the clone's."""
 
     @staticmethod
-    def forward(ctx, state: th.Tensor, action: th.Tensor, cfg: StepConfig, wind: Optional[th.Tensor] = None):
-        state_out, obs = _lib.fast().step_fwd(cfg.params_addr, cfg.substeps, cfg.integrator, cfg.action_type,
-                                              cfg.flags, state, action, wind)
+    def forward(ctx, state: th.Tensor, action: th.Tensor, push: Optional[th.Tensor], cfg: StepConfig,
+                wind: Optional[th.Tensor] = None):
+        state_out, obs, copy = _lib.fast().step_fwd(cfg.params_addr, cfg.substeps, cfg.integrator, cfg.action_type,
+                                                    cfg.flags, state, action, wind, push)
         ctx.cfg, ctx.wind = cfg, wind
         ctx.save_for_backward(state, action)
         ctx.set_materialize_grads(False)
-        return state_out, obs
+        return state_out, obs, copy
 
     @staticmethod
     @th.autograd.function.once_differentiable
-    def backward(ctx, g_state_out, g_obs):
+    def backward(ctx, g_state_out, g_obs, g_copy):
         state, action = ctx.saved_tensors
         cfg = ctx.cfg
         g_state = th.empty_like(state)
@@ -82,7 +87,7 @@ class ControlStep(th.autograd.Function):
             g_obs = g_obs.contiguous()
         _lib.step_bwd(cfg.params, cfg.substeps, cfg.integrator, cfg.action_type, cfg.flags,
                       state, action, g_state_out, g_obs, g_state, g_action, ctx.wind)
-        return g_state, g_action, None, None
+        return g_state, g_action, g_copy, None, None
 
 
 class Dynamics:
@@ -251,9 +256,9 @@ class Dynamics:
                 th.as_tensor(t, dtype=th.float32, device=dev).reshape(n).clone()
             self._n_steps = 0
             self._pre_action = [th.zeros((n, 4), device=dev) for _ in range(self._comm_delay_steps)]
-            self._fifo_versions = [None] * self._comm_delay_steps
             self._prev, self._ext, self._fresh = None, None, None
-            self._t_steps = None
+            self._t_provider = None
+            self._t_custom = t is not None
             self._thrusts_given = None if thrusts is None else self._f(thrusts, 4)
             if self._drag_random and not self._constructing:
                 self._randomize_drag()
@@ -272,7 +277,7 @@ class Dynamics:
                 t_new = th.as_tensor(t, dtype=th.float32, device=dev).reshape(m)
             self._t_base = self._t_base.index_copy(0, idx, t_new - self._n_steps * self.ctrl_dt)
             self._pre_action = [a.index_fill(0, idx, 0.0) for a in self._pre_action]
-            self._fifo_versions = [None] * len(self._pre_action)
+            self._t_custom = self._t_custom or t is not None or self._random_reset_time
             fresh = th.zeros((self.num,), dtype=th.bool, device=dev).index_fill(0, idx, True)
             self._mark_fresh(fresh)
             if thrusts is not None:
@@ -297,7 +302,7 @@ class Dynamics:
             t_new = th.as_tensor(t, dtype=th.float32, device=self.device).reshape(n)
         self._t_base = th.where(mask, t_new - self._n_steps * self.ctrl_dt, self._t_base)
         self._pre_action = [th.where(m1, 0.0, a) for a in self._pre_action]
-        self._fifo_versions = [None] * len(self._pre_action)
+        self._t_custom = self._t_custom or t is not None or self._random_reset_time
         self._mark_fresh(mask)
         return self.state
 
@@ -311,55 +316,57 @@ class Dynamics:
         """Cut the autograd graph at the current state (reference dynamics.py:176-190)."""
         self._state = self._state.detach()
         self._obs = self._obs.detach()
-        self._pre_action = [a.detach() for a in self._pre_action]      # detach() shares the version counter
+        self._pre_action = [a.detach() for a in self._pre_action]
 
     # -- comm-delay FIFO (reference dynamics.py:323-328) ----------------------------------------------------
-    # The reference stores a CLONE of every action (`action.T.clone()`); here the caller's tensor itself waits in the
-    # FIFO (a clone is one more launch per step on a path where the whole step is one launch).  The price is a rule
-    # — an action handed to step() must not be modified in place for comm_delay / ctrl_dt further steps — and the
-    # rule is enforced: the tensor's version counter is remembered and checked when the action is finally consumed.
-    def _fifo_push(self, action: th.Tensor):
-        self._pre_action.append(action)
-        self._fifo_versions.append((id(action), action._version))
-
-    def _fifo_pop(self) -> th.Tensor:
-        action = self._pre_action.pop(0)
-        rec = self._fifo_versions.pop(0)         # None: an entry the engine itself wrote (reset rows, zeros)
-        # the identity test skips entries that were re-created since (deepcopy of the env, detach): those are copies
-        # the engine owns, nothing outside can alias them
-        if rec is not None and rec[0] == id(action) and action._version != rec[1]:
-            raise RuntimeError(
-                "an action tensor was modified in place while it was waiting in the comm-delay FIFO "
-                f"({self._comm_delay_steps} control steps): pass a fresh tensor to step() each time, or action.clone()")
-        return action
+    # The reference stores a CLONE of every action (`action.T.clone()`).  Here the clone is made by the step kernel
+    # itself: the launch that consumes the delayed action also copies the newly arrived one into its own output slab
+    # (`fifo_push` -> `fifo_copy`, +32 B per agent, no extra launch), and that engine-owned copy is what waits in
+    # `_pre_action`.  The caller may therefore overwrite its action buffer as soon as step() returns, like with the
+    # reference.  Actions that reach the device through a conversion (numpy / CPU tensors, other dtypes, strided
+    # views) are already private copies and enter the FIFO directly.
+    def _as_device_action(self, action):
+        """``(action on the device, owned)``: owned = the tensor was created here and nobody else can write to it."""
+        owned = False
+        if not isinstance(action, th.Tensor):
+            action = th.from_numpy(np.asarray(action))
+        if action.dtype is not th.float32 or action.device != self.device:
+            action, owned = action.to(device=self.device, dtype=th.float32), True
+        if action.shape != (self.num, 4):
+            raise ValueError(f"action must have shape ({self.num}, 4), got {tuple(action.shape)}")
+        if not action.is_contiguous():
+            action, owned = action.contiguous(), True
+        return action, owned
 
     # ------------------------------------------------------------------------------------------
     def step(self, action) -> th.Tensor:
         """One control step; ``action`` is (N,4) in ``action_space``; returns ``state`` (reference :319-372)."""
-        if not isinstance(action, th.Tensor):
-            action = th.from_numpy(np.asarray(action))
-        if action.dtype is not th.float32 or action.device != self.device:
-            action = action.to(device=self.device, dtype=th.float32)
-        if action.shape != (self.num, 4):
-            raise ValueError(f"action must have shape ({self.num}, 4), got {tuple(action.shape)}")
+        action, owned = self._as_device_action(action)
+        push = None
         if self._comm_delay_steps:                                   # dynamics.py:323-326
-            self._fifo_push(action)
-            action = self._fifo_pop()
-        if not action.is_contiguous():
-            action = action.contiguous()
+            if owned:
+                self._pre_action.append(action)
+            else:
+                push = action                                        # cloned by the launch below
+            action = self._pre_action.pop(0)
         state, cfg = self._state, self._cfg
         if self._wind_fn is not None:
             self.update_wind()                                       # dynamics.py:320
         wind = self._wind_rows
-        if th.is_grad_enabled() and (state.requires_grad or action.requires_grad):
-            self._prev = (state.detach(), action.detach())
-            self._state, self._obs = ControlStep.apply(state, action, cfg, wind)
+        if th.is_grad_enabled() and (state.requires_grad or action.requires_grad or
+                                     (push is not None and push.requires_grad)):
+            self._prev = (state.detach(), action.detach(), None)
+            self._state, self._obs, copy = ControlStep.apply(state, action, push, cfg, wind)
         else:
             # nothing to differentiate: straight to the launch (an autograd.Function costs ~8 us of host time per
             # call even when no input requires grad; the kernel takes ~11 us at 65 536 agents)
-            self._prev = (state, action)
-            self._state, self._obs = _lib.fast().step_fwd(cfg.params_addr, cfg.substeps, cfg.integrator,
-                                                          cfg.action_type, cfg.flags, state, action, wind)
+            # without a FIFO the consumed action is the caller's own tensor: remember its version so that the lazy
+            # diagnostics (_extras) can tell if it was overwritten in the meantime
+            self._prev = (state, action, None if (owned or self._comm_delay_steps) else action._version)
+            self._state, self._obs, copy = _lib.fast().step_fwd(cfg.params_addr, cfg.substeps, cfg.integrator,
+                                                                cfg.action_type, cfg.flags, state, action, wind, push)
+        if push is not None:
+            self._pre_action.append(copy)
         self._n_steps += 1
         self._ext, self._fresh, self._thrusts_given = None, None, None
         if self._debug_checks:                                       # dynamics.py:333 (device sync!)
@@ -375,9 +382,17 @@ class Dynamics:
             if self._prev is None:
                 ext[:, 4:] = rest
             else:
-                scratch = th.empty_like(self._prev[0])
+                state_in, action, version = self._prev
+                if hasattr(action, "resolve"):          # fused env step: the action as masked by the kernel
+                    action = action.resolve()
+                if version is not None and action._version != version:
+                    raise RuntimeError(
+                        "acceleration / thrusts of the last step are produced on demand from the step's inputs, but the "
+                        "action tensor passed to step() was modified in place since (comm_delay=0 keeps no copy): read "
+                        "these diagnostics before reusing the action buffer, or pass action.clone()")
+                scratch = th.empty_like(state_in)
                 _lib.step_fwd(self._cfg.params, self._cfg.substeps, self._cfg.integrator, self._cfg.action_type,
-                              self._cfg.flags, self._prev[0], self._prev[1], scratch, None, ext, self._wind_rows)
+                              self._cfg.flags, state_in, action, scratch, None, ext, self._wind_rows)
                 if self._fresh is not None:
                     m1 = self._fresh.view(-1, 1)
                     ext = th.cat([th.where(m1, 0.0, ext[:, :4]), th.where(m1, rest, ext[:, 4:])], 1)
@@ -451,8 +466,8 @@ class Dynamics:
 
     @property
     def t(self):
-        if self._t_steps is not None:        # fused env step: time since the agent's last reset
-            return self._t_steps * self.ctrl_dt
+        if self._t_provider is not None:     # fused env step: per-agent step count (+ the offsets given at reset)
+            return self._t_provider()
         return self._t_base + self._n_steps * self.ctrl_dt
 
     # the (N,13) observation is a kernel output; it is rebuilt from the packed state only if a path that does

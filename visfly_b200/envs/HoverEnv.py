@@ -45,9 +45,9 @@ class HoverEnv(DroneGymEnvsBase):
     def _make_fused(self):
         from .. import params as P
         from .base.fused import FusedEnvStep
-        if not self._builtin_task(HoverEnv) or bool((self.target != self.target[0]).any()):
+        if not self._builtin_task(HoverEnv):
             return None
-        return FusedEnvStep(self, P.TASK_HOVER, P.OBS_STATE13, target=self.target[0].tolist())
+        return FusedEnvStep(self, P.TASK_HOVER, P.OBS_STATE13)     # target etc. are read from the live attributes
 
     def get_success(self) -> th.Tensor:
         return th.zeros(self.num_agent, dtype=th.bool, device=self.device)      # reference HoverEnv.py:79-80

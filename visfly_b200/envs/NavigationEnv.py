@@ -47,10 +47,9 @@ class NavigationEnv(DroneGymEnvsBase):
     def _make_fused(self):
         from .. import params as P
         from .base.fused import FusedEnvStep
-        if not self._builtin_task(NavigationEnv) or bool((self.target != self.target[0]).any()):
+        if not self._builtin_task(NavigationEnv):
             return None
-        return FusedEnvStep(self, P.TASK_NAVIGATION, P.OBS_STATE13, target=self.target[0].tolist(),
-                            success_radius=self.success_radius)
+        return FusedEnvStep(self, P.TASK_NAVIGATION, P.OBS_STATE13)   # target / radius: read from the live attributes
 
     def _fused_obs(self, obs):
         return TensorDict({"state": obs, "target": self.target})

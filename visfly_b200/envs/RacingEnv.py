@@ -64,6 +64,25 @@ class RacingEnv(DroneGymEnvsBase):
 
     is_pass_next = property(lambda s: s._is_pass_next)
 
+    # gate bookkeeping: while the one-kernel path is active it lives in the kernel's status records
+    @property
+    def _next_target_i(self):
+        f = self._fused_live()
+        return f.gate.to(th.int64) if f is not None else self.__dict__["_next_target_i_v"]
+
+    @_next_target_i.setter
+    def _next_target_i(self, v):
+        self.__dict__["_next_target_i_v"] = v
+
+    @property
+    def _past_targets_num(self):
+        f = self._fused_live()
+        return f.passed.to(th.int64) if f is not None else self.__dict__["_past_targets_num_v"]
+
+    @_past_targets_num.setter
+    def _past_targets_num(self, v):
+        self.__dict__["_past_targets_num_v"] = v
+
     def _extra_info(self, indice, info):
         info["episode"]["extra"]["past_gate"] = int(self._past_targets_num_at_done[indice])
 
@@ -82,8 +101,7 @@ class RacingEnv(DroneGymEnvsBase):
         owner = RacingEnv2 if isinstance(self, RacingEnv2) else RacingEnv
         if not is_pos_reward or not self._builtin_task(owner) or type(self)._extra_info is not RacingEnv._extra_info:
             return None
-        return FusedEnvStep(self, P.TASK_RACING, self._FUSED_OBS, gates=self.targets,
-                            success_radius=self.success_radius)
+        return FusedEnvStep(self, P.TASK_RACING, self._FUSED_OBS)     # gates / radius: read from the live attributes
 
     def _fused_obs(self, obs):
         gate = self._fused.gate.to(th.int64)

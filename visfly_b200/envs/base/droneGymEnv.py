@@ -28,6 +28,7 @@ from .droneEnv import DroneEnvsBase
 
 
 _RecordInfo = None          # envs/base/fused.py:RecordInfo, bound on first use
+_wait_flag = None
 
 
 class LazyInfo(Sequence):
@@ -152,6 +153,7 @@ class DroneGymEnvsBase(VecEnv):
         self._info = None
         self._indiv_rewards = self._indiv_reward = None
         self.keep_terminal_observation = True     # False: skip writing info["terminal_observation"] rows
+        self.host_ring_depth = 4                  # numpy mode: arrays returned by a step stay valid for depth-1 more steps
         self.use_fused_step = True                # False: force the generic tensor-op path (debugging / comparison)
         self._fused = None                        # FusedEnvStep, created by built-in tasks (_make_fused)
         self.render_mode = ["None"] * n
@@ -173,6 +175,8 @@ class DroneGymEnvsBase(VecEnv):
         if overlap:
             return self._step_fused(host_action=_action)
         self._action = self._stage_action(_action)
+        # a device tensor handed in by the caller is still the caller's: the step launch clones it for the FIFO
+        self._action_owned = self._action is not _action
         if self.debug_checks:                                   # reference droneGymEnv.py:144 (host sync)
             assert self._action.max() <= 1 and self._action.min() >= -1
         if self._fused is not None:
@@ -236,9 +240,11 @@ class DroneGymEnvsBase(VecEnv):
         return out
 
     def _step_fused(self, host_action=None):
-        global _RecordInfo
+        global _RecordInfo, _wait_flag
         if _RecordInfo is None:                  # resolved once (fused.py imports this module's siblings)
             from .fused import RecordInfo as _RecordInfo
+            from ... import _lib
+            _wait_flag = _lib.fast().wait_flag
         if self.requires_grad and not self.tensor_output:
             raise ValueError("requires_grad should be False if tensor_output is False")
         slot = None if self.tensor_output else self._fused.host_slot()
@@ -247,11 +253,13 @@ class DroneGymEnvsBase(VecEnv):
             def late():
                 self._action = self._stage_action(host_action, side_stream=True)
                 return self._action
-        obs, reward, done, record, term = self._fused.step(None if late else self._action, grad=self.requires_grad,
+        obs, reward, done, record, term = self._fused.step(None if late else self._action,
+                                                           owned=bool(late) or self._action_owned,
+                                                           grad=self.requires_grad,
                                                            mirror=None if slot is None else slot["ref"],
                                                            late_action=late)
         self._obs_tensors = self._fused_obs(obs)
-        if self._fused.gate is None:
+        if self._fused.task != 2:                # params.TASK_RACING
             # the terminal-observation dict is built only if somebody reads a finished agent's info
             info = _RecordInfo(self.num_agent, record, term, self.envs.dynamics.ctrl_dt, False, self._fused_obs)
         else:
@@ -263,8 +271,9 @@ class DroneGymEnvsBase(VecEnv):
             self._observations = self._obs_tensors
             return self._obs_tensors, reward, done, info
         # numpy mode (reference droneGymEnv.py:218): the kernel has already written obs / reward / done into the
-        # page-locked host slot (zero-copy stores over PCIe); one stream synchronisation makes them readable
-        th.cuda.current_stream(self.device).synchronize()
+        # page-locked host slot (zero-copy stores over PCIe); its last thread block raises the slot's completion word,
+        # which the host spins on (no driver call, and nothing queued behind the launch is waited for)
+        _wait_flag(slot["flag"].data_ptr(), slot["expect"])
         evt = self.__dict__.pop("_h2d_evt", None)
         if evt is not None:
             evt.synchronize()                        # join the side-stream copy of this step's action
@@ -538,6 +547,52 @@ class DroneGymEnvsBase(VecEnv):
         return (f"{self.__class__.__name__}(Env={self.envs.__class__}, NumAgentPerScene={self.num_agent_per_scene}, "
                 f"NumScene={self.num_scene}, tensorOut={self.tensor_output}, RequiresGrad={self.requires_grad})")
 
+    # -- per-agent bookkeeping that the one-kernel path keeps in its status / episode records ------------------------
+    # While the fused path is active these read straight from the kernel's records (no per-step copies); otherwise
+    # they are the plain tensors the generic path maintains.
+    def _fused_live(self):
+        f = self.__dict__.get("_fused")
+        return f if (f is not None and f.active) else None
+
+    def _record_bit(self, bit, fallback):
+        f = self._fused_live()
+        if f is None or f.record is None:
+            return fallback
+        return (f.record[:, 2].to(th.int32) & bit) != 0
+
+    @property
+    def _step_count(self):
+        f = self._fused_live()
+        return f.sc if f is not None else self.__dict__["_step_count_v"]
+
+    @_step_count.setter
+    def _step_count(self, v):
+        self.__dict__["_step_count_v"] = v
+
+    @property
+    def _rewards(self):
+        f = self._fused_live()
+        return f.ret if f is not None else self.__dict__["_rewards_v"]
+
+    @_rewards.setter
+    def _rewards(self, v):
+        self.__dict__["_rewards_v"] = v
+
+    @property
+    def episode_done(self):
+        f = self._fused_live()
+        return (f.eb & 1) != 0 if f is not None else self._episode_done
+
+    @property
+    def success(self):
+        return self._record_bit(4, self._success)               # params.RBIT_SUCCESS
+
+    @property
+    def failure(self):
+        f = self._fused_live()
+        # built-in tasks have no failure condition of their own (get_failure is all-False, e.g. HoverEnv.py:79-80)
+        return th.zeros_like(self._failure) if f is not None else self._failure
+
     reward = property(lambda s: s._reward)
     sensor_obs = property(lambda s: s.envs.sensor_obs)
     state = property(lambda s: s.envs.state)
@@ -545,9 +600,6 @@ class DroneGymEnvsBase(VecEnv):
     is_collision = property(lambda s: s.envs.is_collision)
     is_out_bounds = property(lambda s: s.envs.is_out_bounds)
     done = property(lambda s: s._done)
-    episode_done = property(lambda s: s._episode_done)
-    success = property(lambda s: s._success)
-    failure = property(lambda s: s._failure)
     direction = property(lambda s: s.envs.direction)
     position = property(lambda s: s.envs.position)
     orientation = property(lambda s: s.envs.orientation)

@@ -27,16 +27,19 @@ _raw_stream = getattr(th._C, "_cuda_getCurrentRawStream", None) or \
     (lambda index: th.cuda.current_stream(index).cuda_stream)
 
 
-def generator_spec(gen, spec: P.VfEnvSpec) -> bool:
-    """Fill the reset-sampler part of ``spec`` from a state generator; False if the kernel cannot express it."""
+def generator_spec(gen, spec: P.VfEnvSpec, watch: Optional[list] = None) -> bool:
+    """Fill the reset-sampler part of ``spec`` from a state generator; False if the kernel cannot express it.
+    The generator's tables are appended to ``watch`` (their version counters are checked every step)."""
     boxes = gen.randomizers if isinstance(gen, UnionRandomizer) else [gen]
     if not 1 <= len(boxes) <= P.GEN_MAX_BOXES:
         return False
     kinds = set()
     for b, g in enumerate(boxes):
+        spec.gen_heading[b] = 0
         if isinstance(g, UniformStateRandomizer):
-            if g.heading:                      # yaw towards the box centre: sampled by the generic path
+            if g.test:                         # deterministic evaluation grid: sampled by the generic path
                 return False
+            spec.gen_heading[b] = int(bool(g.heading))     # yaw towards the box centre (randomization.py:162-165)
             kinds.add(P.GEN_UNIFORM)
             mean, half = g._mean, g._half
         elif isinstance(g, NormalStateRandomizer):
@@ -44,6 +47,8 @@ def generator_spec(gen, spec: P.VfEnvSpec) -> bool:
             mean, half = g._mean, g._std
         else:
             return False
+        if watch is not None:
+            watch.extend((mean, half))
         mean, half = mean.cpu(), half.cpu()
         for f in range(4):
             for j in range(3):
@@ -123,29 +128,28 @@ class RecordInfo(Sequence):
         return (self._record[:, 2].to(th.int32) & P.RBIT_EPISODE_DONE) != 0
 
 
-class FusedEnvStep:
-    """Owns the spec and the in-place per-agent env state of one env object while the fused path is active."""
+_TASK_METHODS = ("get_reward", "get_success", "get_failure", "get_observation")
 
-    def __init__(self, env, task: int, obs_kind: int, target=None, gates=None, success_radius: float = 0.5):
+
+def _ver(t):
+    return -1 if t is None else t._version
+
+
+class FusedEnvStep:
+    """Owns the spec and the per-agent env status records of one env object while the fused path is active.
+
+    Status lives in ONE ``int32 (N,4)`` tensor (``VfEnvStatus``: step count, return, flag bits | gate, gates passed);
+    every step reads the current one and writes a fresh one into its output slab, so the record a step started from
+    stays intact (the adjoint kernel reads it; ``rewind`` goes back to it).  ``sc / ret / eb / gate / passed`` are
+    views of the current record built on demand."""
+
+    def __init__(self, env, task: int, obs_kind: int):
         dyn = env.envs.dynamics
         self.env, self.n, self.device = env, env.num_agent, env.device
         self.task, self.obs_kind = task, obs_kind
         self.obs_width = 13 if obs_kind == P.OBS_STATE13 else 16
         s = P.VfEnvSpec()
         s.task, s.obs_kind = task, obs_kind
-        s.uav_radius = env.envs.uav_radius
-        lo, hi = env.envs._bboxes[0][0].tolist(), env.envs._bboxes[0][1].tolist()
-        for j in range(3):
-            s.bbox_lo[j], s.bbox_hi[j] = lo[j], hi[j]
-            s.target[j] = 0.0 if target is None else float(target[j])
-        s.success_radius = success_radius
-        s.n_gates = 0
-        if gates is not None:
-            g = th.as_tensor(gates).cpu()
-            s.n_gates = g.shape[0]
-            for a in range(g.shape[0]):
-                for j in range(3):
-                    s.gates[a][j] = float(g[a, j])
         s.fifo_depth = dyn._comm_delay_steps
         s.init_motor_omega = float(dyn._init_motor_omega)
         s.seed = (int(env.envs.seed) * 0x9E3779B97F4A7C15 + 0x1234567) & 0xFFFFFFFFFFFFFFFF
@@ -153,12 +157,16 @@ class FusedEnvStep:
         self.table: Optional[th.Tensor] = None
         self.active = False
         self.global_step = 0
-        self.sc = self.ret = self.eb = self.gate = self.passed = None
-        self._key, self._ok = None, False
+        self.status: Optional[th.Tensor] = None
+        self.record: Optional[th.Tensor] = None      # episode record of the last step (success / failure views)
+        self.t_off: Optional[th.Tensor] = None       # per-agent time offsets given at reset (None: all zero)
+        self.step_base: Optional[th.Tensor] = None   # device word added to the Philox step index (graph replays)
+        self._views = (None, None)
+        self._key, self._watch, self._watch_sum, self._ok = None, (), 0, False
         self._fn = None
         self._bind()
 
-    _CTYPES_REFS = ("_fn", "_stepper", "_params_addr", "_spec_addr", "_host_ring", "_host_turn")
+    _CTYPES_REFS = ("_fn", "_stepper", "_params_addr", "_spec_addr", "_host_ring", "_host_turn", "_views")
 
     def __deepcopy__(self, memo):
         """ctypes references are per-object handles: the copy re-creates them against its own env / spec."""
@@ -169,6 +177,7 @@ class FusedEnvStep:
             if k not in self._CTYPES_REFS:
                 setattr(twin, k, copy.deepcopy(v, memo))
         twin._fn = twin._stepper = None   # re-bound on first use (the twin env may not be fully copied yet)
+        twin._views = (None, None)
         return twin
 
     def _bind(self):
@@ -178,59 +187,118 @@ class FusedEnvStep:
         self._spec_addr = ctypes.addressof(self.spec)
 
     def _make_stepper(self):
-        """Bind what does not change from step to step (parameter blocks, kernel variant, in-place status buffers,
-        reset table) into the C++ stepper; rebuilt whenever one of those is replaced (``enter``, ``_refresh``)."""
+        """Bind what does not change from step to step (parameter blocks, kernel variant, reset table, the device
+        word of the Philox step base) into the C++ stepper; rebuilt whenever one of those is replaced."""
         cfg = self.env.envs.dynamics._cfg
         self._stepper = self._fn(self._params_addr, self._spec_addr, cfg.substeps, cfg.integrator, cfg.action_type,
-                                 cfg.flags, self.n, self.sc, self.ret, self.eb, self.gate, self.passed, self.table,
-                                 self.obs_width)
+                                 cfg.flags, self.n, self.table, self.obs_width, self.step_base)
         return self._stepper
+
+    # -- views of the current status record ---------------------------------------------------------------
+    def _fields(self):
+        if self._views[0] is not self.status:
+            self._views = (self.status, _lib.unpack_status(self.status))
+        return self._views[1]
+
+    sc = property(lambda self: self._fields()[0])
+    ret = property(lambda self: self._fields()[1])
+    eb = property(lambda self: self._fields()[2])
+    gate = property(lambda self: self._fields()[3] if self.task == P.TASK_RACING else None)
+    passed = property(lambda self: self._fields()[4] if self.task == P.TASK_RACING else None)
+
+    def t_now(self) -> th.Tensor:
+        t = self.sc * self.env.envs.dynamics.ctrl_dt
+        return t if self.t_off is None else t + self.t_off
 
     # -- eligibility ------------------------------------------------------------------------------------
     def refresh(self) -> bool:
         """Re-read the settings that may change between steps; False => the generic path must be used.
-        The answer is cached on the identity of everything it depends on (this runs once per step)."""
+        The answer is cached on the identity of every object it was derived from plus the version counters of the
+        tensors among them, so in-place edits (``env.target[:] = ...``, generator tables) are seen as well as
+        re-assignments; the check runs once per step and costs well under a microsecond."""
         env = self.env
         envs = env.envs
-        key = (id(envs.stateGenerator), id(envs._reset_table), env.max_episode_steps, env.is_collision_reset,
-               "_generate_state" in envs.__dict__, env.use_fused_step)
-        if key == self._key:
+        d = env.__dict__
+        key = (envs.stateGenerator, envs._reset_table, env.max_episode_steps, env.is_collision_reset,
+               env.use_fused_step, d.get("target"), d.get("targets"), d.get("success_radius"), envs.uav_radius,
+               envs._bboxes[0], envs.dynamics._wind_fn is None)
+        vsum = 0
+        for t in self._watch:
+            vsum += t._version
+        old = self._key
+        if old is not None and vsum == self._watch_sum and len(old) == len(key) and \
+                all(a is b or (type(a) in (int, float, bool) and a == b) for a, b in zip(old, key)):
             return self._ok
         self._key = key
         self._ok = self._refresh()
+        self._watch_sum = sum(t._version for t in self._watch)
         return self._ok
 
     def _refresh(self) -> bool:
-        env, s = self.env, self.spec
+        """Rebuild the spec from the env's live attributes (host reads: only when something changed)."""
+        env, envs, s = self.env, self.env.envs, self.spec
         self._stepper = None
-        if os.environ.get("VISFLY_B200_NO_FUSED_ENV") or not env.use_fused_step or not env.envs._imu_noise_free:
-            return False
-        if not env.envs.dynamics.is_quat_output or "_generate_state" in vars(env.envs):
-            return False
-        if env.envs.dynamics._wind_fn is not None:      # per-agent wind functions: generic path (vf_step_fwd + wind)
-            return False
+        watch = []
+        ok = True
+        if os.environ.get("VISFLY_B200_NO_FUSED_ENV") or not env.use_fused_step or not envs._imu_noise_free:
+            ok = False
+        if not envs.dynamics.is_quat_output or "_generate_state" in vars(envs):
+            ok = False
+        if any(m in vars(env) for m in _TASK_METHODS):      # instance-level override of a task method
+            ok = False
         s.max_episode_steps = int(env.max_episode_steps)
         s.collision_reset = int(bool(env.is_collision_reset))
-        table = env.envs._reset_table
+        s.uav_radius = float(envs.uav_radius)
+        box = envs._bboxes[0]
+        watch.append(box)
+        lo, hi = box[0].tolist(), box[1].tolist()
+        for j in range(3):
+            s.bbox_lo[j], s.bbox_hi[j] = lo[j], hi[j]
+        s.success_radius = float(getattr(env, "success_radius", 0.5))
+        if self.task == P.TASK_RACING:
+            gates = env.targets
+            watch.append(gates)
+            g = gates.detach().cpu()
+            if not 1 <= g.shape[0] <= 4:
+                ok = False
+            else:
+                s.n_gates = g.shape[0]
+                for a in range(g.shape[0]):
+                    for j in range(3):
+                        s.gates[a][j] = float(g[a, j])
+        else:
+            tgt = env.target
+            watch.append(tgt)
+            if bool((tgt != tgt[0]).any()):                 # per-agent targets: tensor-op path
+                ok = False
+            row = tgt[0].tolist()
+            for j in range(3):
+                s.target[j] = float(row[j])
+        table = envs._reset_table
         if table is not None:
             s.gen_kind, s.gen_boxes, self.table = P.GEN_TABLE, 1, table
-            return True
-        self.table = None
-        return generator_spec(env.envs.stateGenerator, s)
+        else:
+            self.table = None
+            ok = generator_spec(envs.stateGenerator, s, watch) and ok
+        self._watch = tuple(watch)
+        return ok
 
     # -- switching between the two paths ----------------------------------------------------------------
     def enter(self):
         env, dyn = self.env, self.env.envs.dynamics
-        self.sc = env._step_count.to(th.int32).clone()
-        self.ret = env._rewards.detach().to(th.float32).clone()
-        self.eb = env.envs._once_collided.to(th.uint8) * P.EBIT_ONCE_COLLIDED \
-            + env._episode_done.to(th.uint8) * P.EBIT_EPISODE_DONE
-        if self.task == P.TASK_RACING:
-            self.gate = env._next_target_i.to(th.int32).clone()
-            self.passed = env._past_targets_num.to(th.int32).clone()
+        racing = self.task == P.TASK_RACING
+        sc = env._step_count.to(th.int32)
+        if dyn._t_custom:                                   # times given at reset (t=..., random_reset_time)
+            self.t_off = (dyn.t - sc * dyn.ctrl_dt).to(th.float32)
+        else:
+            self.t_off = None
+        self.status = _lib.pack_status(
+            sc, env._rewards, env.envs._once_collided.to(th.int32) * P.EBIT_ONCE_COLLIDED
+            + env._episode_done.to(th.int32) * P.EBIT_EPISODE_DONE,
+            env._next_target_i if racing else None, env._past_targets_num if racing else None)
+        self.record = None
         env.envs._fused = self
-        for t, dt in ((self.sc, th.int32), (self.ret, th.float32), (self.eb, th.uint8)):
-            assert t.is_cuda and t.is_contiguous() and t.dtype == dt
+        dyn._t_provider = self.t_now
         self._stepper = None
         self.active = True
 
@@ -239,56 +307,69 @@ class FusedEnvStep:
         if not self.active:
             return
         env, dyn = self.env, self.env.envs.dynamics
-        env._step_count = self.sc.clone()
-        env._rewards = self.ret.clone()
-        env._episode_done = (self.eb & P.EBIT_EPISODE_DONE).bool()
-        env.envs._once_collided = (self.eb & P.EBIT_ONCE_COLLIDED).bool()
+        sc, ret, eb = self.sc.clone(), self.ret.clone(), self.eb
+        t_now = self.t_now()
+        self.active = False                     # from here on env._step_count / _rewards are plain attributes again
+        env._step_count = sc
+        env._rewards = ret
+        env._episode_done = (eb & P.EBIT_EPISODE_DONE).bool()
+        if self.record is not None:
+            env._success = (self.record[:, 2].to(th.int32) & P.RBIT_SUCCESS) != 0
         if self.task == P.TASK_RACING:
             env._next_target_i = self.gate.to(th.int64)
             env._past_targets_num = self.passed.to(th.int64)
         # FIFO rows the kernel treated as zero (agent younger than the entry) become real zeros again
         d = len(dyn._pre_action)
-        dyn._pre_action = [th.where((self.sc < d - j).view(-1, 1), 0.0, a) for j, a in enumerate(dyn._pre_action)]
-        dyn._fifo_versions = [None] * len(dyn._pre_action)
-        dyn._t_base = self.sc * dyn.ctrl_dt - dyn._n_steps * dyn.ctrl_dt
-        dyn._t_steps = None
+        dyn._pre_action = [th.where((sc < d - j).view(-1, 1), 0.0, a) for j, a in enumerate(dyn._pre_action)]
+        dyn._t_base = t_now - dyn._n_steps * dyn.ctrl_dt
+        dyn._t_provider = None
         env.envs.update_observation()
         env.envs.update_collision()
-        env.envs._once_collided = (self.eb & P.EBIT_ONCE_COLLIDED).bool()
+        env.envs._once_collided = (eb & P.EBIT_ONCE_COLLIDED).bool()
         env.envs._fused = None
-        self.active = False
 
     # -- the step -------------------------------------------------------------------------------------------
-    def _launch(self, state_in: th.Tensor, action: th.Tensor, want_saved: bool, mirror=None):
-        """Allocate the step's outputs and launch ``vf_env_step_fwd`` (status buffers are updated in place).
+    def _launch(self, state_in: th.Tensor, action: th.Tensor, status_in: th.Tensor, mirror=None, wind=None, push=None):
+        """Allocate the step's outputs and launch ``vf_env_step_fwd``.
         ``mirror``: address of a ``VfEnvMirror`` (page-locked host destinations for obs / reward / done), or None."""
         # hot call: one Python->C++ transition allocates the outputs (torch caching allocator) and launches through
         # the C-ABI on the current stream of the state's device (csrc/vf_torch.cpp, EnvStepper)
-        out = (self._stepper or self._make_stepper()).step(state_in, action, self.global_step, 0,
-                                                           self.env.keep_terminal_observation, want_saved, mirror or 0)
+        out = (self._stepper or self._make_stepper()).step(state_in, action, status_in, self.global_step, 0,
+                                                           self.env.keep_terminal_observation, mirror or 0, wind, push)
         self.global_step += 1
         return out
 
     def host_slot(self):
-        """Page-locked host destinations of obs / reward / done for the numpy output mode: two alternating sets (the
-        arrays handed out by the previous step stay valid for one more step), each with its ``VfEnvMirror``."""
+        """Page-locked host destinations of obs / reward / done for the numpy output mode: a ring of
+        ``env.host_ring_depth`` sets (arrays handed out by a step stay valid for ``depth - 1`` further steps), each
+        with its ``VfEnvMirror`` and completion word."""
         ring = getattr(self, "_host_ring", None)
         if ring is None:
+            depth = max(2, int(getattr(self.env, "host_ring_depth", 4)))
             ring = []
-            for _ in range(2):
+            self._counter = th.zeros((1,), dtype=th.int32, device=self.device)
+            for _ in range(depth):
                 obs = th.empty((self.n, self.obs_width), dtype=th.float32, pin_memory=True)
                 reward = th.empty((self.n,), dtype=th.float32, pin_memory=True)
                 done = th.empty((self.n,), dtype=th.int32, pin_memory=True)
-                m = P.VfEnvMirror(obs.data_ptr(), reward.data_ptr(), done.data_ptr())
-                ring.append({"obs": obs, "reward": reward, "done": done, "mirror": m, "ref": ctypes.addressof(m),
-                             "np": (obs.numpy(), reward.numpy(), done.numpy())})
-            self._host_ring, self._host_turn = ring, 0
-        self._host_turn ^= 1
-        return ring[self._host_turn]
+                flag = th.zeros((16,), dtype=th.int32, pin_memory=True)       # one cache line of its own
+                m = P.VfEnvMirror(obs.data_ptr(), reward.data_ptr(), done.data_ptr(), flag.data_ptr(),
+                                  self._counter.data_ptr(), 0)
+                ring.append({"obs": obs, "reward": reward, "done": done, "flag": flag, "mirror": m,
+                             "ref": ctypes.addressof(m), "np": (obs.numpy(), reward.numpy(), done.numpy())})
+            self._host_ring, self._host_turn, self._flag_seq = ring, 0, 0
+        self._host_turn = (self._host_turn + 1) % len(ring)
+        slot = ring[self._host_turn]
+        self._flag_seq = (self._flag_seq % 0x7FFFFFF0) + 1
+        slot["mirror"].flag_value = self._flag_seq
+        slot["expect"] = self._flag_seq
+        return slot
 
-    def step(self, action, grad: bool = False, mirror=None, late_action=None):
+    def step(self, action, owned: bool = True, grad: bool = False, mirror=None, late_action=None):
         """One env step = one launch.  ``grad=True`` routes through ``EnvControlStep`` so that the returned state,
         observation and reward carry autograd history (backward = one launch of ``vf_env_step_bwd``).
+        ``owned``: the action tensor is a private device copy (it came through a host->device conversion) and may
+        wait in the comm-delay FIFO as it is; otherwise the launch clones it (``fifo_push`` -> ``fifo_copy``).
         ``late_action`` (numpy mode with a comm-delay FIFO): a callable that stages this step's host action; it is
         called AFTER the launch — the kernel consumes an older FIFO entry, so the staging overlaps with it."""
         env, dyn = self.env, self.env.envs.dynamics
@@ -296,57 +377,86 @@ class FusedEnvStep:
             self._bind()
         if not self.active:
             self.enter()
+        push = None
         if late_action is not None:
-            action = dyn._fifo_pop()
+            action = dyn._pre_action.pop(0)
         elif dyn._comm_delay_steps:
-            dyn._fifo_push(action)
-            action = dyn._fifo_pop()
-        if not action.is_contiguous():
+            if not action.is_contiguous():
+                action, owned = action.contiguous(), True
+            if owned:
+                dyn._pre_action.append(action)
+            else:
+                push = action
+            action = dyn._pre_action.pop(0)
+        elif not action.is_contiguous():
             action = action.contiguous()
-        state_in = dyn._state
+        if dyn._wind_fn is not None:
+            dyn.update_wind()                         # reference dynamics.py:320, from the per-agent time t
+        wind = dyn._wind_rows
+        state_in, status_in = dyn._state, self.status
         if grad:
-            state_out, obs, reward, done, record, term = EnvControlStep.apply(state_in, action, self)
+            state_out, status, obs, reward, done, record, term, copy = EnvControlStep.apply(
+                state_in, action, push, status_in, wind, self)
         else:
-            state_out, obs, reward, done, record, term, _ = self._launch(state_in, action, False, mirror)
+            state_out, status, obs, reward, done, record, term, copy = self._launch(
+                state_in, action, status_in, mirror, wind, push)
+        if push is not None:
+            dyn._pre_action.append(copy)
         if late_action is not None:
-            dyn._fifo_push(late_action())
-        # keep the Dynamics object coherent (lazy views, diagnostics)
-        dyn._prev = (state_in.detach(), action.detach()) if grad else (state_in, action)
+            dyn._pre_action.append(late_action())
+        self.status, self.record = status, record
+        if self.t_off is not None:
+            self.t_off = th.where(done, 0.0, self.t_off)
+        # keep the Dynamics object coherent (lazy views, diagnostics).  The diagnostics re-run the step on its inputs:
+        # agents younger than the FIFO flew a zero action (the kernel masks by age), so the saved action says so too
+        dyn._prev = (state_in.detach(), _MaskedAction(action.detach(), status_in, self.spec.fifo_depth), None)
         dyn._state = state_out
         dyn._obs_t = obs if self.obs_kind == P.OBS_STATE13 else None
         dyn._n_steps += 1
         dyn._ext, dyn._thrusts_given = None, None
         dyn._fresh = done
-        dyn._t_steps = self.sc
         env.envs._collision_stale = True
-        env._step_count, env._rewards, env._reward, env._done = self.sc, self.ret, reward, done
-        if self.gate is not None:
-            env._next_target_i, env._past_targets_num = self.gate, self.passed
+        env._reward, env._done = reward, done
         return obs, reward, done, record, term
 
 
+class _MaskedAction:
+    """The action a fused step really consumed, materialised only if the lazy diagnostics ask for it: the delayed
+    action with the rows of agents younger than the FIFO zeroed (what the kernel does by age)."""
+
+    __slots__ = ("action", "status", "depth")
+
+    def __init__(self, action, status, depth):
+        self.action, self.status, self.depth = action, status, depth
+
+    def resolve(self) -> th.Tensor:
+        if self.depth == 0:
+            return self.action
+        return th.where((self.status[:, 0] < self.depth).view(-1, 1), 0.0, self.action)
+
+
 class EnvControlStep(th.autograd.Function):
-    """``(state, action) -> (state', obs, reward | done, record, terminal obs)`` — the fused env step with its
-    hand-derived adjoint; saves nothing but the step's inputs and 8 bytes per agent of start-of-step status."""
+    """``(state, action, push) -> (state', status', obs, reward, done, record, terminal obs, fifo copy)`` — the fused
+    env step with its hand-derived adjoint; saves nothing but the step's inputs (the start-of-step status record is
+    one of them: the forward writes the new record elsewhere)."""
 
     @staticmethod
-    def forward(ctx, state: th.Tensor, action: th.Tensor, fz: FusedEnvStep):
-        state_out, obs, reward, done, record, term, saved = fz._launch(state, action, True)
-        ctx.fz = fz
-        ctx.save_for_backward(state, action, saved)
+    def forward(ctx, state: th.Tensor, action: th.Tensor, push, status_in: th.Tensor, wind, fz: FusedEnvStep):
+        state_out, status, obs, reward, done, record, term, copy = fz._launch(state, action, status_in, None, wind, push)
+        ctx.fz, ctx.wind = fz, wind
+        ctx.save_for_backward(state, action, status_in)
         ctx.set_materialize_grads(False)
-        outs = (state_out, obs, reward, done, record) + (() if term is None else (term,))
-        ctx.mark_non_differentiable(done, record, *(() if term is None else (term,)))
-        return outs if term is not None else outs + (None,)
+        ctx.mark_non_differentiable(status, done, record, *(() if term is None else (term,)))
+        return state_out, status, obs, reward, done, record, term, copy
 
     @staticmethod
     @th.autograd.function.once_differentiable
-    def backward(ctx, g_state_out, g_obs, g_reward, *_):
-        state, action, saved = ctx.saved_tensors
+    def backward(ctx, g_state_out, _g_status, g_obs, g_reward, _g_done, _g_record, _g_term, g_copy):
+        state, action, status_in = ctx.saved_tensors
         fz = ctx.fz
         cfg = fz.env.envs.dynamics._cfg
         g_state, g_action = th.empty_like(state), th.empty_like(action)
         c = lambda t: None if t is None else t.contiguous()
         _lib.env_step_bwd(cfg.params, fz.spec, cfg.substeps, cfg.integrator, cfg.action_type, cfg.flags, 0,
-                          state, action, saved, c(g_state_out), c(g_obs), c(g_reward), g_state, g_action)
-        return g_state, g_action, None
+                          state, action, status_in, c(g_state_out), c(g_obs), c(g_reward), g_state, g_action, ctx.wind)
+        return g_state, g_action, g_copy, None, None, None

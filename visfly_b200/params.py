@@ -269,11 +269,14 @@ class VfEnvSpec(ctypes.Structure):
         ("gen_boxes", ctypes.c_int),
         ("gen_mean", ((ctypes.c_float * 3) * 4) * GEN_MAX_BOXES),
         ("gen_half", ((ctypes.c_float * 3) * 4) * GEN_MAX_BOXES),
+        ("gen_heading", ctypes.c_int * GEN_MAX_BOXES),
         ("init_motor_omega", ctypes.c_float),
         ("seed", ctypes.c_ulonglong),
     ]
 
 
 class VfEnvMirror(ctypes.Structure):
-    """ctypes mirror of ``struct VfEnvMirror``: page-locked host destinations of obs / reward / done (numpy mode)."""
-    _fields_ = [("obs", ctypes.c_void_p), ("reward", ctypes.c_void_p), ("done", ctypes.c_void_p)]
+    """ctypes mirror of ``struct VfEnvMirror``: page-locked host destinations of obs / reward / done (numpy mode) and
+    the completion word the last thread block raises (``flag`` page-locked host, ``counter`` device, zeroed)."""
+    _fields_ = [("obs", ctypes.c_void_p), ("reward", ctypes.c_void_p), ("done", ctypes.c_void_p),
+                ("flag", ctypes.c_void_p), ("counter", ctypes.c_void_p), ("flag_value", ctypes.c_uint)]

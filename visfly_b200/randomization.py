@@ -29,7 +29,9 @@ def euler_zyx_to_quat(e: th.Tensor) -> th.Tensor:
 
 
 class StateRandomizer:
-    def __init__(self, device="cuda", is_collision_func=None, scene_id=None, seed: int = 42, **_):
+    def __init__(self, device="cuda", is_collision_func=None, scene_id=None, seed: int = 42, **unknown):
+        if unknown:             # a typo in a generator kwarg must not silently change the start distribution
+            raise TypeError(f"{type(self).__name__}: unknown keyword argument(s) {sorted(unknown)}")
         self.device = th.device(device)
         self.is_collision_func, self.scene_id = is_collision_func, scene_id
 
@@ -57,8 +59,17 @@ class StateRandomizer:
 
 class UniformStateRandomizer(StateRandomizer):
     def __init__(self, position=_ZERO3, orientation=_ZERO3, velocity=_ZERO3, angular_velocity=_ZERO3,
-                 heading=False, **kw):
+                 heading=False, test: bool = False, xyz_num=(1, 1, 1), xyz_half=(0, 2, 0.), **kw):
         super().__init__(**kw)
+        #: reference :141-151 — evaluation mode: start positions walk over a regular grid of the position box
+        #: (``xyz_num`` points per axis, `indexing="ij"`), one grid point per generated agent, plus U(-1,1)*xyz_half
+        self.test = bool(test)
+        if self.test:
+            axes = [th.linspace(-1, 1, int(k)) for k in xyz_num]
+            gx, gy, gz = th.meshgrid(*axes, indexing="ij")
+            self._grid = th.stack([gx.flatten(), gy.flatten(), gz.flatten()], dim=1)
+            self._grid_index = 0
+            self._xyz_half = th.atleast_2d(th.tensor(list(xyz_half), dtype=th.float32))
         # one (4,3) mean and half-width table: a single rand call covers all four fields
         fields = (position, orientation, velocity, angular_velocity)
         self._mean = th.tensor([list(f["mean"]) for f in fields], dtype=th.float32)
@@ -74,15 +85,25 @@ class UniformStateRandomizer(StateRandomizer):
     def to(self, device):
         super().to(device)
         self._mean, self._half = self._mean.to(device), self._half.to(device)
+        if self.test:
+            self._grid, self._xyz_half = self._grid.to(device), self._xyz_half.to(device)
         return self
 
     def _generate(self, num, **kw):
         if self._mean.device != self.device:
             self.to(self.device)
-        if self._deterministic:
+        if self._deterministic and not self.test:
             s = self._mean.unsqueeze(0).expand(num, 4, 3)
         else:
             s = (2 * th.rand((num, 4, 3), device=self.device) - 1) * self._half + self._mean     # :153-169
+        if self.test:
+            # the reference generates agent by agent and advances the grid index once per call (:156-160): agent k of
+            # this batch gets grid point (index + k) mod len(grid)
+            k = (self._grid_index + th.arange(num, device=self.device)) % self._grid.shape[0]
+            self._grid_index += num
+            pos = self._grid[k] * self._half[0] + self._mean[0] + \
+                (2 * th.rand((num, 3), device=self.device) - 1) * self._xyz_half
+            s = th.cat([pos.unsqueeze(1), s[:, 1:]], dim=1)
         if self.heading:
             d = self._mean[0] - s[:, 0]                                   # direction = -half  (:163)
             yaw = th.arccos(d[:, 0] / d[:, :2].norm(dim=1)) * th.where(d[:, 1].sign() >= 0, 1, -1)   # :27-28
