@@ -375,15 +375,19 @@ def racing_leg(n_weak, dev, rank, world, K, W, stream, barrier):
     """BASELINE configs[4]: RacingEnv semantics (gates, radius 0.3, hover-style reward + 20 per gate, 16-wide
     observation; reference envs/RacingEnv.py:87-98,142-148,203-215,250-267), RK4 x8, agents sharded over the GPUs:
     weak scaling (65 536 agents per GPU) and strong scaling (524 288 agents in total, rank r owns shard_range(r))."""
-    from visfly_b200.distributed import EpisodeReturnsGather, shard_range, shard_seed
+    from visfly_b200.distributed import EpisodeReturnsGather, shard_range
     from visfly_b200.envs import RacingEnv2
     out = {"workload": "RacingEnv2 visual=False RK4 dt=0.0025 ctrl_dt=0.02 bodyrate (BASELINE configs[4])"}
     total_strong = 524288
     lo, hi = shard_range(total_strong, rank, world)
-    for name, n, n_total in (("weak", n_weak, n_weak * world), ("strong", hi - lo, total_strong)):
+    for name, n, n_total, first in (("weak", n_weak, n_weak * world, rank * n_weak),
+                                    ("strong", hi - lo, total_strong, lo)):
         replicas = max(2, -(-16 * 65536 // n))          # keep >= ~280 MB of per-step traffic in rotation (> L2)
+        # every rank uses the SAME seed and declares its shard: placements and in-kernel restarts are the rows the
+        # whole n_total-agent batch would draw (tests/test_gpu_multirank.py), whatever the number of GPUs
         envs = [RacingEnv2(num_agent_per_scene=n, visual=False, device=dev, dynamics_kwargs=dict(DYN),
-                           seed=shard_seed(42 + 1000 * j, rank), max_episode_steps=256, tensor_output=True)
+                           seed=42 + 1000 * j, max_episode_steps=256, tensor_output=True,
+                           shard=None if world == 1 else (first, n_total))
                 for j in range(replicas)]
         for e in envs:
             e.reset()

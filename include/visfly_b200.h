@@ -256,6 +256,8 @@ typedef struct VfEnvSpec {
                                               /* centre of the position box, randomization.py:27-29,162-165       */
     float init_motor_omega;   /* hover rotor speed after reset, dynamics.py:86                                    */
     unsigned long long seed;  /* Philox key of the reset sampler                                                  */
+    unsigned agent_offset;    /* global index of this batch's agent 0: the sampler is keyed by (seed, agent_offset + i, */
+                              /* step), so a shard of a larger batch draws exactly the restarts the whole batch would  */
 } VfEnvSpec;
 
 int vf_env_spec_size(void);
@@ -298,6 +300,8 @@ int vf_wait_flag(const volatile unsigned* flag, unsigned value, long long timeou
  *   reward_out  float[n], done_out uint8[n]
  *   record_out  float[n][4]   [episode return, episode length, VF_RBIT_* as float, gates passed] of this step
  *   term_obs_out float[n][13|16] or NULL: observation BEFORE the reset, written only for finished agents
+ *   gate_out    int64[n] or NULL: next gate index after the step (racing) as the tensor the observation dict carries
+ *                 (reference RacingEnv.py:267 `"gate": self._next_target_i`), so that no per-step unpacking is needed
  *   host_mirror NULL, or page-locked host destinations written in addition to obs_out / reward_out / done_out
  */
 int vf_env_step_fwd(const VfParams* params, const VfEnvSpec* spec, int n, int substeps, int integrator,
@@ -306,7 +310,7 @@ int vf_env_step_fwd(const VfParams* params, const VfEnvSpec* spec, int n, int su
                     const float* state_in, const float* action, const float* wind, const float* fifo_push,
                     const float* reset_table, const int* status_in,
                     float* state_out, int* status_out, float* fifo_copy, float* obs_out, float* reward_out,
-                    unsigned char* done_out, float* record_out, float* term_obs_out,
+                    unsigned char* done_out, float* record_out, float* term_obs_out, long long* gate_out,
                     const VfEnvMirror* host_mirror, void* stream);
 
 /*

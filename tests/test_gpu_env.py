@@ -286,9 +286,61 @@ def test_numpy_mode_host_mirror_equals_tensor_mode(task):
         for i in np.nonzero(d2)[0]:
             assert float(i1[int(i)]["episode"]["r"]) == float(i2[int(i)]["episode"]["r"])
         held.append((o2["state"], o2["state"].copy()))
-        if len(held) >= 2:                                # arrays handed out one step ago are still intact
-            view, snap = held[-2]
+        if len(held) >= 3:                                # arrays handed out two steps ago are still intact
+            view, snap = held[-3]
             assert np.array_equal(view, snap)
+        # the env objects show the step that was handed out, although the numpy env runs one step ahead inside
+        assert th.equal(dev_env.state, np_env.state) and th.equal(dev_env._step_count, np_env._step_count)
+        assert th.equal(dev_env._rewards, np_env._rewards)
+
+
+@pytest.mark.parametrize("depth", [1, 3])
+def test_host_mode_runs_ahead_and_rewinds_when_the_env_is_touched(depth):
+    """numpy mode with a comm-delay FIFO launches step t+1 before it hands out step t (FusedEnvStep.step_host).
+    Anything else done to the env in between (index-based reset, hand-over to the generic path, deep copy, switching
+    to tensor output) must see the env exactly as after the step that was handed out: compared with a tensor-mode twin
+    that steps synchronously and gets the same treatment."""
+    z = load_env_golden("navigation", "rk4")
+    acts = np.concatenate([z["actions"], z["actions"][::-1]])
+    T, n = acts.shape[:2]
+    dyn = dict(DYN["rk4"], comm_delay=0.02 * depth)
+
+    def build(tensor_output):
+        from visfly_b200.envs import NavigationEnv
+        env = NavigationEnv(num_agent_per_scene=n, visual=False, device="cuda", dynamics_kwargs=dict(dyn),
+                            max_episode_steps=9, tensor_output=tensor_output)
+        env.envs.set_reset_table(*[x.cuda() for x in table_of(z)])
+        env.reset()
+        return env
+
+    a_env, b_env = build(True), build(False)
+    twins = None
+    for t in range(T):
+        o1, r1, d1, _ = a_env.step(th.from_numpy(acts[t]).cuda())
+        o2, r2, d2, _ = b_env.step(acts[t].copy())
+        if b_env.tensor_output:
+            o2, r2, d2 = {k: v.cpu().numpy() for k, v in o2.items()}, r2.cpu().numpy(), d2.cpu().numpy()
+        assert np.array_equal(o1["state"].cpu().numpy(), o2["state"]), t
+        assert np.array_equal(r1.cpu().numpy(), r2) and np.array_equal(d1.cpu().numpy().astype(np.int32), d2.astype(np.int32))
+        if not b_env.tensor_output and b_env.use_fused_step:
+            assert len(b_env._fused._ahead) == 1              # one step in flight between calls
+        if t == 5:                                            # index-based reset of a few agents
+            for e in (a_env, b_env):
+                e.reset_agent_by_id([1, 4, 7])
+            assert th.equal(a_env.state, b_env.state)
+        if t == 11:                                           # a few steps on the generic tensor-op path
+            a_env.use_fused_step = b_env.use_fused_step = False
+        if t == 15:
+            a_env.use_fused_step = b_env.use_fused_step = True
+        if t == 20:                                           # deep copies continue identically
+            twins = (copy.deepcopy(a_env), copy.deepcopy(b_env))
+        if t == 30:                                           # switch the host env to tensor output mid-run
+            b_env.tensor_output = True
+    assert twins is not None
+    for t in range(21, 26):
+        o1 = twins[0].step(th.from_numpy(acts[t]).cuda())[0]["state"]
+        o2 = twins[1].step(acts[t].copy())[0]["state"]
+        assert np.array_equal(o1.cpu().numpy(), o2)
 
 
 def test_numpy_mode_host_mirror_ragged_batch():

@@ -42,7 +42,7 @@ SIGNATURES = {
     "vf_wait_flag": (_i, [_vp, _u, ctypes.c_longlong]),
     "vf_env_step_fwd": (_i, [_P(VfParams), _P(VfEnvSpec), _i, _i, _i, _i, _u, _u, ctypes.c_ulonglong, _vp,
                              _vp, _vp, _vp, _vp, _vp, _vp,
-                             _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                             _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                              _P(VfEnvMirror), _vp]),
     "vf_env_step_bwd": (_i, [_P(VfParams), _P(VfEnvSpec), _i, _i, _i, _i, _u, _u,
                              _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
@@ -229,7 +229,8 @@ def env_step_fwd(params: VfParams, spec: VfEnvSpec, substeps: int, integrator: i
                  obs_out: th.Tensor, reward_out: th.Tensor, done_out: th.Tensor, record_out: th.Tensor,
                  term_obs_out: Optional[th.Tensor], host_mirror: Optional[VfEnvMirror] = None,
                  wind: Optional[th.Tensor] = None, fifo_push: Optional[th.Tensor] = None,
-                 fifo_copy: Optional[th.Tensor] = None, step_base: Optional[th.Tensor] = None) -> None:
+                 fifo_copy: Optional[th.Tensor] = None, step_base: Optional[th.Tensor] = None,
+                 gate_out: Optional[th.Tensor] = None) -> None:
     """Binding of ``vf_env_step_fwd`` (fused control step + env wrapper tail, one launch)."""
     lib = load(require_cuda=True)
     n = state_in.shape[1]
@@ -243,7 +244,7 @@ def env_step_fwd(params: VfParams, spec: VfEnvSpec, substeps: int, integrator: i
             _dev_ptr(state_out, "state_out"), _any_ptr(status_out, "status_out", th.int32),
             _dev_ptr(fifo_copy, "fifo_copy"), _dev_ptr(obs_out, "obs_out"), _dev_ptr(reward_out, "reward_out"),
             _any_ptr(done_out, "done_out", th.bool), _dev_ptr(record_out, "record_out"),
-            _dev_ptr(term_obs_out, "term_obs_out"),
+            _dev_ptr(term_obs_out, "term_obs_out"), _any_ptr(gate_out, "gate_out", th.int64),
             None if host_mirror is None else ctypes.byref(host_mirror), _stream(state_in.device)))
 
 

@@ -249,7 +249,8 @@ vf_env_step_fwd_kernel(const __grid_constant__ VfParams params, const __grid_con
                        float* __restrict__ state_out, int* __restrict__ status_out, float* __restrict__ fifo_copy,
                        float* __restrict__ obs_out, float* __restrict__ reward_out,
                        unsigned char* __restrict__ done_out, float* __restrict__ record_out,
-                       float* __restrict__ term_obs_out, const VfEnvMirror mirror) {
+                       float* __restrict__ term_obs_out, long long* __restrict__ gate_out,
+                       const VfEnvMirror mirror) {
     __shared__ __align__(16) float s_obs[(BLOCK / 32) * kWarpObs];
     const vf::Params<float>& P = reinterpret_cast<const vf::Params<float>&>(params);
     const int i = blockIdx.x * BLOCK + threadIdx.x;
@@ -329,7 +330,7 @@ vf_env_step_fwd_kernel(const __grid_constant__ VfParams params, const __grid_con
                 passed = 0;
             }
             const unsigned long long step = step_index + (step_base ? *step_base : 0ull);
-            vf::sample_reset(E, unsigned(i), step, reset_table ? reset_table + size_t(i) * 13 : nullptr,
+            vf::sample_reset(E, E.agent_offset + unsigned(i), step, reset_table ? reset_table + size_t(i) * 13 : nullptr,
                              s.p, s.q, s.v, s.w);
             for (int j = 0; j < 4; ++j) s.mot[j] = E.init_motor_omega;
             s.al[0] = s.al[1] = s.al[2] = 0.f;
@@ -339,6 +340,7 @@ vf_env_step_fwd_kernel(const __grid_constant__ VfParams params, const __grid_con
         store_state(state_out, n, i, s);
         const int ebo = int((ep_done ? VF_EBIT_EPISODE_DONE : 0u) | (once ? VF_EBIT_ONCE_COLLIDED : 0u));
         reinterpret_cast<int4*>(status_out)[i] = make_int4(sc, __float_as_int(ret), ebo | (g << 8), passed);
+        if (gate_out) gate_out[i] = g;
 
         if (E.obs_kind == VF_OBS_RACING16) {
             float o[16];
@@ -644,11 +646,11 @@ void launch_env_fwd(const VfParams& p, const VfEnvSpec& e, int n, int substeps, 
                     unsigned long long step_index, const unsigned long long* step_base, const float* si,
                     const float* a, const float* wind, const float* push, const float* table, const int* status_in,
                     float* so, int* status_out, float* copy, float* obs, float* rew, unsigned char* done, float* rec,
-                    float* tobs, const VfEnvMirror& mirror, cudaStream_t st) {
+                    float* tobs, long long* gate_out, const VfEnvMirror& mirror, cudaStream_t st) {
     const int grid = (n + kBlock - 1) / kBlock;
     launch_pdl(vf_env_step_fwd_kernel<INTEG, ACT, LAG, kBlock>, grid, kBlock, st, p, e, n, substeps, env_flags,
                step_index, step_base, si, a, wind, push, table, status_in, so, status_out, copy, obs, rew, done, rec,
-               tobs, mirror);
+               tobs, gate_out, mirror);
 }
 
 template <int INTEG, int ACT, bool LAG>
@@ -818,7 +820,7 @@ int vf_env_step_fwd(const VfParams* params, const VfEnvSpec* spec, int n, int su
                     const float* state_in, const float* action, const float* wind, const float* fifo_push,
                     const float* reset_table, const int* status_in,
                     float* state_out, int* status_out, float* fifo_copy, float* obs_out, float* reward_out,
-                    unsigned char* done_out, float* record_out, float* term_obs_out,
+                    unsigned char* done_out, float* record_out, float* term_obs_out, long long* gate_out,
                     const VfEnvMirror* host_mirror, void* stream) {
     if (check_common(params, n, substeps, integrator, action_type)) return 1;
     if (check_spec(spec)) return 1;
@@ -874,7 +876,7 @@ int vf_env_step_fwd(const VfParams* params, const VfEnvSpec* spec, int n, int su
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     VF_DISPATCH_FWD(launch_env_fwd, *params, *spec, n, substeps, env_flags, step_index, step_base, state_in, action,
                     wind, fifo_push, reset_table, status_in, state_out, status_out, fifo_copy, obs_out, reward_out,
-                    done_out, record_out, term_obs_out, mirror, st);
+                    done_out, record_out, term_obs_out, gate_out, mirror, st);
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return fail("vf_env_step_fwd launch failed", err);
     return 0;

@@ -102,13 +102,15 @@ class EnvStepper {
         o_rew_ = o_obs_ + pad(4 * obs_width_ * n_);
         o_rec_ = o_rew_ + pad(4 * n_);
         o_done_ = o_rec_ + pad(16 * n_);
-        o_copy_ = o_done_ + pad(n_);
+        o_gate_ = o_done_ + pad(n_);
+        racing_ = spec_->task == VF_TASK_RACING;
+        o_copy_ = o_gate_ + (racing_ ? pad(8 * n_) : 0);     // racing: the gate index as the obs dict carries it
         sz_copy_ = pad(16 * n_);
         sz_term_ = pad(4 * obs_width_ * n_);
     }
 
-    // returns (state', status', obs, reward, done, record, terminal obs | None, fifo copy | None)
-    std::tuple<at::Tensor, at::Tensor, at::Tensor, at::Tensor, at::Tensor, at::Tensor, OptTensor, OptTensor>
+    // returns (state', status', obs, reward, done, record, terminal obs | None, fifo copy | None, gate | None)
+    std::tuple<at::Tensor, at::Tensor, at::Tensor, at::Tensor, at::Tensor, at::Tensor, OptTensor, OptTensor, OptTensor>
     step(const at::Tensor& state_in, const at::Tensor& action, const at::Tensor& status_in, int64_t step_index,
          int64_t env_flags, bool want_term, int64_t host_mirror, const OptTensor& wind, const OptTensor& push) {
         check_f32_cuda(state_in, "state_in");
@@ -136,7 +138,8 @@ class EnvStepper {
         at::Tensor reward = carve(slab, o_rew_, at::kFloat, {n_});
         at::Tensor record = carve(slab, o_rec_, at::kFloat, {n_, 4});
         at::Tensor done = carve(slab, o_done_, at::kBool, {n_});
-        OptTensor term, copy;
+        OptTensor term, copy, gate;
+        if (racing_) gate = obs_width_ == 16 ? carve(slab, o_gate_, at::kLong, {n_, 1}) : carve(slab, o_gate_, at::kLong, {n_});
         if (push.has_value()) copy = carve(slab, o_copy_, at::kFloat, {n_, 4});
         if (want_term) term = carve(slab, o_term, at::kFloat, {n_, obs_width_});
         const int rc = vf_env_step_fwd(
@@ -148,10 +151,11 @@ class EnvStepper {
             status_in.data_ptr<int>(), state_out.data_ptr<float>(), status.data_ptr<int>(),
             static_cast<float*>(ptr(copy)), obs.data_ptr<float>(), reward.data_ptr<float>(),
             reinterpret_cast<unsigned char*>(done.data_ptr<bool>()), record.data_ptr<float>(),
-            static_cast<float*>(ptr(term)), reinterpret_cast<const VfEnvMirror*>(host_mirror),
+            static_cast<float*>(ptr(term)), reinterpret_cast<long long*>(ptr(gate)),
+            reinterpret_cast<const VfEnvMirror*>(host_mirror),
             c10::cuda::getCurrentCUDAStream(state_in.device().index()).stream());
         TORCH_CHECK(rc == 0, "visfly_b200: ", vf_last_error());
-        return {state_out, status, obs, reward, done, record, term, copy};
+        return {state_out, status, obs, reward, done, record, term, copy, gate};
     }
 
   private:
@@ -161,7 +165,8 @@ class EnvStepper {
     unsigned flags_;
     int64_t n_, obs_width_;
     OptTensor reset_table_, step_base_;
-    int64_t o_status_ = 0, o_obs_ = 0, o_rew_ = 0, o_rec_ = 0, o_done_ = 0, o_copy_ = 0, sz_copy_ = 0, sz_term_ = 0;
+    bool racing_ = false;
+    int64_t o_status_ = 0, o_obs_ = 0, o_rew_ = 0, o_rec_ = 0, o_done_ = 0, o_gate_ = 0, o_copy_ = 0, sz_copy_ = 0, sz_term_ = 0;
 };
 
 // Spin on the kernel's completion word (VfEnvMirror.flag) with the GIL released.

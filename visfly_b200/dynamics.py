@@ -355,14 +355,14 @@ class Dynamics:
         wind = self._wind_rows
         if th.is_grad_enabled() and (state.requires_grad or action.requires_grad or
                                      (push is not None and push.requires_grad)):
-            self._prev = (state.detach(), action.detach(), None)
+            self._prev = (state.detach(), action.detach(), None, None)
             self._state, self._obs, copy = ControlStep.apply(state, action, push, cfg, wind)
         else:
             # nothing to differentiate: straight to the launch (an autograd.Function costs ~8 us of host time per
             # call even when no input requires grad; the kernel takes ~11 us at 65 536 agents)
             # without a FIFO the consumed action is the caller's own tensor: remember its version so that the lazy
             # diagnostics (_extras) can tell if it was overwritten in the meantime
-            self._prev = (state, action, None if (owned or self._comm_delay_steps) else action._version)
+            self._prev = (state, action, None if (owned or self._comm_delay_steps) else action._version, None)
             self._state, self._obs, copy = _lib.fast().step_fwd(cfg.params_addr, cfg.substeps, cfg.integrator,
                                                                 cfg.action_type, cfg.flags, state, action, wind, push)
         if push is not None:
@@ -382,9 +382,10 @@ class Dynamics:
             if self._prev is None:
                 ext[:, 4:] = rest
             else:
-                state_in, action, version = self._prev
-                if hasattr(action, "resolve"):          # fused env step: the action as masked by the kernel
-                    action = action.resolve()
+                state_in, action, version, status = self._prev
+                if status is not None and self._comm_delay_steps:
+                    # fused env step: agents younger than the FIFO flew a zero action (the kernel masks by age)
+                    action = th.where((status[:, 0] < self._comm_delay_steps).view(-1, 1), 0.0, action)
                 if version is not None and action._version != version:
                     raise RuntimeError(
                         "acceleration / thrusts of the last step are produced on demand from the step's inputs, but the "

@@ -103,9 +103,9 @@ class RacingEnv(DroneGymEnvsBase):
             return None
         return FusedEnvStep(self, P.TASK_RACING, self._FUSED_OBS)     # gates / radius: read from the live attributes
 
-    def _fused_obs(self, obs):
-        gate = self._fused.gate.to(th.int64)
-        return TensorDict({"state": obs, "gate": gate.unsqueeze(1) if self._FUSED_OBS else gate})
+    def _fused_obs(self, obs, gate=None):
+        # the kernel writes the gate index in the dtype / shape the observation dict carries ((N,) here, (N,1) for v2)
+        return TensorDict({"state": obs, "gate": self._fused.gate_obs if gate is None else gate})
 
     def get_success(self) -> th.Tensor:
         """Gate passing (reference :142-148); never ends the episode."""

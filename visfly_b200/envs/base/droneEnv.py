@@ -36,6 +36,7 @@ class DroneEnvsBase:
             sensitive_radius: float = 10.,
             multi_drone: bool = False,
             device="cuda",
+            shard=None,
     ):
         if visual:
             raise NotImplementedError(
@@ -44,6 +45,9 @@ class DroneEnvsBase:
         random_kwargs = dict(random_kwargs or {})
         self.device = th.device(device)
         self.seed = seed
+        #: (agent_offset, total_agents) when this env is one contiguous shard of a larger batch spread over several
+        #: GPUs: initial placements and in-kernel restarts are then the rows the whole batch would draw
+        self.shard = None if shard is None else (int(shard[0]), int(shard[1]))
         self.visual = visual
         self.uav_radius = uav_radius
         self.is_multi_drone = multi_drone
@@ -117,6 +121,10 @@ class DroneEnvsBase:
             t = self._reset_table if indices is None else self._reset_table[th.as_tensor(indices, device=self.device)]
             return t[:, 0:3], t[:, 3:7], t[:, 7:10], t[:, 10:13]
         n = self.dynamics.num if indices is None else len(indices)
+        if self.shard is not None and indices is None and num is None:
+            # draw for the whole batch and keep this shard's rows: same seed => same placement as one big env
+            lo, total = self.shard
+            return tuple(x[lo:lo + n] for x in self.stateGenerator.safe_generate(num=total))
         return self.stateGenerator.safe_generate(num=n if num is None else num)
 
     def reset(self, state=None):

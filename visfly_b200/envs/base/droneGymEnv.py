@@ -113,10 +113,12 @@ class DroneGymEnvsBase(VecEnv):
             is_train: bool = False,
             is_collision_reset: bool = True,
             debug_checks: bool = False,
+            shard=None,
     ):
         device = th.device(device)
         self.envs = DroneEnvsBase(
             num_agent_per_scene=num_agent_per_scene, num_scene=num_scene, seed=seed, visual=visual, device=device,
+            shard=shard,
             dynamics_kwargs=dict(dynamics_kwargs or {}), random_kwargs=dict(random_kwargs or {}),
             scene_kwargs=dict(scene_kwargs or {}), sensor_kwargs=sensor_kwargs or [])
         self.device = self.envs.device
@@ -168,12 +170,13 @@ class DroneGymEnvsBase(VecEnv):
         if world is not None or predict:
             raise NotImplementedError("world-model rollouts are not part of the dynamics path")
         fused = self._fused is not None and not is_test and self._fused.refresh()
-        # numpy mode + comm-delay FIFO: this step's kernel consumes an OLDER action, so the host->device copy of the
-        # new one can run on a side stream concurrently with the kernel (joined before step() returns)
-        overlap = fused and not self.tensor_output and not self.debug_checks and self._fused.spec.fifo_depth >= 1 \
+        # numpy mode + comm-delay FIFO: a step consumes an OLDER action, so the engine runs one step ahead of its
+        # caller (FusedEnvStep.step_host) and the host->device copy of the new action rides on a side stream
+        ahead = fused and not self.tensor_output and not self.debug_checks and not self.requires_grad \
+            and self._fused.spec.fifo_depth >= 1 and self.envs.dynamics._wind_fn is None \
             and not (isinstance(_action, th.Tensor) and _action.is_cuda)
-        if overlap:
-            return self._step_fused(host_action=_action)
+        if ahead:
+            return self._step_fused_host(_action)
         self._action = self._stage_action(_action)
         # a device tensor handed in by the caller is still the caller's: the step launch clones it for the FIFO
         self._action_owned = self._action is not _action
@@ -239,7 +242,37 @@ class DroneGymEnvsBase(VecEnv):
             out[k] = hit[1]
         return out
 
-    def _step_fused(self, host_action=None):
+    def _step_fused_host(self, host_action):
+        """numpy in / numpy out through the one-kernel path, one step ahead of the caller (see step_host)."""
+        global _RecordInfo, _wait_flag
+        if _RecordInfo is None:
+            from .fused import RecordInfo as _RecordInfo
+            from ... import _lib
+            _wait_flag = _lib.fast().wait_flag
+        fz = self._fused
+
+        def stage():
+            # with a FIFO of depth 1 the step launched in this call consumes this very action: stage it on the main
+            # stream; deeper FIFOs take the side stream (the copy is joined below, long before it is consumed)
+            self._action = self._stage_action(host_action, side_stream=fz.spec.fifo_depth > 1)
+            return self._action
+        obs, reward, done, record, term, slot = fz.step_host(stage)
+        self._obs_tensors = self._fused_obs(obs)
+        if fz.task != 2:                         # params.TASK_RACING
+            info = _RecordInfo(self.num_agent, record, term, self.envs.dynamics.ctrl_dt, False, self._fused_obs)
+        else:
+            gate = fz.gate_obs
+            info = _RecordInfo(self.num_agent, record, term, self.envs.dynamics.ctrl_dt, True,
+                               lambda t: self._fused_obs(t, gate))
+        self._info = info
+        evt = self.__dict__.pop("_h2d_evt", None)
+        if evt is not None:
+            evt.synchronize()                        # join the side-stream copy of this call's action
+        np_obs, np_reward, np_done = slot["np"]
+        self._observations = self._fused_np_obs(np_obs)
+        return self._observations, np_reward, np_done, info
+
+    def _step_fused(self):
         global _RecordInfo, _wait_flag
         if _RecordInfo is None:                  # resolved once (fused.py imports this module's siblings)
             from .fused import RecordInfo as _RecordInfo
@@ -247,36 +280,26 @@ class DroneGymEnvsBase(VecEnv):
             _wait_flag = _lib.fast().wait_flag
         if self.requires_grad and not self.tensor_output:
             raise ValueError("requires_grad should be False if tensor_output is False")
-        slot = None if self.tensor_output else self._fused.host_slot()
-        late = None
-        if host_action is not None:
-            def late():
-                self._action = self._stage_action(host_action, side_stream=True)
-                return self._action
-        obs, reward, done, record, term = self._fused.step(None if late else self._action,
-                                                           owned=bool(late) or self._action_owned,
-                                                           grad=self.requires_grad,
-                                                           mirror=None if slot is None else slot["ref"],
-                                                           late_action=late)
+        fz = self._fused
+        slot = None if self.tensor_output else fz.host_slot()
+        obs, reward, done, record, term = fz.step(self._action, self._action_owned, self.requires_grad,
+                                                  None if slot is None else slot["ref"])
         self._obs_tensors = self._fused_obs(obs)
-        if self._fused.task != 2:                # params.TASK_RACING
-            # the terminal-observation dict is built only if somebody reads a finished agent's info
+        # the terminal-observation dict is built only if somebody reads a finished agent's info
+        if fz.task != 2:                         # params.TASK_RACING
             info = _RecordInfo(self.num_agent, record, term, self.envs.dynamics.ctrl_dt, False, self._fused_obs)
-        else:
-            # racing: the observation includes the gate index, a buffer later steps update in place -> build it now
-            info = _RecordInfo(self.num_agent, record, {} if term is None else self._fused_obs(term),
-                               self.envs.dynamics.ctrl_dt, True)
+        else:                                    # racing: the dict also carries this step's gate tensor
+            gate = fz.gate_obs
+            info = _RecordInfo(self.num_agent, record, term, self.envs.dynamics.ctrl_dt, True,
+                               lambda t: self._fused_obs(t, gate))
         self._info = info
         if self.tensor_output:                   # kernel outputs never carry autograd history: nothing to detach
             self._observations = self._obs_tensors
             return self._obs_tensors, reward, done, info
-        # numpy mode (reference droneGymEnv.py:218): the kernel has already written obs / reward / done into the
-        # page-locked host slot (zero-copy stores over PCIe); its last thread block raises the slot's completion word,
-        # which the host spins on (no driver call, and nothing queued behind the launch is waited for)
+        # numpy mode without a FIFO to run ahead in (reference droneGymEnv.py:218): the kernel has already written
+        # obs / reward / done into the page-locked host slot (zero-copy stores over PCIe); its last thread block
+        # raises the slot's completion word, which the host spins on (no driver call)
         _wait_flag(slot["flag"].data_ptr(), slot["expect"])
-        evt = self.__dict__.pop("_h2d_evt", None)
-        if evt is not None:
-            evt.synchronize()                        # join the side-stream copy of this step's action
         np_obs, np_reward, np_done = slot["np"]
         self._observations = self._fused_np_obs(np_obs)
         return self._observations, np_reward, np_done, info
@@ -375,6 +398,8 @@ class DroneGymEnvsBase(VecEnv):
         """Deep-copyable like the reference env (utils/algorithms/shac.py:121); host staging buffers and CUDA
         events are per-object scratch and are re-created lazily by the copy."""
         import copy
+        if self.__dict__.get("_fused") is not None:
+            self._fused.rewind()          # a step launched ahead of the caller (host mode) is not part of the state
         twin = self.__class__.__new__(self.__class__)
         memo[id(self)] = twin
         for k, v in self.__dict__.items():

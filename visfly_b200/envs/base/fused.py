@@ -10,6 +10,7 @@ Everything else (custom tasks) keeps using the generic tensor-op path, which has
 """
 from __future__ import annotations
 
+import collections
 import ctypes
 import os
 from collections.abc import Sequence
@@ -158,19 +159,26 @@ class FusedEnvStep:
         self.active = False
         self.global_step = 0
         self.status: Optional[th.Tensor] = None
+        self.gate_obs: Optional[th.Tensor] = None    # racing: next gate index as the observation dict carries it
         self.record: Optional[th.Tensor] = None      # episode record of the last step (success / failure views)
         self.t_off: Optional[th.Tensor] = None       # per-agent time offsets given at reset (None: all zero)
         self.step_base: Optional[th.Tensor] = None   # device word added to the Philox step index (graph replays)
         self._views = (None, None)
         self._key, self._watch, self._watch_sum, self._ok = None, (), 0, False
+        # host-driven (numpy) mode runs one step ahead of its caller: steps launched but not yet handed out, and the
+        # (state, status) the next launch starts from.  See step_host / rewind.
+        self._ahead = collections.deque()
+        self._front = None
         self._fn = None
         self._bind()
 
-    _CTYPES_REFS = ("_fn", "_stepper", "_params_addr", "_spec_addr", "_host_ring", "_host_turn", "_views")
+    _CTYPES_REFS = ("_fn", "_stepper", "_params_addr", "_spec_addr", "_host_ring", "_host_turn", "_views", "_ahead",
+                    "_front", "_counter", "_flag_seq")
 
     def __deepcopy__(self, memo):
         """ctypes references are per-object handles: the copy re-creates them against its own env / spec."""
         import copy
+        self.rewind()                     # steps launched ahead of the caller are not part of the copied state
         twin = self.__class__.__new__(self.__class__)
         memo[id(self)] = twin
         for k, v in self.__dict__.items():
@@ -178,6 +186,7 @@ class FusedEnvStep:
                 setattr(twin, k, copy.deepcopy(v, memo))
         twin._fn = twin._stepper = None   # re-bound on first use (the twin env may not be fully copied yet)
         twin._views = (None, None)
+        twin._ahead, twin._front = collections.deque(), None
         return twin
 
     def _bind(self):
@@ -215,21 +224,23 @@ class FusedEnvStep:
         """Re-read the settings that may change between steps; False => the generic path must be used.
         The answer is cached on the identity of every object it was derived from plus the version counters of the
         tensors among them, so in-place edits (``env.target[:] = ...``, generator tables) are seen as well as
-        re-assignments; the check runs once per step and costs well under a microsecond."""
+        re-assignments.  Runs once per step: straight-line identity tests, about a microsecond."""
         env = self.env
         envs = env.envs
         d = env.__dict__
-        key = (envs.stateGenerator, envs._reset_table, env.max_episode_steps, env.is_collision_reset,
-               env.use_fused_step, d.get("target"), d.get("targets"), d.get("success_radius"), envs.uav_radius,
-               envs._bboxes[0], envs.dynamics._wind_fn is None)
-        vsum = 0
-        for t in self._watch:
-            vsum += t._version
-        old = self._key
-        if old is not None and vsum == self._watch_sum and len(old) == len(key) and \
-                all(a is b or (type(a) in (int, float, bool) and a == b) for a, b in zip(old, key)):
-            return self._ok
-        self._key = key
+        k = self._key
+        if k is not None and envs.stateGenerator is k[0] and envs._reset_table is k[1] \
+                and env.max_episode_steps == k[2] and env.is_collision_reset == k[3] and env.use_fused_step == k[4] \
+                and d.get("target") is k[5] and d.get("targets") is k[6] and d.get("success_radius") == k[7] \
+                and envs.uav_radius == k[8] and envs._bboxes[0] is k[9] and (envs.dynamics._wind_fn is None) == k[10]:
+            vsum = 0
+            for t in self._watch:
+                vsum += t._version
+            if vsum == self._watch_sum:
+                return self._ok
+        self._key = (envs.stateGenerator, envs._reset_table, env.max_episode_steps, env.is_collision_reset,
+                     env.use_fused_step, d.get("target"), d.get("targets"), d.get("success_radius"), envs.uav_radius,
+                     envs._bboxes[0], envs.dynamics._wind_fn is None)
         self._ok = self._refresh()
         self._watch_sum = sum(t._version for t in self._watch)
         return self._ok
@@ -237,6 +248,7 @@ class FusedEnvStep:
     def _refresh(self) -> bool:
         """Rebuild the spec from the env's live attributes (host reads: only when something changed)."""
         env, envs, s = self.env, self.env.envs, self.spec
+        self.rewind()                     # a step launched ahead saw the old settings
         self._stepper = None
         watch = []
         ok = True
@@ -249,6 +261,7 @@ class FusedEnvStep:
         s.max_episode_steps = int(env.max_episode_steps)
         s.collision_reset = int(bool(env.is_collision_reset))
         s.uav_radius = float(envs.uav_radius)
+        s.agent_offset = 0 if envs.shard is None else envs.shard[0]
         box = envs._bboxes[0]
         watch.append(box)
         lo, hi = box[0].tolist(), box[1].tolist()
@@ -306,6 +319,7 @@ class FusedEnvStep:
         """Hand the per-agent state back to the attributes the generic path works on."""
         if not self.active:
             return
+        self.rewind()
         env, dyn = self.env, self.env.envs.dynamics
         sc, ret, eb = self.sc.clone(), self.ret.clone(), self.eb
         t_now = self.t_now()
@@ -365,22 +379,20 @@ class FusedEnvStep:
         slot["expect"] = self._flag_seq
         return slot
 
-    def step(self, action, owned: bool = True, grad: bool = False, mirror=None, late_action=None):
+    def step(self, action, owned: bool = True, grad: bool = False, mirror=None):
         """One env step = one launch.  ``grad=True`` routes through ``EnvControlStep`` so that the returned state,
         observation and reward carry autograd history (backward = one launch of ``vf_env_step_bwd``).
         ``owned``: the action tensor is a private device copy (it came through a host->device conversion) and may
-        wait in the comm-delay FIFO as it is; otherwise the launch clones it (``fifo_push`` -> ``fifo_copy``).
-        ``late_action`` (numpy mode with a comm-delay FIFO): a callable that stages this step's host action; it is
-        called AFTER the launch — the kernel consumes an older FIFO entry, so the staging overlaps with it."""
+        wait in the comm-delay FIFO as it is; otherwise the launch clones it (``fifo_push`` -> ``fifo_copy``)."""
         env, dyn = self.env, self.env.envs.dynamics
         if self._fn is None:
             self._bind()
         if not self.active:
             self.enter()
+        if self._ahead:
+            self.rewind()
         push = None
-        if late_action is not None:
-            action = dyn._pre_action.pop(0)
-        elif dyn._comm_delay_steps:
+        if dyn._comm_delay_steps:
             if not action.is_contiguous():
                 action, owned = action.contiguous(), True
             if owned:
@@ -395,21 +407,21 @@ class FusedEnvStep:
         wind = dyn._wind_rows
         state_in, status_in = dyn._state, self.status
         if grad:
-            state_out, status, obs, reward, done, record, term, copy = EnvControlStep.apply(
+            state_out, status, obs, reward, done, record, term, copy, gate = EnvControlStep.apply(
                 state_in, action, push, status_in, wind, self)
+            dyn._prev = (state_in.detach(), action.detach(), None, status_in)
         else:
-            state_out, status, obs, reward, done, record, term, copy = self._launch(
+            state_out, status, obs, reward, done, record, term, copy, gate = self._launch(
                 state_in, action, status_in, mirror, wind, push)
+            dyn._prev = (state_in, action, None, status_in)
         if push is not None:
             dyn._pre_action.append(copy)
-        if late_action is not None:
-            dyn._pre_action.append(late_action())
-        self.status, self.record = status, record
+        self.status, self.record, self.gate_obs = status, record, gate
         if self.t_off is not None:
             self.t_off = th.where(done, 0.0, self.t_off)
-        # keep the Dynamics object coherent (lazy views, diagnostics).  The diagnostics re-run the step on its inputs:
-        # agents younger than the FIFO flew a zero action (the kernel masks by age), so the saved action says so too
-        dyn._prev = (state_in.detach(), _MaskedAction(action.detach(), status_in, self.spec.fifo_depth), None)
+        # keep the Dynamics object coherent (lazy views, diagnostics).  The diagnostics re-run the step on its inputs
+        # (dyn._prev, set above): agents younger than the FIFO flew a zero action — the kernel masks by age — so the
+        # start-of-step status record rides along and _extras applies the same mask
         dyn._state = state_out
         dyn._obs_t = obs if self.obs_kind == P.OBS_STATE13 else None
         dyn._n_steps += 1
@@ -420,19 +432,62 @@ class FusedEnvStep:
         return obs, reward, done, record, term
 
 
-class _MaskedAction:
-    """The action a fused step really consumed, materialised only if the lazy diagnostics ask for it: the delayed
-    action with the rows of agents younger than the FIFO zeroed (what the kernel does by age)."""
+    # -- host-driven mode: one step ahead of the caller ---------------------------------------------------------
+    # With a comm-delay FIFO of depth d >= 1 the action handed to call t is consumed by step t+d, so when call t
+    # arrives everything step t+1 needs is already known.  step_host therefore launches step t+1 BEFORE it waits for
+    # step t: the GPU always has the next kernel queued behind the running one and the zero-copy PCIe stores of one
+    # step overlap with the caller's work on the previous one.  The results handed out are bit-identical to stepping
+    # synchronously (steps are launched in order, each from its predecessor's outputs); what the env / Dynamics
+    # objects show (state, status, info) is always the step that was handed out, and anything that touches the env
+    # other than step() first drops the step in flight (rewind) — it is recomputed by the next call.
+    def _launch_ahead(self):
+        dyn = self.env.envs.dynamics
+        action = dyn._pre_action.pop(0)
+        slot = self.host_slot()
+        state_in, status_in = self._front if self._front is not None else (dyn._state, self.status)
+        out = self._launch(state_in, action, status_in, slot["ref"], None, None)
+        self._front = (out[0], out[1])
+        self._ahead.append((out, slot, state_in, status_in, action))
 
-    __slots__ = ("action", "status", "depth")
+    def rewind(self):
+        """Drop the steps launched ahead of the caller: their actions go back to the head of the FIFO."""
+        if not self._ahead:
+            self._front = None
+            return
+        dyn = self.env.envs.dynamics
+        while self._ahead:
+            _, _, _, _, action = self._ahead.pop()
+            dyn._pre_action.insert(0, action)
+            self.global_step -= 1
+        self._front = None
 
-    def __init__(self, action, status, depth):
-        self.action, self.status, self.depth = action, status, depth
-
-    def resolve(self) -> th.Tensor:
-        if self.depth == 0:
-            return self.action
-        return th.where((self.status[:, 0] < self.depth).view(-1, 1), 0.0, self.action)
+    def step_host(self, stage_action):
+        """One env step for a caller that lives in host memory.  ``stage_action()`` starts the host->device copy of
+        this call's action and returns the device tensor.  Returns ``(obs, reward, done, record, term, slot)`` of the
+        step this call hands out; ``slot`` holds the page-locked numpy views the kernel wrote."""
+        env, dyn = self.env, self.env.envs.dynamics
+        if self._fn is None:
+            self._bind()
+        if not self.active:
+            self.enter()
+        dyn._pre_action.append(stage_action())
+        while len(self._ahead) < 2 and dyn._pre_action:
+            self._launch_ahead()
+        out, slot, state_in, status_in, action = self._ahead.popleft()
+        state_out, status, obs, reward, done, record, term, _, gate = out
+        _lib.fast().wait_flag(slot["flag"].data_ptr(), slot["expect"])
+        self.status, self.record, self.gate_obs = status, record, gate
+        if self.t_off is not None:
+            self.t_off = th.where(done, 0.0, self.t_off)
+        dyn._prev = (state_in, action, None, status_in)
+        dyn._state = state_out
+        dyn._obs_t = obs if self.obs_kind == P.OBS_STATE13 else None
+        dyn._n_steps += 1
+        dyn._ext, dyn._thrusts_given = None, None
+        dyn._fresh = done
+        env.envs._collision_stale = True
+        env._reward, env._done = reward, done
+        return obs, reward, done, record, term, slot
 
 
 class EnvControlStep(th.autograd.Function):
@@ -442,16 +497,17 @@ class EnvControlStep(th.autograd.Function):
 
     @staticmethod
     def forward(ctx, state: th.Tensor, action: th.Tensor, push, status_in: th.Tensor, wind, fz: FusedEnvStep):
-        state_out, status, obs, reward, done, record, term, copy = fz._launch(state, action, status_in, None, wind, push)
+        state_out, status, obs, reward, done, record, term, copy, gate = fz._launch(state, action, status_in, None,
+                                                                                    wind, push)
         ctx.fz, ctx.wind = fz, wind
         ctx.save_for_backward(state, action, status_in)
         ctx.set_materialize_grads(False)
-        ctx.mark_non_differentiable(status, done, record, *(() if term is None else (term,)))
-        return state_out, status, obs, reward, done, record, term, copy
+        ctx.mark_non_differentiable(status, done, record, *(t for t in (term, gate) if t is not None))
+        return state_out, status, obs, reward, done, record, term, copy, gate
 
     @staticmethod
     @th.autograd.function.once_differentiable
-    def backward(ctx, g_state_out, _g_status, g_obs, g_reward, _g_done, _g_record, _g_term, g_copy):
+    def backward(ctx, g_state_out, _g_status, g_obs, g_reward, _g_done, _g_record, _g_term, g_copy, _g_gate):
         state, action, status_in = ctx.saved_tensors
         fz = ctx.fz
         cfg = fz.env.envs.dynamics._cfg

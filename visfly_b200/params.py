@@ -272,6 +272,7 @@ class VfEnvSpec(ctypes.Structure):
         ("gen_heading", ctypes.c_int * GEN_MAX_BOXES),
         ("init_motor_omega", ctypes.c_float),
         ("seed", ctypes.c_ulonglong),
+        ("agent_offset", ctypes.c_uint),
     ]
 
 
