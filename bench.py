@@ -338,7 +338,9 @@ def rotating_brackets(envs, act_list, K, preroll, brackets, stream, barrier, col
     inputs evicted from L2 while launches stay back to back): after `preroll` untimed steps, `brackets` consecutive
     brackets of exactly K steps (+ the rollout's one collective, if given), each opened behind barrier + synchronize
     and closed by synchronising on the bracket's last CUDA event — no barrier, no other collective inside the
-    timed region.  Returns per bracket the device time (CUDA events on the launching stream) and the wall time."""
+    timed region.  `collective`: None, or a FusedReturnsGather — armed before the bracket's last step (whose launch then
+    scatters the per-agent returns to every rank) and finished (cross-rank barrier) right after it.
+    Returns per bracket the device time (CUDA events on the launching stream) and the wall time."""
     R, pool = len(envs), len(act_list)
     for i in range(preroll):
         envs[i % R].step(act_list[i % pool])
@@ -348,10 +350,14 @@ def rotating_brackets(envs, act_list, K, preroll, brackets, stream, barrier, col
         r0, r1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         r0.record(stream)
-        for i in range(K):
+        for i in range(K - 1):
             envs[i % R].step(act_list[i % pool])
+        last = envs[(K - 1) % R]
         if collective is not None:
-            collective()
+            collective.arm(last)
+        last.step(act_list[(K - 1) % pool])
+        if collective is not None:
+            collective.finish(last)
         r1.record(stream)
         r1.synchronize()
         wall_ms.append((time.perf_counter() - t0) * 1e3)
@@ -375,7 +381,7 @@ def racing_leg(n_weak, dev, rank, world, K, W, stream, barrier):
     """BASELINE configs[4]: RacingEnv semantics (gates, radius 0.3, hover-style reward + 20 per gate, 16-wide
     observation; reference envs/RacingEnv.py:87-98,142-148,203-215,250-267), RK4 x8, agents sharded over the GPUs:
     weak scaling (65 536 agents per GPU) and strong scaling (524 288 agents in total, rank r owns shard_range(r))."""
-    from visfly_b200.distributed import EpisodeReturnsGather, shard_range
+    from visfly_b200.distributed import FusedReturnsGather, shard_range
     from visfly_b200.envs import RacingEnv2
     out = {"workload": "RacingEnv2 visual=False RK4 dt=0.0025 ctrl_dt=0.02 bodyrate (BASELINE configs[4])"}
     total_strong = 524288
@@ -393,14 +399,16 @@ def racing_leg(n_weak, dev, rank, world, K, W, stream, barrier):
             e.reset()
         pool = 4
         act_list = list(hover_actions(n, pool, dev, seed=rank).unbind(0))
-        gather = EpisodeReturnsGather(n_total, rank, world, dev)
+        gather = FusedReturnsGather(n, n_total, rank, world, dev)
         dev_ms, wall_ms = rotating_brackets(envs, act_list, K, max(W * replicas, HOT_PREROLL), BRACKETS, stream, barrier,
-                                            collective=lambda: gather(envs[0]._rewards))
+                                            collective=gather)
         ms = max_over_ranks([max(d, w) for d, w in zip(dev_ms, wall_ms)], dev, world)
         t = median(ms)
         out[name] = {"value": n_total * K / (t * 1e-3), "unit": UNIT, "agents_total": n_total, "agents_this_gpu": n,
                      "ms_per_step": t / K, "bracket_ms": ms, "replicas": replicas,
                      "fused": bool(envs[0]._fused is not None and envs[0]._fused.active),
+                     "collective": "fused into the last step (peer-memory stores + barrier)" if gather.fused else
+                                   f"NCCL all_gather_into_tensor ({gather.why_not})",
                      "scaling": name}
         del envs, gather
         th.cuda.empty_cache()
@@ -410,7 +418,7 @@ def racing_leg(n_weak, dev, rank, world, K, W, stream, barrier):
 def run_ours(args):
     import torch.distributed as dist
     from visfly_b200 import _lib
-    from visfly_b200.distributed import EpisodeReturnsGather
+    from visfly_b200.distributed import FusedReturnsGather
     from visfly_b200.envs import HoverEnv
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -449,9 +457,14 @@ def run_ours(args):
         env_step(i)
     # the one collective of the path: episode returns of all shards, once per rollout (a no-op at world 1); buffers
     # and shard sizes are fixed ahead of the rollout, the call is one asynchronous all_gather_into_tensor
-    gather = EpisodeReturnsGather(n * world, rank, world, dev)
-    for _ in range(3):
-        gather(env._rewards)              # NCCL communicator set-up happens here, not in a timed bracket
+    # fused: the rollout's last step stores the returns into every rank's buffer through peer-mapped memory and a
+    # cross-rank barrier follows (FusedReturnsGather); NCCL all_gather_into_tensor where P2P mappings are unavailable
+    gather = FusedReturnsGather(n, n * world, rank, world, dev)
+    for _ in range(3):                    # communicator / barrier set-up happens here, not in a timed bracket
+        gather.arm(env)
+        env_step(0)
+        gather.finish(env)
+        gather.fallback(env._rewards)
     # long-lived objects (modules, the envs) leave the garbage collector's working set: a full collection walking
     # them costs ~1 ms, which is 50 env steps on this path
     import gc
@@ -469,7 +482,7 @@ def run_ours(args):
         #     work to clock back up (measured: 19.8 -> 17.1 -> 14.5 us/step over three consecutive 200-step loops),
         #     hence the untimed pre-roll
         hot_dev, hot_wall = rotating_brackets([env], act_list, K, max(W, HOT_PREROLL), 1, stream, barrier,
-                                              collective=lambda: gather(env._rewards))
+                                              collective=gather)
         # (C) THE reported value: the contract's bracket with inputs larger than L2 and no flush kernel inside it —
         #     REPLICAS independent copies of the 65 536-agent env take turns, so every step finds its state, actions
         #     and env status evicted (REPLICAS x ~17 MB per step >> 126 MB L2) while launches stay back to back.
@@ -482,7 +495,7 @@ def run_ours(args):
             e.reset()
         preroll = max(W * REPLICAS, HOT_PREROLL)
         bracket_dev_ms, bracket_wall_ms = rotating_brackets(envs, act_list, K, preroll, BRACKETS, stream, barrier,
-                                                            collective=lambda: gather(env._rewards))
+                                                            collective=gather)
         # (D) the same loop WITHOUT the collective: the step kernel's own launch-to-launch time (roofline.kernel_us)
         nocoll_dev_ms, _ = rotating_brackets(envs, act_list, K, 50, BRACKETS, stream, barrier)
         # (E) the collective alone, back to back
@@ -490,10 +503,12 @@ def run_ours(args):
         barrier()
         c0.record(stream)
         for _ in range(10):
-            gather(env._rewards)
+            gather.fallback(env._rewards)
         c1.record(stream)
         c1.synchronize()
-        collective_us = c0.elapsed_time(c1) * 1e3 / 10 if world > 1 else 0.0
+        nccl_collective_us = c0.elapsed_time(c1) * 1e3 / 10 if world > 1 else 0.0
+        # the fused form: what the bracket with the collective costs beyond the collective-free one
+        collective_us = max(0.0, (median(bracket_dev_ms) - median(nocoll_dev_ms)) * 1e3) if world > 1 else 0.0
         del envs
     except BaseException:
         clk.__exit__(None, None, None)
@@ -681,9 +696,14 @@ def run_ours(args):
             "clocks": clk.summary(), "e2e": e2e, "gpu_launches": K * env_launches_per_step(env), "apg": apg,
             "racing": racing, "roofline": roofline, "cpu_baseline": cpu, "reference_dynamics_on_gpu": ref_gpu,
             "rollout_collective_us": collective_us,
+            "rollout_collective": {"fused_into_last_step": gather.fused, "why_not": gather.why_not,
+                                   "us_added_to_the_bracket": collective_us,
+                                   "nccl_all_gather_into_tensor_us": nccl_collective_us},
             "dynamics_step_value_per_gpu": dynamics_step_value,
             "cold_l2_device_value": cold_value, "hot_l2_bracketed_value": hot_value, "kernel_only_value": n / k_avg,
             "bracket_ms": bracket_ms,
+            "bracket_detail_rank0": {"device_ms": bracket_dev_ms, "wall_ms": bracket_wall_ms,
+                                     "collective_free_device_ms": nocoll_dev_ms},
         }
         emit(line)
     if world > 1:

@@ -282,6 +282,19 @@ typedef struct VfEnvMirror {
     unsigned  flag_value;  /* what the last block stores into *flag                               */
 } VfEnvMirror;
 
+/* Fused compute + collective: the one collective of the path is an all-gather of per-agent episode returns once per
+ * rollout.  Instead of a collective launched after the rollout's last step, that step's own launch
+ * stores every agent's accumulated return straight into the gather buffer of EVERY rank through peer-mapped device
+ * memory (NVLink / NVSwitch; `dst[r]` = rank r's buffer as mapped into this process, e.g. from
+ * torch.distributed._symmetric_memory): agent i of this shard lands at dst[r][offset + i].  What remains of the
+ * collective is a cross-rank barrier on the stream (the stores are complete when the kernel is).  world = 0 disables. */
+#define VF_MAX_PEERS 8
+typedef struct VfPeerScatter {
+    float*    dst[VF_MAX_PEERS];   /* gather buffer of each rank (this rank's own included), float[n_total]      */
+    long long offset;              /* global index of this shard's agent 0                                       */
+    int       world;               /* number of ranks (<= VF_MAX_PEERS); 0 = nothing to do                       */
+} VfPeerScatter;
+
 /* Spin until the page-locked word *flag equals value (see VfEnvMirror).  Returns 0, or 1 after timeout_us
  * microseconds (timeout_us <= 0: wait forever). */
 int vf_wait_flag(const volatile unsigned* flag, unsigned value, long long timeout_us);
@@ -303,6 +316,7 @@ int vf_wait_flag(const volatile unsigned* flag, unsigned value, long long timeou
  *   gate_out    int64[n] or NULL: next gate index after the step (racing) as the tensor the observation dict carries
  *                 (reference RacingEnv.py:267 `"gate": self._next_target_i`), so that no per-step unpacking is needed
  *   host_mirror NULL, or page-locked host destinations written in addition to obs_out / reward_out / done_out
+ *   peer_returns NULL, or where to scatter the accumulated episode returns of this step (see VfPeerScatter)
  */
 int vf_env_step_fwd(const VfParams* params, const VfEnvSpec* spec, int n, int substeps, int integrator,
                     int action_type, unsigned flags, unsigned env_flags, unsigned long long step_index,
@@ -311,7 +325,7 @@ int vf_env_step_fwd(const VfParams* params, const VfEnvSpec* spec, int n, int su
                     const float* reset_table, const int* status_in,
                     float* state_out, int* status_out, float* fifo_copy, float* obs_out, float* reward_out,
                     unsigned char* done_out, float* record_out, float* term_obs_out, long long* gate_out,
-                    const VfEnvMirror* host_mirror, void* stream);
+                    const VfEnvMirror* host_mirror, const VfPeerScatter* peer_returns, void* stream);
 
 /*
  * Reverse mode of vf_env_step_fwd with respect to (state_in, action), given the gradients of its differentiable

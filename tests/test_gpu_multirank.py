@@ -26,7 +26,7 @@ def _actions():
     return a
 
 
-def _run(lo, hi, device):
+def _run(lo, hi, device, gather=None):
     from visfly_b200.envs import RacingEnv2
     env = RacingEnv2(num_agent_per_scene=hi - lo, visual=False, device=device, tensor_output=True, seed=SEED,
                      dynamics_kwargs=dict(DYN), max_episode_steps=MAX_STEPS,
@@ -36,12 +36,20 @@ def _run(lo, hi, device):
     acts = _actions()[:, lo:hi].to(device)
     out = []
     returns = th.zeros(hi - lo, device=device)
+    fused_returns = []
     for t in range(T):
+        last_of_rollout = gather is not None and t % 4 == 3          # a "rollout" of 4 steps, then the all-gather
+        if last_of_rollout:
+            gather.arm(env)
         obs, r, d, info = env.step(acts[t])
+        if last_of_rollout:
+            fused_returns.append(gather.finish(env).clone())
+        else:
+            fused_returns.append(env._rewards.clone())
         returns = returns + r
         out.append(th.cat([obs["state"], obs["gate"].float(), r.unsqueeze(1), d.float().unsqueeze(1)], 1).cpu())
     assert env._fused.active
-    return th.stack(out), returns
+    return th.stack(out), returns, fused_returns
 
 
 def _free_port():
@@ -60,16 +68,21 @@ def _worker(rank, world, port, nccl, out):
                             **({"device_id": device} if nccl else {}))
     try:
         lo, hi = shard_range(TOTAL, rank, world)
-        rows, returns = _run(lo, hi, device)
+        fg = None
+        if nccl:
+            from visfly_b200.distributed import FusedReturnsGather
+            fg = FusedReturnsGather(hi - lo, TOTAL, rank, world, device)
+        rows, returns, fused_returns = _run(lo, hi, device, fg)
         full = gather_episode_returns(returns if nccl else returns.cpu(), n_total=TOTAL)
-        out[rank] = (lo, hi, rows, full.cpu().clone())
+        out[rank] = (lo, hi, rows, full.cpu().clone(), [x.cpu() for x in fused_returns],
+                     None if fg is None else (fg.fused, fg.why_not))
     finally:
         dist.destroy_process_group()
 
 
 def test_two_ranks_reproduce_the_one_gpu_racing_batch_bitwise():
     import torch.multiprocessing as mp
-    whole, whole_returns = _run(0, TOTAL, th.device("cuda", 0))
+    whole, whole_returns, whole_acc = _run(0, TOTAL, th.device("cuda", 0))
     assert bool(whole[MAX_STEPS - 1][:, -1].all())          # everybody truncated once: Philox restarts are crossed
     nccl = th.cuda.device_count() >= 2
     world = 2
@@ -78,6 +91,12 @@ def test_two_ranks_reproduce_the_one_gpu_racing_batch_bitwise():
         mp.spawn(_worker, args=(world, _free_port(), nccl, out), nprocs=world, join=True)
         res = dict(out)
     assert sorted(res) == [0, 1]
-    for rank, (lo, hi, rows, full) in res.items():
+    for rank, (lo, hi, rows, full, fused_returns, how) in res.items():
         assert th.equal(rows, whole[:, lo:hi]), f"rank {rank}: shard rows differ from the whole batch"
         assert th.equal(full, whole_returns.cpu()), f"rank {rank}: gathered returns differ"
+        if how is not None:
+            # the all-gather fused into the rollout's last env step (peer-memory stores + barrier), or its NCCL
+            # fallback: either way every rank ends up with the whole batch's per-agent episode accumulators
+            print(f"rank {rank}: fused gather = {how}")
+            for t in range(3, T, 4):
+                assert th.equal(fused_returns[t], whole_acc[t].cpu()), (rank, t, how)

@@ -53,3 +53,25 @@ pr.disable()
 th.cuda.synchronize()
 ps = pstats.Stats(pr)
 ps.sort_stats("tottime").print_stats(18)
+
+# short brackets: what does a K-step loop cost right after a device synchronisation (the driver's K = 20 bracket)?
+for K in (20, 200):
+    rows = []
+    for rep in range(8):
+        th.cuda.synchronize()
+        e0, e1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        marks = []
+        for i in range(K):
+            env.step(acts[i % 16])
+            if i in (0, 1, 4, K - 1):
+                marks.append(time.perf_counter() - t0)
+        t_enq = time.perf_counter() - t0
+        e1.record()
+        e1.synchronize()
+        t_all = time.perf_counter() - t0
+        rows.append((t_enq * 1e6 / K, t_all * 1e6 / K, e0.elapsed_time(e1) * 1e3 / K, [round(m * 1e6, 1) for m in marks]))
+    print(f"K={K}: per-step us (enqueue, wall incl. sync, device) and cumulative enqueue marks at steps 1,2,5,K:")
+    for r in rows:
+        print("   %.2f  %.2f  %.2f  %s" % r)

@@ -11,7 +11,7 @@ from typing import Optional
 
 import torch as th
 
-from .params import VfEnvMirror, VfEnvSpec, VfParams
+from .params import VfEnvMirror, VfEnvSpec, VfParams, VfPeerScatter
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvisfly_b200.so")
@@ -43,7 +43,7 @@ SIGNATURES = {
     "vf_env_step_fwd": (_i, [_P(VfParams), _P(VfEnvSpec), _i, _i, _i, _i, _u, _u, ctypes.c_ulonglong, _vp,
                              _vp, _vp, _vp, _vp, _vp, _vp,
                              _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
-                             _P(VfEnvMirror), _vp]),
+                             _P(VfEnvMirror), _P(VfPeerScatter), _vp]),
     "vf_env_step_bwd": (_i, [_P(VfParams), _P(VfEnvSpec), _i, _i, _i, _i, _u, _u,
                              _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
 }
@@ -230,7 +230,7 @@ def env_step_fwd(params: VfParams, spec: VfEnvSpec, substeps: int, integrator: i
                  term_obs_out: Optional[th.Tensor], host_mirror: Optional[VfEnvMirror] = None,
                  wind: Optional[th.Tensor] = None, fifo_push: Optional[th.Tensor] = None,
                  fifo_copy: Optional[th.Tensor] = None, step_base: Optional[th.Tensor] = None,
-                 gate_out: Optional[th.Tensor] = None) -> None:
+                 gate_out: Optional[th.Tensor] = None, peer_returns: Optional[VfPeerScatter] = None) -> None:
     """Binding of ``vf_env_step_fwd`` (fused control step + env wrapper tail, one launch)."""
     lib = load(require_cuda=True)
     n = state_in.shape[1]
@@ -245,7 +245,8 @@ def env_step_fwd(params: VfParams, spec: VfEnvSpec, substeps: int, integrator: i
             _dev_ptr(fifo_copy, "fifo_copy"), _dev_ptr(obs_out, "obs_out"), _dev_ptr(reward_out, "reward_out"),
             _any_ptr(done_out, "done_out", th.bool), _dev_ptr(record_out, "record_out"),
             _dev_ptr(term_obs_out, "term_obs_out"), _any_ptr(gate_out, "gate_out", th.int64),
-            None if host_mirror is None else ctypes.byref(host_mirror), _stream(state_in.device)))
+            None if host_mirror is None else ctypes.byref(host_mirror),
+            None if peer_returns is None else ctypes.byref(peer_returns), _stream(state_in.device)))
 
 
 def env_step_bwd(params: VfParams, spec: VfEnvSpec, substeps: int, integrator: int, action_type: int, flags: int,

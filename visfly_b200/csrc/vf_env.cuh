@@ -45,18 +45,26 @@ template <class T> struct BoxHit {
     T dis;          // |delta|
     bool out;       // is_out_bounds
 };
+// component `axis` of a 3-vector held in registers: selects, not an indexed access (a register array indexed at run
+// time is demoted to local memory together with the struct around it — measured: it cost the forward kernel a
+// 152-byte stack frame and 45 local stores per agent)
+template <class T> VF_HD T pick3(const T v[3], int axis) { return axis == 0 ? v[0] : (axis == 1 ? v[1] : v[2]); }
+
 template <class T> VF_HD BoxHit<T> box_hit(const T p[3], const float lo[3], const float hi[3]) {
     BoxHit<T> h;
-    T best = p[0] - T(lo[0]);
+    // gaps to the six faces in the reference's order [p-lo (x,y,z), hi-p (x,y,z)]; first minimum wins (torch.min)
+    const T gap[6] = {p[0] - T(lo[0]), p[1] - T(lo[1]), p[2] - T(lo[2]),
+                      T(hi[0]) - p[0], T(hi[1]) - p[1], T(hi[2]) - p[2]};
+    T best = gap[0];
     int face = 0;
-    for (int j = 1; j < 6; ++j) {                   // order [p-lo (x,y,z), hi-p (x,y,z)], first minimum wins
-        const T g = j < 3 ? p[j] - T(lo[j]) : T(hi[j - 3]) - p[j - 3];
-        if (g < best) { best = g; face = j; }
-    }
-    h.axis = face % 3;
-    const T wall = face < 3 ? T(lo[h.axis]) : T(hi[h.axis]);
-    h.delta = wall - p[h.axis];
-    h.dis = vsqrt(h.delta * h.delta);
+    for (int j = 1; j < 6; ++j)
+        if (gap[j] < best) { best = gap[j]; face = j; }
+    h.axis = face < 3 ? face : face - 3;
+    // collision_vector[axis] = wall - p[axis]: lo - p = -(p - lo) and hi - p are the gaps themselves (exact)
+    h.delta = face < 3 ? -best : best;
+    // the reference takes the 2-norm of a vector with one non-zero component: sqrt(delta^2) = |delta| (exact in
+    // binary floating point short of underflow of the square)
+    h.dis = vabs(best);
     h.out = (p[0] < T(lo[0])) | (p[1] < T(lo[1])) | (p[2] < T(lo[2])) | (p[0] > T(hi[0])) | (p[1] > T(hi[1])) |
             (p[2] > T(hi[2]));
     return h;
@@ -98,7 +106,7 @@ VF_HD T reward_navigation(const T p[3], const T q[4], const T v[3], const T w[3]
     const T near = T(1) / (hit.dis + T(0.2)) * T(-0.01);
     T prox = T(1) - hit.dis;
     prox = prox > T(0) ? prox : T(0);
-    T closing = (hit.delta * v[hit.axis]) / (T(1e-6) + hit.dis);
+    T closing = (hit.delta * pick3(v, hit.axis)) / (T(1e-6) + hit.dis);
     closing = closing > T(0) ? closing : T(0);
     const T bonus = success ? T(max_steps - step_count) * T(0.1) * (T(0.2) + T(0.8) / (T(1) + T(1) * vn)) : T(0);
     return T(0.1) * T(0) + approach * T(0.01) + ang * T(-0.01) + stable + near + prox * closing * T(-0.005) + bonus;
@@ -196,7 +204,7 @@ VF_HD void reward_navigation_adj(const T p[3], const T q[4], const T v[3], const
         const T dis = hit.dis, delta = hit.delta;
         T g_dis = gr * T(0.01) / ((dis + T(0.2)) * (dis + T(0.2)));
         const T den = T(1e-6) + dis;
-        const T num = delta * v[ax];
+        const T num = delta * pick3(v, ax);
         const T cl0 = num / den;
         const T A = T(1) - dis > T(0) ? T(1) - dis : T(0);
         const T Bc = cl0 > T(0) ? cl0 : T(0);
@@ -204,10 +212,13 @@ VF_HD void reward_navigation_adj(const T p[3], const T q[4], const T v[3], const
         if (cl0 > T(0)) {
             const T g_cl0 = gr * T(-0.005) * A;
             for (int j = 0; j < 3; ++j) gp[j] -= g_cl0 * v[j] / den;      // d num / d p_j = -v_j
-            gv[ax] += g_cl0 * delta / den;                               // d num / d v_ax = delta
+            for (int j = 0; j < 3; ++j)
+                if (j == ax) gv[j] += g_cl0 * delta / den;               // d num / d v_ax = delta
             g_dis -= g_cl0 * num / (den * den);
         }
-        if (dis > T(0)) gp[ax] -= g_dis * delta / dis;                   // dis = |delta|, d delta / d p_ax = -1
+        if (dis > T(0))
+            for (int j = 0; j < 3; ++j)
+                if (j == ax) gp[j] -= g_dis * delta / dis;               // dis = |delta|, d delta / d p_ax = -1
     }
     // success bonus
     if (success && vn > T(0)) {
@@ -246,7 +257,8 @@ VF_HD void env_eval(const Params<T>& P, const VfEnvSpec& E, const State<T>& s, c
     } else {
         for (int j = 0; j < 3; ++j) tgt[j] = T(E.gates[gate_in][j]);
         ev.pass = norm3(s.p[0] - tgt[0], s.p[1] - tgt[1], s.p[2] - tgt[2]) <= T(E.success_radius);
-        ev.gate = (gate_in + (ev.pass ? 1 : 0)) % E.n_gates;
+        ev.gate = gate_in + (ev.pass ? 1 : 0);
+        if (ev.gate >= E.n_gates) ev.gate -= E.n_gates;          // (gate_in + pass) % n_gates with gate_in < n_gates
         for (int j = 0; j < 3; ++j) tgt[j] = T(E.gates[ev.gate][j]);
         ev.reward = reward_hover<T>(s.p, s.q, ev.vel, s.w, tgt) + (ev.pass ? T(20) : T(0));
     }

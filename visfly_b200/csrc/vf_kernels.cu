@@ -250,7 +250,7 @@ vf_env_step_fwd_kernel(const __grid_constant__ VfParams params, const __grid_con
                        float* __restrict__ obs_out, float* __restrict__ reward_out,
                        unsigned char* __restrict__ done_out, float* __restrict__ record_out,
                        float* __restrict__ term_obs_out, long long* __restrict__ gate_out,
-                       const VfEnvMirror mirror) {
+                       const VfEnvMirror mirror, const __grid_constant__ VfPeerScatter peers) {
     __shared__ __align__(16) float s_obs[(BLOCK / 32) * kWarpObs];
     const vf::Params<float>& P = reinterpret_cast<const vf::Params<float>&>(params);
     const int i = blockIdx.x * BLOCK + threadIdx.x;
@@ -317,9 +317,11 @@ vf_env_step_fwd_kernel(const __grid_constant__ VfParams params, const __grid_con
             } else {
                 float* t = term_obs_out + size_t(i) * 16;
                 // the reference builds the terminal observation before the gate index advances (RacingEnv.py:254)
-                const int g0 = g_in;
-                for (int kk = 0; kk < 2; ++kk)
-                    for (int j = 0; j < 3; ++j) t[3 * kk + j] = (E.gates[(g0 + kk) % E.n_gates][j] - s.p[j]) / 10.f;
+                const int g0 = g_in, g1 = g_in + 1 >= E.n_gates ? g_in + 1 - E.n_gates : g_in + 1;
+                for (int j = 0; j < 3; ++j) {
+                    t[j] = (E.gates[g0][j] - s.p[j]) / 10.f;
+                    t[3 + j] = (E.gates[g1][j] - s.p[j]) / 10.f;
+                }
                 t[6] = s.q[0]; t[7] = s.q[1]; t[8] = s.q[2]; t[9] = s.q[3];
                 for (int j = 0; j < 3; ++j) { t[10 + j] = vel[j] / 10.f; t[13 + j] = s.w[j] / 10.f; }
             }
@@ -341,11 +343,17 @@ vf_env_step_fwd_kernel(const __grid_constant__ VfParams params, const __grid_con
         const int ebo = int((ep_done ? VF_EBIT_EPISODE_DONE : 0u) | (once ? VF_EBIT_ONCE_COLLIDED : 0u));
         reinterpret_cast<int4*>(status_out)[i] = make_int4(sc, __float_as_int(ret), ebo | (g << 8), passed);
         if (gate_out) gate_out[i] = g;
+        // the rollout's all-gather, fused: this agent's episode return goes to every rank's gather buffer through
+        // peer-mapped memory (NVLink); a warp stores 128 contiguous bytes per peer
+        for (int r = 0; r < peers.world; ++r) peers.dst[r][peers.offset + i] = ret;
 
         if (E.obs_kind == VF_OBS_RACING16) {
             float o[16];
-            for (int kk = 0; kk < 2; ++kk)
-                for (int j = 0; j < 3; ++j) o[3 * kk + j] = (E.gates[(g + kk) % E.n_gates][j] - s.p[j]) / 10.f;
+            const int g1 = g + 1 >= E.n_gates ? g + 1 - E.n_gates : g + 1;      // (g + 1) % n_gates
+            for (int j = 0; j < 3; ++j) {
+                o[j] = (E.gates[g][j] - s.p[j]) / 10.f;
+                o[3 + j] = (E.gates[g1][j] - s.p[j]) / 10.f;
+            }
             o[6] = s.q[0]; o[7] = s.q[1]; o[8] = s.q[2]; o[9] = s.q[3];
             for (int j = 0; j < 3; ++j) { o[10 + j] = vel[j] / 10.f; o[13 + j] = s.w[j] / 10.f; }
             for (int kk = 0; kk < 4; ++kk) {
@@ -646,11 +654,12 @@ void launch_env_fwd(const VfParams& p, const VfEnvSpec& e, int n, int substeps, 
                     unsigned long long step_index, const unsigned long long* step_base, const float* si,
                     const float* a, const float* wind, const float* push, const float* table, const int* status_in,
                     float* so, int* status_out, float* copy, float* obs, float* rew, unsigned char* done, float* rec,
-                    float* tobs, long long* gate_out, const VfEnvMirror& mirror, cudaStream_t st) {
+                    float* tobs, long long* gate_out, const VfEnvMirror& mirror, const VfPeerScatter& peers,
+                    cudaStream_t st) {
     const int grid = (n + kBlock - 1) / kBlock;
     launch_pdl(vf_env_step_fwd_kernel<INTEG, ACT, LAG, kBlock>, grid, kBlock, st, p, e, n, substeps, env_flags,
                step_index, step_base, si, a, wind, push, table, status_in, so, status_out, copy, obs, rew, done, rec,
-               tobs, gate_out, mirror);
+               tobs, gate_out, mirror, peers);
 }
 
 template <int INTEG, int ACT, bool LAG>
@@ -821,9 +830,17 @@ int vf_env_step_fwd(const VfParams* params, const VfEnvSpec* spec, int n, int su
                     const float* reset_table, const int* status_in,
                     float* state_out, int* status_out, float* fifo_copy, float* obs_out, float* reward_out,
                     unsigned char* done_out, float* record_out, float* term_obs_out, long long* gate_out,
-                    const VfEnvMirror* host_mirror, void* stream) {
+                    const VfEnvMirror* host_mirror, const VfPeerScatter* peer_returns, void* stream) {
     if (check_common(params, n, substeps, integrator, action_type)) return 1;
     if (check_spec(spec)) return 1;
+    VfPeerScatter peers = {};
+    if (peer_returns && peer_returns->world > 0) {
+        if (peer_returns->world > VF_MAX_PEERS) return fail("peer_returns.world exceeds VF_MAX_PEERS");
+        if (peer_returns->offset < 0) return fail("peer_returns.offset must be >= 0");
+        for (int r = 0; r < peer_returns->world; ++r)
+            if (!peer_returns->dst[r]) return fail("peer_returns.dst has a NULL entry");
+        peers = *peer_returns;
+    }
     if (n == 0) return 0;
     if (!state_in || !action || !state_out || !status_in || !status_out || !obs_out || !reward_out || !done_out ||
         !record_out)
@@ -876,7 +893,7 @@ int vf_env_step_fwd(const VfParams* params, const VfEnvSpec* spec, int n, int su
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     VF_DISPATCH_FWD(launch_env_fwd, *params, *spec, n, substeps, env_flags, step_index, step_base, state_in, action,
                     wind, fifo_push, reset_table, status_in, state_out, status_out, fifo_copy, obs_out, reward_out,
-                    done_out, record_out, term_obs_out, gate_out, mirror, st);
+                    done_out, record_out, term_obs_out, gate_out, mirror, peers, st);
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return fail("vf_env_step_fwd launch failed", err);
     return 0;

@@ -112,7 +112,8 @@ class EnvStepper {
     // returns (state', status', obs, reward, done, record, terminal obs | None, fifo copy | None, gate | None)
     std::tuple<at::Tensor, at::Tensor, at::Tensor, at::Tensor, at::Tensor, at::Tensor, OptTensor, OptTensor, OptTensor>
     step(const at::Tensor& state_in, const at::Tensor& action, const at::Tensor& status_in, int64_t step_index,
-         int64_t env_flags, bool want_term, int64_t host_mirror, const OptTensor& wind, const OptTensor& push) {
+         int64_t env_flags, bool want_term, int64_t host_mirror, const OptTensor& wind, const OptTensor& push,
+         int64_t peer_returns) {
         check_f32_cuda(state_in, "state_in");
         check_f32_cuda(action, "action");
         TORCH_CHECK(state_in.dim() == 3 && state_in.size(0) == VF_STATE_PLANES && state_in.size(1) == n_ &&
@@ -152,7 +153,7 @@ class EnvStepper {
             static_cast<float*>(ptr(copy)), obs.data_ptr<float>(), reward.data_ptr<float>(),
             reinterpret_cast<unsigned char*>(done.data_ptr<bool>()), record.data_ptr<float>(),
             static_cast<float*>(ptr(term)), reinterpret_cast<long long*>(ptr(gate)),
-            reinterpret_cast<const VfEnvMirror*>(host_mirror),
+            reinterpret_cast<const VfEnvMirror*>(host_mirror), reinterpret_cast<const VfPeerScatter*>(peer_returns),
             c10::cuda::getCurrentCUDAStream(state_in.device().index()).stream());
         TORCH_CHECK(rc == 0, "visfly_b200: ", vf_last_error());
         return {state_out, status, obs, reward, done, record, term, copy, gate};
@@ -190,7 +191,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         .def(py::init<int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, OptTensor, int64_t, OptTensor>())
         .def("step", &EnvStepper::step, py::arg("state_in"), py::arg("action"), py::arg("status_in"),
              py::arg("step_index"), py::arg("env_flags"), py::arg("want_term"), py::arg("host_mirror"),
-             py::arg("wind") = py::none(), py::arg("push") = py::none());
+             py::arg("wind") = py::none(), py::arg("push") = py::none(), py::arg("peer_returns") = 0);
     m.def("wait_flag", &wait_flag, py::arg("flag_addr"), py::arg("value"), py::arg("timeout_us") = 10000000);
     m.def("abi_version", []() { return vf_abi_version(); });
 }

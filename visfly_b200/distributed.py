@@ -98,9 +98,9 @@ class EpisodeReturnsGather:
     def __call__(self, returns: th.Tensor) -> th.Tensor:
         if returns.numel() != self.n_local:
             raise ValueError(f"rank {self.rank} owns {self.n_local} agents, got {returns.numel()} returns")
-        src = returns.detach().reshape(-1)
         if self.world == 1:
-            return src
+            return returns
+        src = returns.detach().reshape(-1)
         if not self.ragged:
             dist.all_gather_into_tensor(self.out, src.contiguous(), group=self.group)
             return self.out
@@ -108,6 +108,95 @@ class EpisodeReturnsGather:
         dist.all_gather_into_tensor(self.wide, self.stage, group=self.group)
         th.index_select(self.wide, 0, self.index, out=self.out)
         return self.out
+
+
+class FusedReturnsGather:
+    """The rollout's all-gather of episode returns, fused into the rollout's last env step.
+
+    ``EpisodeReturnsGather`` launches a collective behind the last step (copy to a contiguous send buffer, NCCL
+    all-gather, two stream hand-overs: ~40 us on 2 GPUs, as long as three env steps).  Here the last step's own launch
+    stores each agent's return directly into the gather buffer of every rank through peer-mapped device memory
+    (``torch.distributed._symmetric_memory``: NVLink / NVSwitch P2P mappings exchanged once at construction), so the
+    transfer rides inside the step kernel and what is left of the collective is one cross-rank barrier on the stream.
+
+        gather = FusedReturnsGather(n_local, n_total, rank, world, device)    # once (collective: all ranks)
+        ... K-1 x env.step(a) ...
+        gather.arm(env)                                               # the NEXT env.step also scatters the returns
+        env.step(a)
+        returns = gather.finish(env)                                  # (n_total,) in rank order, valid in stream order
+
+    Two buffers alternate between rollouts, so a rank that is already scattering rollout k+1 never writes into the
+    buffer a slower rank is still reading for rollout k (``finish`` keeps ranks within one rollout of each other).
+    Falls back to ``EpisodeReturnsGather`` (NCCL) where peer mappings are unavailable, or for envs on the generic
+    tensor-op path; ``self.fused`` says which one is in use."""
+
+    def __init__(self, n_local: int, n_total: int, rank: int, world: int, device, group=None):
+        from .params import MAX_PEERS, VfPeerScatter
+        self.n_local, self.n_total, self.rank, self.world = int(n_local), int(n_total), int(rank), int(world)
+        self.device = th.device(device)
+        lo, hi = shard_range(n_total, rank, world)
+        if hi - lo != self.n_local:
+            raise ValueError(f"rank {rank} owns {hi - lo} of {n_total} agents, not {n_local}")
+        self.offset = lo
+        self.fallback = EpisodeReturnsGather(n_total, rank, world, self.device, group=group)
+        self.fused, self.why_not = False, None
+        self._turn, self._armed = 0, False
+        if world == 1:
+            self.why_not = "single process"
+            return
+        if world > MAX_PEERS:
+            self.why_not = f"more than {MAX_PEERS} ranks"
+            return
+        try:
+            import torch.distributed._symmetric_memory as symm
+            grp = group if group is not None else dist.group.WORLD
+            self._bufs, self._hdls, self._peers = [], [], []
+            for _ in range(2):
+                buf = symm.empty(self.n_total, dtype=th.float32, device=self.device)
+                hdl = symm.rendezvous(buf, grp)
+                ptrs = list(hdl.buffer_ptrs)
+                if len(ptrs) != world or not all(ptrs):
+                    raise RuntimeError("incomplete peer mapping")
+                ps = VfPeerScatter()
+                for r, ptr in enumerate(ptrs):
+                    ps.dst[r] = ptr
+                ps.offset, ps.world = lo, world
+                buf.zero_()
+                self._bufs.append(buf); self._hdls.append(hdl); self._peers.append(ps)
+            th.cuda.synchronize(self.device)
+            self._hdls[0].barrier(channel=0)
+            self.fused = True
+        except Exception as e:          # no P2P / fabric handles on this box: the NCCL collective does the job
+            self.why_not = repr(e)[:200]
+            self.fused = False
+        # every rank must take the same path (the barrier is collective)
+        flag = th.tensor([1 if self.fused else 0], device=self.device, dtype=th.int32)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        if int(flag) == 0 and self.fused:
+            self.fused, self.why_not = False, "a peer could not map the buffers"
+
+    def arm(self, env):
+        """The next ``env.step`` scatters the accumulated episode returns to every rank (fused path only)."""
+        fz = getattr(env, "_fused", None)
+        self._armed = bool(self.fused and fz is not None and env.use_fused_step and env.num_agent == self.n_local)
+        if self._armed:
+            import ctypes
+            fz.peer_next = ctypes.addressof(self._peers[self._turn])
+
+    def finish(self, env) -> th.Tensor:
+        """All ranks' returns ``(n_total,)`` in rank order; valid in stream order, overwritten two rollouts later."""
+        fz = getattr(env, "_fused", None)
+        if self._armed and fz is not None and fz.peer_next == 0 and fz.peer_done:
+            fz.peer_done = False
+            buf, hdl = self._bufs[self._turn], self._hdls[self._turn]
+            hdl.barrier(channel=0)                   # every rank's step kernel has finished storing
+            self._turn ^= 1
+            self._armed = False
+            return buf
+        if fz is not None:
+            fz.peer_next = 0
+        self._armed = False
+        return self.fallback(env._rewards)
 
 
 _GATHERS = {}

@@ -163,6 +163,8 @@ class FusedEnvStep:
         self.record: Optional[th.Tensor] = None      # episode record of the last step (success / failure views)
         self.t_off: Optional[th.Tensor] = None       # per-agent time offsets given at reset (None: all zero)
         self.step_base: Optional[th.Tensor] = None   # device word added to the Philox step index (graph replays)
+        self.peer_next = 0                           # address of a VfPeerScatter for the NEXT launch (fused all-gather)
+        self.peer_done = False                       # ... and whether that launch has happened
         self._views = (None, None)
         self._key, self._watch, self._watch_sum, self._ok = None, (), 0, False
         # host-driven (numpy) mode runs one step ahead of its caller: steps launched but not yet handed out, and the
@@ -173,7 +175,7 @@ class FusedEnvStep:
         self._bind()
 
     _CTYPES_REFS = ("_fn", "_stepper", "_params_addr", "_spec_addr", "_host_ring", "_host_turn", "_views", "_ahead",
-                    "_front", "_counter", "_flag_seq")
+                    "_front", "_counter", "_flag_seq", "peer_next", "peer_done")
 
     def __deepcopy__(self, memo):
         """ctypes references are per-object handles: the copy re-creates them against its own env / spec."""
@@ -187,6 +189,7 @@ class FusedEnvStep:
         twin._fn = twin._stepper = None   # re-bound on first use (the twin env may not be fully copied yet)
         twin._views = (None, None)
         twin._ahead, twin._front = collections.deque(), None
+        twin.peer_next, twin.peer_done = 0, False
         return twin
 
     def _bind(self):
@@ -204,16 +207,32 @@ class FusedEnvStep:
         return self._stepper
 
     # -- views of the current status record ---------------------------------------------------------------
-    def _fields(self):
+    # built on demand, one field at a time (sc / ret / passed are strided views — no kernel; eb / gate unpack bits)
+    def _field(self, k):
         if self._views[0] is not self.status:
-            self._views = (self.status, _lib.unpack_status(self.status))
-        return self._views[1]
+            self._views = (self.status, {})
+        cache = self._views[1]
+        v = cache.get(k)
+        if v is None:
+            st = self.status
+            if k == 0:
+                v = st[:, 0]
+            elif k == 1:
+                v = st[:, 1].view(th.float32)
+            elif k == 2:
+                v = st[:, 2] & 0xFF
+            elif k == 3:
+                v = (st[:, 2] >> 8) & 0xFF
+            else:
+                v = st[:, 3]
+            cache[k] = v
+        return v
 
-    sc = property(lambda self: self._fields()[0])
-    ret = property(lambda self: self._fields()[1])
-    eb = property(lambda self: self._fields()[2])
-    gate = property(lambda self: self._fields()[3] if self.task == P.TASK_RACING else None)
-    passed = property(lambda self: self._fields()[4] if self.task == P.TASK_RACING else None)
+    sc = property(lambda self: self._field(0))
+    ret = property(lambda self: self._field(1))
+    eb = property(lambda self: self._field(2))
+    gate = property(lambda self: self._field(3) if self.task == P.TASK_RACING else None)
+    passed = property(lambda self: self._field(4) if self.task == P.TASK_RACING else None)
 
     def t_now(self) -> th.Tensor:
         t = self.sc * self.env.envs.dynamics.ctrl_dt
@@ -348,8 +367,12 @@ class FusedEnvStep:
         ``mirror``: address of a ``VfEnvMirror`` (page-locked host destinations for obs / reward / done), or None."""
         # hot call: one Python->C++ transition allocates the outputs (torch caching allocator) and launches through
         # the C-ABI on the current stream of the state's device (csrc/vf_torch.cpp, EnvStepper)
+        peer = self.peer_next
         out = (self._stepper or self._make_stepper()).step(state_in, action, status_in, self.global_step, 0,
-                                                           self.env.keep_terminal_observation, mirror or 0, wind, push)
+                                                           self.env.keep_terminal_observation, mirror or 0, wind, push,
+                                                           peer)
+        if peer:
+            self.peer_next, self.peer_done = 0, True
         self.global_step += 1
         return out
 

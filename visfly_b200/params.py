@@ -281,3 +281,12 @@ class VfEnvMirror(ctypes.Structure):
     the completion word the last thread block raises (``flag`` page-locked host, ``counter`` device, zeroed)."""
     _fields_ = [("obs", ctypes.c_void_p), ("reward", ctypes.c_void_p), ("done", ctypes.c_void_p),
                 ("flag", ctypes.c_void_p), ("counter", ctypes.c_void_p), ("flag_value", ctypes.c_uint)]
+
+
+MAX_PEERS = 8
+
+
+class VfPeerScatter(ctypes.Structure):
+    """ctypes mirror of ``struct VfPeerScatter``: peer-mapped gather buffers the rollout's last env step scatters the
+    per-agent episode returns into (the fused all-gather of SURVEY.md §8e)."""
+    _fields_ = [("dst", ctypes.c_void_p * MAX_PEERS), ("offset", ctypes.c_longlong), ("world", ctypes.c_int)]
