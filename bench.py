@@ -626,6 +626,28 @@ def run_ours(args):
     for i in range(5):
         kernel_mirror(i)
     km_avg = float(np.mean(timed_steps(kernel_mirror, 50, flush, stream))) * 1e-3
+    # ... and with the completion word the host spins on (fence.sys per thread + one atomic per block at the end)
+    m_flag = th.zeros(16, dtype=th.int32, pin_memory=True)
+    m_counter = th.zeros(1, dtype=th.int32, device=dev)
+    mirror_f = VfEnvMirror(m_obs.data_ptr(), m_rew.data_ptr(), m_done.data_ptr(), m_flag.data_ptr(),
+                           m_counter.data_ptr(), 1)
+
+    def kernel_mirror_flag(i):
+        _lib.env_step_fwd(cfg.params, fz.spec, cfg.substeps, cfg.integrator, cfg.action_type, cfg.flags, 0, 20_000 + i,
+                          st_in, acts[i % pool], None, status, st_out, status_o, obs_out, rew_o, done_o, rec_o, None,
+                          mirror_f)
+
+    for i in range(5):
+        kernel_mirror_flag(i)
+    kmf_avg = float(np.mean(timed_steps(kernel_mirror_flag, 50, flush, stream))) * 1e-3
+    # back to back (what the run-ahead host loop keeps queued): K launches between one event pair
+    b0, b1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
+    b0.record(stream)
+    for i in range(50):
+        kernel_mirror_flag(i)
+    b1.record(stream)
+    b1.synchronize()
+    kmf_b2b = b0.elapsed_time(b1) * 1e-3 / 50
 
     # ---- e2e: numpy in / numpy out through the public env API -------------------------------------------
     env_np = HoverEnv(num_agent_per_scene=n, visual=False, device=dev, dynamics_kwargs=dict(DYN), seed=142 + rank,
@@ -644,14 +666,18 @@ def run_ours(args):
         e2e_step(i)
     # three consecutive K-step brackets (barrier + synchronize on both sides, max over ranks), the median is reported:
     # this loop is one host thread ping-ponging with the GPU, and a single bracket has been seen 20 % off
-    e2e_brackets = []
+    e2e_brackets, e2e_dev = [], []
     for _ in range(3):
         barrier()
+        x0, x1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
+        x0.record(stream)
         for i in range(K):
             e2e_step(i)
+        x1.record(stream)
         th.cuda.synchronize()
         e2e_brackets.append(time.perf_counter() - t0)
+        e2e_dev.append(x0.elapsed_time(x1))
     e2e_all = th.tensor(e2e_brackets, device=dev, dtype=th.float64)
     if world > 1:
         dist.all_reduce(e2e_all, op=dist.ReduceOp.MAX)
@@ -660,10 +686,14 @@ def run_ours(args):
            "d2h_bytes_per_step": n * (13 * 4 + 4 + 4), "ms_per_step": 1e3 * float(e2e_s) / K,
            "bracket_ms": [1e3 * float(x) for x in e2e_all],
            "api": "HoverEnv(tensor_output=False).step(numpy actions) -> numpy obs/reward/done",
-           "kernel_with_host_mirror_us": km_avg * 1e6,
+           "kernel_with_host_mirror_us": km_avg * 1e6, "kernel_with_mirror_and_flag_us": kmf_avg * 1e6,
+           "kernel_with_mirror_and_flag_back_to_back_us": kmf_b2b * 1e6, "bracket_device_ms_rank0": e2e_dev,
+           "launches_in_bracket": "K handed out + 1 running ahead (the engine launches step t+1 before it hands out "
+                                  "step t; the bracket's closing synchronize waits for it)",
            "pcie_write_gbs_of_that_kernel": n * (13 * 4 + 4 + 4) / km_avg / 1e9,
            "transfers": "H2D: async DMA of the page-locked action array; D2H: the kernel stores obs/reward/done "
-                        "straight into page-locked host memory (zero-copy over PCIe), one stream sync per step"}
+                        "straight into page-locked host memory (zero-copy over PCIe); its last thread block raises a "
+                        "page-locked completion word the host spins on (no stream synchronisation per step)"}
 
     # ---- config[2]: APG-style analytic policy gradient through NavigationEnv (requires_grad=True) -----------------
     apg = None if args.no_apg else apg_benchmark(n, dev, rank, world, barrier)

@@ -332,7 +332,11 @@ VF_HD void euler_to_quat(const float e[3], float q[4]) {
 }
 
 // Fresh initial state of one agent (position, quaternion, velocity, body rates).
-VF_HD void sample_reset(const VfEnvSpec& E, unsigned agent, unsigned long long step, const float* table_row,
+// Deliberately NOT inlined on the device: an agent restarts once per episode (one step in a few hundred), while the
+// sampler — ten Philox rounds per draw, Box-Muller with the slow paths of logf / cosf — is a third of the env
+// kernel's code.  Kept out of line, the per-step path stays contiguous in the instruction cache and keeps its
+// registers.
+VF_HD_COLD void sample_reset(const VfEnvSpec& E, unsigned agent, unsigned long long step, const float* table_row,
                         float p[3], float q[4], float v[3], float w[3]) {
     if (E.gen_kind == VF_GEN_TABLE) {
         for (int j = 0; j < 3; ++j) { p[j] = table_row[j]; v[j] = table_row[7 + j]; w[j] = table_row[10 + j]; }

@@ -332,8 +332,13 @@ vf_env_step_fwd_kernel(const __grid_constant__ VfParams params, const __grid_con
                 passed = 0;
             }
             const unsigned long long step = step_index + (step_base ? *step_base : 0ull);
+            // out-of-line call (see sample_reset): results come back through temporaries so that the state itself
+            // never has its address taken and stays in registers on the per-step path
+            float rp[3], rq[4], rv[3], rw[3];
             vf::sample_reset(E, E.agent_offset + unsigned(i), step, reset_table ? reset_table + size_t(i) * 13 : nullptr,
-                             s.p, s.q, s.v, s.w);
+                             rp, rq, rv, rw);
+            for (int j = 0; j < 3; ++j) { s.p[j] = rp[j]; s.v[j] = rv[j]; s.w[j] = rw[j]; }
+            for (int j = 0; j < 4; ++j) s.q[j] = rq[j];
             for (int j = 0; j < 4; ++j) s.mot[j] = E.init_motor_omega;
             s.al[0] = s.al[1] = s.al[2] = 0.f;
             sc = 0; ret = 0.f; ep_done = false; once = false;

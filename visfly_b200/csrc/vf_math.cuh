@@ -30,8 +30,10 @@
 
 #if defined(__CUDACC__)
 #define VF_HD __host__ __device__ __forceinline__
+#define VF_HD_COLD __host__ __device__ __noinline__
 #else
 #define VF_HD inline
+#define VF_HD_COLD inline
 #endif
 
 #if !defined(__CUDACC__)
