@@ -50,6 +50,9 @@ L2_FLUSH_BYTES = 256 << 20
 REPLICAS = 16                 # env copies rotated in the timed loop: 16 x ~17 MB per step > 126 MB L2
 BRACKETS = 5                  # consecutive K-step brackets; value = the median one
 HOT_PREROLL = 600             # untimed back-to-back steps before the bracketed loop (host clock ramp, see run_ours)
+E2E_PREROLL = 400             # untimed numpy-mode steps before the e2e brackets: the zero-copy PCIe write rate of the
+                              # first ~20 ms after an idle period is 20-25 % below its steady state (measured: brackets
+                              # of 200 steps took 24.5 / 20.8 / 19.9 ms in a row)
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -662,7 +665,7 @@ def run_ours(args):
         sink[1] += float(obs["state"][0, 2]) + float(obs["state"][-1, 2])
         sink[2] += int(done[0]) + int(done[-1])
 
-    for i in range(W):
+    for i in range(max(W, E2E_PREROLL)):
         e2e_step(i)
     # three consecutive K-step brackets (barrier + synchronize on both sides, max over ranks), the median is reported:
     # this loop is one host thread ping-ponging with the GPU, and a single bracket has been seen 20 % off
@@ -696,7 +699,18 @@ def run_ours(args):
                         "page-locked completion word the host spins on (no stream synchronisation per step)"}
 
     # ---- config[2]: APG-style analytic policy gradient through NavigationEnv (requires_grad=True) -----------------
-    apg = None if args.no_apg else apg_benchmark(n, dev, rank, world, barrier)
+    apg = None
+    if not args.no_apg:
+        try:
+            apg = apg_benchmark(n, dev, rank, world, barrier, graph=True)      # whole update replayed as one CUDA graph
+        except Exception as e:  # noqa: BLE001 - fall back to the eager update rather than lose the leg
+            apg = {"graph_error": repr(e)[:300]}
+        eager = apg_benchmark(n, dev, rank, world, barrier, graph=False)
+        if "value" in apg:
+            apg["eager"] = {k: eager[k] for k in ("value", "ms_per_update")}
+        else:
+            eager.update(apg)
+            apg = eager
 
     racing = None if args.no_racing else racing_leg(n, dev, rank, world, K, W, stream, barrier)
     clk.__exit__(None, None, None)
@@ -740,7 +754,7 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def apg_benchmark(n, dev, rank, world, barrier, H=32, rollouts=5, gamma=0.99):
+def apg_benchmark(n, dev, rank, world, barrier, H=32, rollouts=5, gamma=0.99, graph=True):
     """BPTT updates (reference utils/algorithms/BPTT.py:107-134) through visfly_b200.algorithms.BPTT: H steps with grad
     through NavigationEnv, loss = -sum discount_t r_t, backward, gradient all-reduce over the ranks, Adam step,
     env.detach().  Forward = one fused env-step launch per step, backward = one adjoint launch per step; the policy
@@ -753,8 +767,8 @@ def apg_benchmark(n, dev, rank, world, barrier, H=32, rollouts=5, gamma=0.99):
                         random_kwargs={"state_generator": {"class": "Uniform", "kwargs": [
                             {"position": {"mean": [2., 0., 1.5], "half": [1.0, 1.0, 0.5]}}]}})
     algo = BPTT(env, horizon=H, gamma=gamma, learning_rate=1e-3, policy_kwargs=dict(net_arch=[64, 64]), seed=0,
-                make_eval_env=False, dump_step=1 << 62)
-    algo.learn(total_timesteps=2 * n * H)                      # warm-up: two updates
+                make_eval_env=False, dump_step=1 << 62, cuda_graph=graph)
+    algo.learn(total_timesteps=(4 if graph else 2) * n * H)   # warm-up (graph: eager update, side-stream warm-up, capture)
     barrier()
     e0, e1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
@@ -770,7 +784,8 @@ def apg_benchmark(n, dev, rank, world, barrier, H=32, rollouts=5, gamma=0.99):
                         "H=32 (visfly_b200.algorithms.BPTT, MLP 16-64-64-4 policy, grad all-reduce over ranks)",
             "value": world * n * H * rollouts / (float(ms) * 1e-3), "unit": UNIT + " (fwd+bwd+update)",
             "ms_per_update": float(ms) / rollouts, "horizon": H, "weights_finite": finite,
-            "fused": bool(env._fused is not None and env._fused.active)}
+            "fused": bool(env._fused is not None and env._fused.active),
+            "cuda_graph": bool(graph and algo._graph is not None)}
 
 
 def env_launches_per_step(env) -> int:

@@ -27,14 +27,100 @@ class BPTT(AnalyticGradientBase):
             discount = discount * self.gamma * ~done + done
         return actor_loss.mean()
 
+    # -- the whole update as one CUDA graph -------------------------------------------------------------------------
+    # What makes an update replayable: (i) everything that carries over from one update to the next — packed state,
+    # env status records, the comm-delay FIFO, the last observation — lives in fixed holder tensors that the graph
+    # reads first and overwrites last; (ii) the in-kernel restart sampler takes its step number from a device word
+    # (VfEnvSpec step_base) that the graph itself advances by H, so every replay draws fresh restarts; (iii) the
+    # optimiser is constructed with capturable=True; (iv) nothing in the horizon synchronises with the host (lazy info
+    # records, no .item()).  torch's generator (policy noise) is graph-safe by itself.
+    def _holders_from_env(self):
+        dyn, fz = self.env.envs.dynamics, self.env._fused
+        self._g_state = dyn._state.detach().clone()
+        self._g_status = fz.status.clone()
+        self._g_fifo = [a.detach().clone() for a in dyn._pre_action]
+        self._g_obs = None if dyn._obs_t is None else dyn._obs_t.detach().clone()
+
+    def _env_to_holders(self):
+        """Point the env at the holder tensors (start of an update)."""
+        dyn, fz = self.env.envs.dynamics, self.env._fused
+        dyn._state, fz.status = self._g_state, self._g_status
+        dyn._pre_action = list(self._g_fifo)
+        dyn._obs_t = self._g_obs
+
+    def _holders_from_outputs(self):
+        """Copy what the update left in the env back into the holders (end of an update, inside the graph)."""
+        dyn, fz = self.env.envs.dynamics, self.env._fused
+        self._g_state.copy_(dyn._state)
+        self._g_status.copy_(fz.status)
+        for h, a in zip(self._g_fifo, dyn._pre_action):
+            h.copy_(a)
+        if self._g_obs is not None:
+            self._g_obs.copy_(dyn._obs_t)
+        fz.step_base.add_(self.H)
+
+    def _one_update(self):
+        loss = self.rollout_loss()
+        self._actor_update(loss)
+        self.env.detach()
+        return loss.detach()
+
+    def _capture(self):
+        env = self.env
+        fz, dyn = env._fused, env.envs.dynamics
+        if fz is None or not fz.active or not fz.refresh():
+            raise RuntimeError("cuda_graph=True needs the one-kernel env step (built-in task, fused path active)")
+        if fz.t_off is not None or dyn._wind_fn is not None:
+            raise NotImplementedError("cuda_graph=True with per-agent time offsets / wind functions")
+        # from here on the restart sampler's step number is (host counter) + (device word); the device word takes over
+        # the count so far, so that numbers stay unique across eager steps, warm-up updates and replays
+        fz.step_base = th.full((1,), int(fz.global_step), dtype=th.int64, device=self.device)
+        fz.global_step = 0
+        fz._stepper = None                                    # re-bound with the step-base word
+        self._holders_from_env()
+        main = th.cuda.current_stream(self.device)
+        side = th.cuda.Stream(self.device)
+        side.wait_stream(main)
+        with th.cuda.stream(side):                            # warm-up on a side stream, as graph capture wants it
+            for _ in range(2):
+                self._env_to_holders()
+                self._one_update()
+                self._holders_from_outputs()
+        main.wait_stream(side)
+        th.cuda.synchronize(self.device)
+        steps0 = self.num_timesteps
+        graph = th.cuda.CUDAGraph()
+        self.actor.optimizer.zero_grad(set_to_none=True)
+        self._env_to_holders()
+        with th.cuda.graph(graph):
+            self._g_loss = self._one_update()
+            self._holders_from_outputs()
+        self._g_steps = self.num_timesteps - steps0           # time steps one replay stands for
+        self.num_timesteps = steps0                           # the capture pass itself computed nothing
+        self._graph = graph
+
+    def _replay(self):
+        self._graph.replay()
+        self.num_timesteps += self._g_steps
+        self.env.envs.dynamics._n_steps += self.H
+        return self._g_loss
+
     def learn(self, total_timesteps: int):
         assert self.H >= 1, "horizon must be at least 1"
         self.policy.train()
         start, last_dump, t0 = self.num_timesteps, self.num_timesteps, time.time()
         while self.num_timesteps - start < total_timesteps:
-            actor_loss = self.rollout_loss()
-            self._actor_update(actor_loss)
-            self.env.detach()
+            if self.cuda_graph:
+                if self._graph is None:
+                    if not (self.env._fused is not None and self.env._fused.active):
+                        actor_loss = self._one_update()       # the first eager update switches the env to the fused path
+                        continue
+                    self._capture()
+                actor_loss = self._replay()
+            else:
+                actor_loss = self.rollout_loss()
+                self._actor_update(actor_loss)
+                self.env.detach()
             if self.num_timesteps - last_dump >= self._dump_step:
                 rec = {"timesteps": self.num_timesteps, "actor_loss": float(actor_loss),
                        "fps": (self.num_timesteps - last_dump) / max(time.time() - t0, 1e-9)}

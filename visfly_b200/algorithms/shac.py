@@ -38,7 +38,7 @@ class AnalyticGradientBase:
                  gamma: float = 0.99, gradient_steps: int = 5, buffer_size: int = int(1e6),
                  batch_size: int = int(2e5), clip_range_vf: float = 0.1, pre_stop: float = 0.1,
                  policy_noise: float = 0., device=None, seed: int = 42, max_grad_norm: float = 0.5,
-                 make_eval_env: bool = True, verbose: int = 0):
+                 make_eval_env: bool = True, verbose: int = 0, cuda_graph: bool = False):
         self.env = env
         self.device = th.device(device) if device is not None else env.device
         self.num_envs = env.num_envs
@@ -47,12 +47,19 @@ class AnalyticGradientBase:
         self.gradient_steps, self.max_grad_norm = gradient_steps, max_grad_norm
         self.policy_noise, self._dump_step, self.verbose = policy_noise, dump_step, verbose
         self.learning_rate, self.comment, self.save_path = learning_rate, comment, save_path
+        #: replay a whole update (horizon forward, backward, gradient exchange, optimiser step) as ONE CUDA graph: an
+        #: update is ~80 small launches per env step and is otherwise bound by the host side of those launches
+        self.cuda_graph = bool(cuda_graph)
+        self._graph = None
         th.manual_seed(seed)
         if isinstance(policy, th.nn.Module):
             self.policy = policy.to(self.device)
         else:
+            policy_kwargs = dict(policy_kwargs or {})
+            if self.cuda_graph:           # optimiser state (step counters) must live on the device to be replayable
+                policy_kwargs["optimizer_kwargs"] = dict(policy_kwargs.get("optimizer_kwargs") or {}, capturable=True)
             self.policy = ActorCritic(self.observation_space, self.action_space, learning_rate=learning_rate,
-                                      **(policy_kwargs or {})).to(self.device)
+                                      **policy_kwargs).to(self.device)
         broadcast_parameters(self.policy)
         self.actor, self.critic, self.critic_target = self.policy.actor, self.policy.critic, self.policy.critic_target
         self.eval_env = None
