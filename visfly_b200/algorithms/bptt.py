@@ -74,6 +74,10 @@ class BPTT(AnalyticGradientBase):
             raise NotImplementedError("cuda_graph=True with per-agent time offsets / wind functions")
         # from here on the restart sampler's step number is (host counter) + (device word); the device word takes over
         # the count so far, so that numbers stay unique across eager steps, warm-up updates and replays
+        import gc
+        self.actor.optimizer.zero_grad(set_to_none=True)
+        env.detach()
+        gc.collect()            # no autograd graph of an earlier (default-stream) update may survive into the capture
         fz.step_base = th.full((1,), int(fz.global_step), dtype=th.int64, device=self.device)
         fz.global_step = 0
         fz._stepper = None                                    # re-bound with the step-base word

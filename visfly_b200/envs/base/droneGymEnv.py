@@ -507,6 +507,8 @@ class DroneGymEnvsBase(VecEnv):
         self._reward = self._reward.detach()
         self._action = self._action.detach()
         self._obs_tensors = self._obs_tensors.detach()
+        if isinstance(self._observations, TensorDict) and self.tensor_output:
+            self._observations = self._obs_tensors      # the dict handed out last must not keep the old graph alive
 
     # -- task interface ---------------------------------------------------------------------------------------
     def get_done(self):
