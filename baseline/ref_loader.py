@@ -213,3 +213,101 @@ def load_reference_envs():
 
     _state["envs"] = {"HoverEnv": HoverEnv, "NavigationEnv": NavigationEnv, "RacingEnv2": RacingEnv2}
     return _state["envs"]
+
+
+# ---------------------------------------------------------------------------------------------------
+# the reference's own analytic-gradient trainers (utils/algorithms/BPTT.py, shac.py), stable-baselines3 stubbed
+# ---------------------------------------------------------------------------------------------------
+def load_reference_algorithms():
+    """Import the reference's ``BPTT`` / ``shac`` trainer classes unmodified.
+
+    They sit on stable-baselines3 for logging, learning-rate schedules and the policy classes.  None of that is on
+    the path this repository replaces, and the package is not installed here, so the handful of names the two modules
+    import are provided as inert ``sys.modules`` stubs (a logger that records into a dict, ``get_schedule_fn`` for
+    constant rates, ``update_learning_rate``, ``polyak_update`` ...).  The trainer loops themselves —
+    ``BPTT.learn`` (BPTT.py:77-180), ``TemporalDifferBase.__init__/_build`` (shac.py:53-136) — run as written, on
+    whatever env object they are given; the policy is passed in as a class (``_create_policy``, shac.py:156-175)."""
+    if "algos" in _state:
+        return _state["algos"]
+    import types
+
+    load_reference_envs()                       # gymnasium / vec_env stubs, VisFly package on sys.path
+
+    def mod(name, **attrs):
+        m = sys.modules.get(name) or types.ModuleType(name)
+        m.__dict__.update(attrs)
+        sys.modules[name] = m
+        return m
+
+    class Logger:
+        def __init__(self):
+            self.values, self.dumps = {}, []
+
+        def record(self, key, value, **_):
+            self.values[key] = value
+
+        def dump(self, step=0):
+            self.dumps.append((step, dict(self.values)))
+
+    def configure(folder=None, format_strings=None):
+        return Logger()
+
+    def get_schedule_fn(value):
+        return value if callable(value) else (lambda _progress: float(value))
+
+    def update_learning_rate(optimizer, lr):
+        for group in optimizer.param_groups:
+            group["lr"] = lr
+
+    def safe_mean(xs):
+        xs = [float(x) for x in xs]
+        return sum(xs) / len(xs) if xs else float("nan")
+
+    def polyak_update(params, target_params, tau):
+        with th.no_grad():
+            for p, t in zip(params, target_params):
+                t.mul_(1 - tau).add_(p, alpha=tau)
+
+    def get_parameters_by_name(model, included_names):
+        return [p for n, p in model.state_dict().items() if any(k in n for k in included_names)]
+
+    class _Anything:                            # names that are only used in annotations / never on this path
+        def __init__(self, *a, **k):
+            pass
+
+    for name in ("Space", "Discrete", "MultiDiscrete", "MultiBinary"):      # annotations in utils/algorithms/common.py
+        sys.modules["gymnasium.spaces"].__dict__.setdefault(name, _Anything)
+    sb3 = mod("stable_baselines3")
+    common = mod("stable_baselines3.common")
+    sb3.common = common
+    common.logger = mod("stable_baselines3.common.logger", Logger=Logger, configure=configure)
+    mod("stable_baselines3.common.type_aliases", Schedule=object, RolloutBufferSamples=_Anything,
+        DictRolloutBufferSamples=_Anything, ReplayBufferSamples=_Anything, DictReplayBufferSamples=_Anything)
+    mod("stable_baselines3.common.utils", get_schedule_fn=get_schedule_fn, safe_mean=safe_mean,
+        update_learning_rate=update_learning_rate, polyak_update=polyak_update,
+        get_parameters_by_name=get_parameters_by_name)
+    mod("stable_baselines3.common.buffers", BaseBuffer=_Anything)
+    sys.modules["stable_baselines3.common.vec_env"].__dict__.setdefault("VecNormalize", _Anything)
+    mod("stable_baselines3.sac")
+    mod("stable_baselines3.sac.policies", MultiInputPolicy=_Anything)
+    gym = mod("gym")
+    gym.vector = mod("gym.vector")
+    gym.vector.utils = mod("gym.vector.utils", spaces=sys.modules["gymnasium.spaces"])
+    mod("VisFly.utils.policies")
+    mod("VisFly.utils.policies.td_policies", CnnPolicy=_Anything, BasePolicy=_Anything, MultiInputPolicy=_Anything)
+    mod("VisFly.utils.test")
+    mod("VisFly.utils.test.debug", get_network_statistics=lambda *a, **k: None,
+        check_none_parameters=lambda *a, **k: None)
+    for absent in ("cv2", "matplotlib", "matplotlib.pyplot"):        # imported by VisFly/utils/common.py (set_seed)
+        if absent not in sys.modules:
+            try:
+                __import__(absent)
+            except Exception:
+                mod(absent)
+    if not hasattr(sys.modules["matplotlib"], "pyplot"):
+        sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+
+    from VisFly.utils.algorithms.BPTT import BPTT           # noqa
+    from VisFly.utils.algorithms.shac import shac           # noqa
+    _state["algos"] = {"BPTT": BPTT, "shac": shac}
+    return _state["algos"]

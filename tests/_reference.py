@@ -14,6 +14,6 @@ _ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if _ROOT not in sys.path:
     sys.path.insert(0, _ROOT)
 
-from baseline.ref_loader import (REFERENCE_ROOT, default_dtype, load_reference, load_reference_envs,  # noqa: E402,F401
-                                 make_reference_dynamics, reference_available, reference_on_device,
-                                 reference_origin)
+from baseline.ref_loader import (REFERENCE_ROOT, default_dtype, load_reference, load_reference_algorithms,  # noqa: E402,F401
+                                 load_reference_envs, make_reference_dynamics, reference_available,
+                                 reference_on_device, reference_origin)

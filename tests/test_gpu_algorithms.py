@@ -94,3 +94,51 @@ def test_bptt_update_replayed_as_a_cuda_graph_equals_the_eager_update():
                       env.envs.dynamics.packed_state.detach().clone(), env._step_count.clone())
     assert th.allclose(out[True][0], out[False][0], atol=2e-5, rtol=1e-4)
     assert th.allclose(out[True][1], out[False][1], atol=1e-4, rtol=1e-4) and th.equal(out[True][2], out[False][2])
+
+
+@pytest.mark.parametrize("task", ["hover", "navigation"])
+def test_bptt_rollout_loss_and_policy_gradient_match_autograd_through_the_env_oracle(task):
+    """n3 parity against the ORACLE, not against ourselves: `BPTT.rollout_loss` on the GPU env (one fused launch per
+    step forward, one adjoint launch per step backward) versus the same horizon written out on the float64 CPU
+    restatement of the reference env (`oracle/env_oracle.py`) with a float64 copy of the same policy: the loss and the
+    gradient of every policy parameter.  Auto-resets happen inside the horizon (max_episode_steps < H)."""
+    import copy as _copy
+    from oracle.env_oracle import OracleEnv
+    from visfly_b200.algorithms import BPTT
+    from visfly_b200.algorithms.policies import flatten_obs
+    from visfly_b200.envs import HoverEnv, NavigationEnv
+    n, H, gamma = 192, 12, 0.99
+    g = th.Generator().manual_seed(21)
+    pos = th.stack([th.rand(n, generator=g) * 6 + 1, th.rand(n, generator=g) * 4 - 2, th.rand(n, generator=g) + 1], 1)
+    quat = th.nn.functional.normalize(th.tensor([[1.0, 0, 0, 0]]) + 0.05 * th.randn(n, 4, generator=g), dim=1)
+    vel, rate = 0.3 * th.randn(n, 3, generator=g), 0.2 * th.randn(n, 3, generator=g)
+    dyn = dict(DYN["rk4"], comm_delay=0.04)
+    cls = HoverEnv if task == "hover" else NavigationEnv
+    kw = dict(tensor_output=True) if task == "hover" else {}
+    env = cls(num_agent_per_scene=n, visual=False, device="cuda", requires_grad=True, max_episode_steps=7,
+              dynamics_kwargs=dict(dyn), **kw)
+    env.envs.set_reset_table(pos.cuda(), quat.cuda(), vel.cuda(), rate.cuda())
+    algo = BPTT(env, horizon=H, gamma=gamma, policy_kwargs=dict(net_arch=[32, 32]), seed=9, make_eval_env=False)
+    loss = algo.rollout_loss()
+    assert env._fused is not None and env._fused.active
+    algo.actor.optimizer.zero_grad()
+    loss.backward()
+    grads = [p.grad.detach().cpu().double() for p in algo.actor.parameters() if p.grad is not None]
+
+    actor64 = _copy.deepcopy(algo.actor).cpu().double()
+    table = tuple(x.double() for x in (pos, quat, vel, rate))
+    orc = OracleEnv(task, n, dict(dyn), max_episode_steps=7, requires_grad=True, dtype=th.float64, faithful_rng=False,
+                    generate_state=lambda idx=None: table if idx is None else tuple(x[th.as_tensor(idx)] for x in table))
+    obs = orc.reset()
+    ref_loss, discount = 0.0, th.ones(n, dtype=th.float64)
+    for _ in range(H):
+        act, _, _ = actor64.action_log_prob(flatten_obs({k: v.double() for k, v in obs.items()}), noise_scale=0.0)
+        obs, r, d, info = orc.step(act.clip(-1, 1))
+        ref_loss = ref_loss - r * discount
+        discount = discount * gamma * ~d + d
+    ref_loss = ref_loss.mean()
+    ref_grads = th.autograd.grad(ref_loss, [p for p in actor64.parameters()], allow_unused=True)
+    ref_grads = [gr for gr in ref_grads if gr is not None]
+    assert abs(float(loss) - float(ref_loss)) < 1e-5 * max(1.0, abs(float(ref_loss)))
+    assert len(grads) == len(ref_grads)
+    assert rel_l2(th.cat([x.reshape(-1) for x in grads]), th.cat([x.reshape(-1) for x in ref_grads])) < 1e-4
