@@ -105,7 +105,6 @@ def test_bptt_rollout_loss_and_policy_gradient_match_autograd_through_the_env_or
     import copy as _copy
     from oracle.env_oracle import OracleEnv
     from visfly_b200.algorithms import BPTT
-    from visfly_b200.algorithms.policies import flatten_obs
     from visfly_b200.envs import HoverEnv, NavigationEnv
     n, H, gamma = 192, 12, 0.99
     g = th.Generator().manual_seed(21)
@@ -132,7 +131,8 @@ def test_bptt_rollout_loss_and_policy_gradient_match_autograd_through_the_env_or
     obs = orc.reset()
     ref_loss, discount = 0.0, th.ones(n, dtype=th.float64)
     for _ in range(H):
-        act, _, _ = actor64.action_log_prob(flatten_obs({k: v.double() for k, v in obs.items()}), noise_scale=0.0)
+        flat = th.cat([obs[k].double() for k in sorted(obs.keys())], dim=-1)       # flatten_obs, kept in float64
+        act, _, _ = actor64.action_log_prob(flat, noise_scale=0.0)
         obs, r, d, info = orc.step(act.clip(-1, 1))
         ref_loss = ref_loss - r * discount
         discount = discount * gamma * ~d + d
