@@ -40,6 +40,11 @@ SIGNATURES = {
     "vf_export_pose_habitat": (_i, [_P(VfParams), _i, _vp, _vp, _vp, _vp]),
     "vf_env_spec_size": (_i, []),
     "vf_wait_flag": (_i, [_vp, _u, ctypes.c_longlong]),
+    "vf_policy_fwd": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_float, ctypes.c_float, _vp, _vp]),
+    "vf_policy_bwd": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_float, ctypes.c_float, _vp, _vp,
+                           _vp, _vp, _vp]),
+    "vf_policy_partial_floats": (_i, [_i, _i, _i]),
+    "vf_policy_last_error": (ctypes.c_char_p, []),
     "vf_env_step_fwd": (_i, [_P(VfParams), _P(VfEnvSpec), _i, _i, _i, _i, _u, _u, ctypes.c_ulonglong, _vp,
                              _vp, _vp, _vp, _vp, _vp, _vp,
                              _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
@@ -284,3 +289,36 @@ def export_pose_habitat(params: VfParams, state: th.Tensor, pose_out: th.Tensor,
     with th.cuda.device(state.device):
         _check(lib.vf_export_pose_habitat(ctypes.byref(params), n, _dev_ptr(state, "state"), pose_out.data_ptr(),
                                           None if vel_out is None else vel_out.data_ptr(), _stream(state.device)))
+
+
+def _policy_check(rc: int):
+    if rc != 0:
+        raise RuntimeError("visfly_b200: " + load().vf_policy_last_error().decode())
+
+
+def policy_fwd(x: th.Tensor, params, lo: float, hi: float) -> th.Tensor:
+    """Binding of ``vf_policy_fwd``: ``params`` = (W1, b1, W2, b2, W3, b3) contiguous float32 CUDA tensors."""
+    lib = load(require_cuda=True)
+    n, d = x.shape
+    h = params[0].shape[0]
+    action = th.empty((n, 4), dtype=th.float32, device=x.device)
+    with th.cuda.device(x.device):
+        _policy_check(lib.vf_policy_fwd(n, d, h, _dev_ptr(x, "x"), *[_dev_ptr(p, "param") for p in params],
+                                        float(lo), float(hi), action.data_ptr(), _stream(x.device)))
+    return action
+
+
+def policy_bwd(x: th.Tensor, params, lo: float, hi: float, g_action: th.Tensor, want_gx: bool):
+    """Binding of ``vf_policy_bwd``: returns ``(grad_x | None, flat parameter gradients)``."""
+    lib = load(require_cuda=True)
+    n, d = x.shape
+    h = params[0].shape[0]
+    g_x = th.empty_like(x) if want_gx else None
+    partial = th.empty((lib.vf_policy_partial_floats(n, d, h),), dtype=th.float32, device=x.device)
+    flat = th.empty((h * d + h + h * h + h + 4 * h + 4,), dtype=th.float32, device=x.device)
+    with th.cuda.device(x.device):
+        _policy_check(lib.vf_policy_bwd(n, d, h, _dev_ptr(x, "x"), *[_dev_ptr(p, "param") for p in params],
+                                        float(lo), float(hi), _dev_ptr(g_action, "grad_action"),
+                                        None if g_x is None else g_x.data_ptr(), partial.data_ptr(), flat.data_ptr(),
+                                        _stream(x.device)))
+    return g_x, flat

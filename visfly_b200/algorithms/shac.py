@@ -72,11 +72,16 @@ class AnalyticGradientBase:
         self.rollout_buffer = RolloutBuffer(gamma=gamma)
         self._lo = th.as_tensor(self.action_space.low, device=self.device)
         self._hi = th.as_tensor(self.action_space.high, device=self.device)
+        lo, hi = self._lo.flatten().tolist(), self._hi.flatten().tolist()
+        #: (low, high) as plain floats when the action box is the same in every dimension (it is: Box(-1, 1, (4,)))
+        self._scalar_bounds = (lo[0], hi[0]) if len(set(lo)) == 1 and len(set(hi)) == 1 else None
         self.history: List[Dict[str, float]] = []
         self.num_timesteps = 0
 
     # -- pieces shared by SHAC and BPTT ---------------------------------------------------------------------
     def _act(self, obs):
+        if self.policy_noise == 0 and self._scalar_bounds is not None and hasattr(self.actor, "deterministic_action"):
+            return self.actor.deterministic_action(obs, *self._scalar_bounds)      # one launch where supported
         actions, _, _ = self.actor.action_log_prob(obs, noise_scale=self.policy_noise)
         return th.clip(actions, self._lo, self._hi)
 
