@@ -350,17 +350,21 @@ int vf_env_step_bwd(const VfParams* params, const VfEnvSpec* spec, int n, int su
  * reference's BPTT / SHAC loops evaluate once per env step (utils/algorithms/BPTT.py:107-115, shac.py:213-222)
  *     action = clip(tanh(W3 tanh(W2 tanh(W1 x + b1) + b2) + b3), lo, hi)      x (n, d <= 32), hidden h in {32, 64}
  * forward and backward as one launch each (csrc/vf_policy.cu) instead of ~40 library launches per env step.
+ * The observation may be handed over in two row-major pieces x = [xa (n, da) | xb (n, db)], d = da + db (the obs dict
+ * of NavigationEnv is {state (n,13), target (n,3)}; no concatenated copy is made); db = 0, xb = NULL for one piece.
  * All weights row-major like torch.nn.Linear (W1 (h, d), W2 (h, h), W3 (4, h)); fp32.
- *   vf_policy_bwd: grad_x (n, d) may be NULL; `partial` is scratch of vf_policy_partial_floats(n, d, h) floats;
- *   grad_params receives [dW1 (h,d) | db1 (h) | dW2 (h,h) | db2 (h) | dW3 (4,h) | db3 (4)] (overwritten, summed over
- *   agents in a fixed order: bit-reproducible).  Nothing is saved between the two calls: the backward recomputes the
- *   activations from x.
+ *   vf_policy_bwd: grad_xa (n, da) / grad_xb (n, db) may each be NULL; `partial` is scratch of
+ *   vf_policy_partial_floats(n, d, h) floats; grad_params receives
+ *   [dW1 (h,d) | db1 (h) | dW2 (h,h) | db2 (h) | dW3 (4,h) | db3 (4)] (overwritten, summed over agents in a fixed
+ *   order: bit-reproducible).  Nothing is saved between the two calls: the backward recomputes the activations.
  * ===================================================================================================== */
-int vf_policy_fwd(int n, int d, int h, const float* x, const float* w1, const float* b1, const float* w2,
-                  const float* b2, const float* w3, const float* b3, float lo, float hi, float* action, void* stream);
-int vf_policy_bwd(int n, int d, int h, const float* x, const float* w1, const float* b1, const float* w2,
-                  const float* b2, const float* w3, const float* b3, float lo, float hi, const float* grad_action,
-                  float* grad_x, float* partial, float* grad_params, void* stream);
+int vf_policy_fwd(int n, int da, int db, int h, const float* xa, const float* xb, const float* w1, const float* b1,
+                  const float* w2, const float* b2, const float* w3, const float* b3, float lo, float hi,
+                  float* action, void* stream);
+int vf_policy_bwd(int n, int da, int db, int h, const float* xa, const float* xb, const float* w1, const float* b1,
+                  const float* w2, const float* b2, const float* w3, const float* b3, float lo, float hi,
+                  const float* grad_action, float* grad_xa, float* grad_xb, float* partial, float* grad_params,
+                  void* stream);
 int vf_policy_partial_floats(int n, int d, int h);
 const char* vf_policy_last_error(void);
 

@@ -31,6 +31,13 @@ def test_fused_actor_matches_the_library_ops(n, d, h):
     params64 = [p for p in actor64.parameters() if p is not actor64.log_std]
     grads64 = th.autograd.grad((ref64 * g.double()).sum(), [x64] + params64)
     assert rel_l2(a.detach().cpu(), ref64.detach().cpu()) < 2e-6
+    if d > 3:               # the same observation handed over as a dict of two pieces: identical results, no cat
+        xa = x.detach()[:, :d - 3].contiguous().requires_grad_(True)
+        xb = x.detach()[:, d - 3:].contiguous().requires_grad_(True)
+        a2 = actor.deterministic_action({"a_first": xa, "b_second": xb}, -1.0, 1.0)
+        g2 = th.autograd.grad((a2 * g).sum(), [xa, xb] + params)
+        assert th.equal(a2, a) and th.equal(th.cat([g2[0], g2[1]], 1), grads[0])
+        assert all(th.equal(u, v) for u, v in zip(g2[2:], grads[1:]))
     for got, r32, r64 in zip(grads, grads32, grads64):
         err, floor = rel_l2(got.cpu(), r64.cpu()), rel_l2(r32.cpu(), r64.cpu())
         assert err < max(5e-6, 3 * floor), (tuple(got.shape), err, floor)

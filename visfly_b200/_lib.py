@@ -40,9 +40,10 @@ SIGNATURES = {
     "vf_export_pose_habitat": (_i, [_P(VfParams), _i, _vp, _vp, _vp, _vp]),
     "vf_env_spec_size": (_i, []),
     "vf_wait_flag": (_i, [_vp, _u, ctypes.c_longlong]),
-    "vf_policy_fwd": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_float, ctypes.c_float, _vp, _vp]),
-    "vf_policy_bwd": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_float, ctypes.c_float, _vp, _vp,
-                           _vp, _vp, _vp]),
+    "vf_policy_fwd": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_float, ctypes.c_float,
+                           _vp, _vp]),
+    "vf_policy_bwd": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_float, ctypes.c_float,
+                           _vp, _vp, _vp, _vp, _vp, _vp]),
     "vf_policy_partial_floats": (_i, [_i, _i, _i]),
     "vf_policy_last_error": (ctypes.c_char_p, []),
     "vf_env_step_fwd": (_i, [_P(VfParams), _P(VfEnvSpec), _i, _i, _i, _i, _u, _u, ctypes.c_ulonglong, _vp,
@@ -296,29 +297,36 @@ def _policy_check(rc: int):
         raise RuntimeError("visfly_b200: " + load().vf_policy_last_error().decode())
 
 
-def policy_fwd(x: th.Tensor, params, lo: float, hi: float) -> th.Tensor:
-    """Binding of ``vf_policy_fwd``: ``params`` = (W1, b1, W2, b2, W3, b3) contiguous float32 CUDA tensors."""
+def policy_fwd(xa: th.Tensor, xb: Optional[th.Tensor], params, lo: float, hi: float) -> th.Tensor:
+    """Binding of ``vf_policy_fwd``: observation pieces ``xa (n, da)`` [, ``xb (n, db)``], ``params`` =
+    (W1, b1, W2, b2, W3, b3), all contiguous float32 CUDA tensors."""
     lib = load(require_cuda=True)
-    n, d = x.shape
+    n, da = xa.shape
+    db = 0 if xb is None else xb.shape[1]
     h = params[0].shape[0]
-    action = th.empty((n, 4), dtype=th.float32, device=x.device)
-    with th.cuda.device(x.device):
-        _policy_check(lib.vf_policy_fwd(n, d, h, _dev_ptr(x, "x"), *[_dev_ptr(p, "param") for p in params],
-                                        float(lo), float(hi), action.data_ptr(), _stream(x.device)))
+    action = th.empty((n, 4), dtype=th.float32, device=xa.device)
+    with th.cuda.device(xa.device):
+        _policy_check(lib.vf_policy_fwd(n, da, db, h, _dev_ptr(xa, "xa"), _dev_ptr(xb, "xb"),
+                                        *[_dev_ptr(p, "param") for p in params], float(lo), float(hi),
+                                        action.data_ptr(), _stream(xa.device)))
     return action
 
 
-def policy_bwd(x: th.Tensor, params, lo: float, hi: float, g_action: th.Tensor, want_gx: bool):
-    """Binding of ``vf_policy_bwd``: returns ``(grad_x | None, flat parameter gradients)``."""
+def policy_bwd(xa: th.Tensor, xb: Optional[th.Tensor], params, lo: float, hi: float, g_action: th.Tensor,
+               want_ga: bool, want_gb: bool):
+    """Binding of ``vf_policy_bwd``: returns ``(grad_xa | None, grad_xb | None, flat parameter gradients)``."""
     lib = load(require_cuda=True)
-    n, d = x.shape
-    h = params[0].shape[0]
-    g_x = th.empty_like(x) if want_gx else None
-    partial = th.empty((lib.vf_policy_partial_floats(n, d, h),), dtype=th.float32, device=x.device)
-    flat = th.empty((h * d + h + h * h + h + 4 * h + 4,), dtype=th.float32, device=x.device)
-    with th.cuda.device(x.device):
-        _policy_check(lib.vf_policy_bwd(n, d, h, _dev_ptr(x, "x"), *[_dev_ptr(p, "param") for p in params],
-                                        float(lo), float(hi), _dev_ptr(g_action, "grad_action"),
-                                        None if g_x is None else g_x.data_ptr(), partial.data_ptr(), flat.data_ptr(),
-                                        _stream(x.device)))
-    return g_x, flat
+    n, da = xa.shape
+    db = 0 if xb is None else xb.shape[1]
+    d, h = da + db, params[0].shape[0]
+    g_a = th.empty_like(xa) if want_ga else None
+    g_b = th.empty_like(xb) if (want_gb and xb is not None) else None
+    partial = th.empty((lib.vf_policy_partial_floats(n, d, h),), dtype=th.float32, device=xa.device)
+    flat = th.empty((h * d + h + h * h + h + 4 * h + 4,), dtype=th.float32, device=xa.device)
+    with th.cuda.device(xa.device):
+        _policy_check(lib.vf_policy_bwd(n, da, db, h, _dev_ptr(xa, "xa"), _dev_ptr(xb, "xb"),
+                                        *[_dev_ptr(p, "param") for p in params], float(lo), float(hi),
+                                        _dev_ptr(g_action, "grad_action"), _dev_ptr(g_a, "grad_xa"),
+                                        _dev_ptr(g_b, "grad_xb"), partial.data_ptr(), flat.data_ptr(),
+                                        _stream(xa.device)))
+    return g_a, g_b, flat

@@ -97,28 +97,32 @@ def mlp(sizes: Sequence[int], activation: Type[nn.Module], out_activation: Optio
 class _FusedActorFn(th.autograd.Function):
     """``clip(tanh(W3 tanh(W2 tanh(W1 x + b1) + b2) + b3), lo, hi)`` as ONE launch forward (``vf_policy_fwd``) and one
     backward (``vf_policy_bwd`` + a fixed-order reduction of the per-tile weight gradients) instead of ~40 library
-    launches per env step; the backward recomputes the activations from ``x``, nothing else is saved."""
+    launches per env step.  ``x = [xa | xb]`` may arrive in two pieces (no concatenated copy); the backward recomputes
+    the activations from the inputs, nothing else is saved."""
 
     @staticmethod
-    def forward(ctx, x, lo, hi, w1, b1, w2, b2, w3, b3):
+    def forward(ctx, xa, xb, lo, hi, w1, b1, w2, b2, w3, b3):
         from .. import _lib
         params = tuple(p.contiguous() for p in (w1, b1, w2, b2, w3, b3))
-        x = x.contiguous()
-        ctx.save_for_backward(x, *params)
-        ctx.lo, ctx.hi = lo, hi
-        return _lib.policy_fwd(x, params, lo, hi)
+        xa = xa.contiguous()
+        xb = None if xb is None else xb.contiguous()
+        ctx.save_for_backward(xa, *params, *(() if xb is None else (xb,)))
+        ctx.lo, ctx.hi, ctx.two = lo, hi, xb is not None
+        return _lib.policy_fwd(xa, xb, params, lo, hi)
 
     @staticmethod
     @th.autograd.function.once_differentiable
     def backward(ctx, g_action):
         from .. import _lib
-        x, *params = ctx.saved_tensors
-        g_x, flat = _lib.policy_bwd(x, params, ctx.lo, ctx.hi, g_action.contiguous(), ctx.needs_input_grad[0])
+        saved = ctx.saved_tensors
+        xa, params, xb = saved[0], saved[1:7], (saved[7] if ctx.two else None)
+        g_a, g_b, flat = _lib.policy_bwd(xa, xb, params, ctx.lo, ctx.hi, g_action.contiguous(),
+                                         ctx.needs_input_grad[0], ctx.needs_input_grad[1])
         grads, off = [], 0
         for p in params:
             grads.append(flat[off:off + p.numel()].view_as(p))
             off += p.numel()
-        return (g_x, None, None, *grads)
+        return (g_a, g_b, None, None, *grads)
 
 
 class Actor(nn.Module):
@@ -146,13 +150,24 @@ class Actor(nn.Module):
 
     def deterministic_action(self, obs, lo: float = -1.0, hi: float = 1.0) -> th.Tensor:
         """``clip(tanh(mean(obs)), lo, hi)`` — the noise-free action of the trainers' rollouts; one kernel each way where
-        ``fused_ok``, the library ops otherwise (same function, same gradients)."""
-        x = flatten_obs(obs)
-        if self.fused_ok(x):
+        ``fused_ok``, the library ops otherwise (same function, same gradients).  An observation dict of two float32
+        matrices (e.g. ``{"state": (N,13), "target": (N,3)}``) is handed to the kernel piecewise, in ``flatten_obs``'s
+        key order, without being concatenated."""
+        pieces = None
+        if not isinstance(obs, th.Tensor) and len(obs) == 2:
+            pieces = [obs[k] for k in sorted(obs.keys())]
+            if not all(p.dim() == 2 and p.dtype is th.float32 and p.is_cuda for p in pieces) or \
+                    pieces[0].shape[1] + pieces[1].shape[1] != self.body[0].in_features:
+                pieces = None
+        if pieces is not None and self.fused_ok(pieces[0]):
+            xa, xb = pieces
+        else:
+            xa, xb = flatten_obs(obs), None
+        if self.fused_ok(xa):
             l1, l2 = self.body[0], self.body[2]
-            return _FusedActorFn.apply(x, float(lo), float(hi), l1.weight, l1.bias, l2.weight, l2.bias,
+            return _FusedActorFn.apply(xa, xb, float(lo), float(hi), l1.weight, l1.bias, l2.weight, l2.bias,
                                        self.mu.weight, self.mu.bias)
-        return th.clip(th.tanh(self.mu(self.body(x))), lo, hi)
+        return th.clip(th.tanh(self.mu(self.body(xa))), lo, hi)
 
     def _dist(self, obs) -> Tuple[th.Tensor, th.Tensor]:
         h = self.body(flatten_obs(obs))
