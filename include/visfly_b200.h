@@ -352,19 +352,23 @@ int vf_env_step_bwd(const VfParams* params, const VfEnvSpec* spec, int n, int su
  * forward and backward as one launch each (csrc/vf_policy.cu) instead of ~40 library launches per env step.
  * The observation may be handed over in two row-major pieces x = [xa (n, da) | xb (n, db)], d = da + db (the obs dict
  * of NavigationEnv is {state (n,13), target (n,3)}; no concatenated copy is made); db = 0, xb = NULL for one piece.
- * All weights row-major like torch.nn.Linear (W1 (h, d), W2 (h, h), W3 (4, h)); fp32.
+ * Weights: vf_policy_pack converts the six torch.nn.Linear tensors (row-major W1 (h, d), b1, W2 (h, h), b2,
+ * W3 (4, h), b3; fp32) into one block of vf_policy_packed_floats(h) floats holding them in the tile layouts of the
+ * kernels (k-major and natural, columns interleaved over threads); call it once per weight update, the forward and
+ * backward of every env step of the horizon read the block.
  *   vf_policy_bwd: grad_xa (n, da) / grad_xb (n, db) may each be NULL; `partial` is scratch of
  *   vf_policy_partial_floats(n, d, h) floats; grad_params receives
  *   [dW1 (h,d) | db1 (h) | dW2 (h,h) | db2 (h) | dW3 (4,h) | db3 (4)] (overwritten, summed over agents in a fixed
  *   order: bit-reproducible).  Nothing is saved between the two calls: the backward recomputes the activations.
  * ===================================================================================================== */
-int vf_policy_fwd(int n, int da, int db, int h, const float* xa, const float* xb, const float* w1, const float* b1,
-                  const float* w2, const float* b2, const float* w3, const float* b3, float lo, float hi,
-                  float* action, void* stream);
-int vf_policy_bwd(int n, int da, int db, int h, const float* xa, const float* xb, const float* w1, const float* b1,
-                  const float* w2, const float* b2, const float* w3, const float* b3, float lo, float hi,
-                  const float* grad_action, float* grad_xa, float* grad_xb, float* partial, float* grad_params,
-                  void* stream);
+int vf_policy_packed_floats(int h);
+int vf_policy_pack(int d, int h, const float* w1, const float* b1, const float* w2, const float* b2, const float* w3,
+                   const float* b3, float* packed, void* stream);
+int vf_policy_fwd(int n, int da, int db, int h, const float* xa, const float* xb, const float* packed, float lo,
+                  float hi, float* action, void* stream);
+int vf_policy_bwd(int n, int da, int db, int h, const float* xa, const float* xb, const float* packed, float lo,
+                  float hi, const float* grad_action, float* grad_xa, float* grad_xb, float* partial,
+                  float* grad_params, void* stream);
 int vf_policy_partial_floats(int n, int d, int h);
 const char* vf_policy_last_error(void);
 

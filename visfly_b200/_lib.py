@@ -40,10 +40,11 @@ SIGNATURES = {
     "vf_export_pose_habitat": (_i, [_P(VfParams), _i, _vp, _vp, _vp, _vp]),
     "vf_env_spec_size": (_i, []),
     "vf_wait_flag": (_i, [_vp, _u, ctypes.c_longlong]),
-    "vf_policy_fwd": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_float, ctypes.c_float,
-                           _vp, _vp]),
-    "vf_policy_bwd": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_float, ctypes.c_float,
-                           _vp, _vp, _vp, _vp, _vp, _vp]),
+    "vf_policy_packed_floats": (_i, [_i]),
+    "vf_policy_pack": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "vf_policy_fwd": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, ctypes.c_float, ctypes.c_float, _vp, _vp]),
+    "vf_policy_bwd": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, ctypes.c_float, ctypes.c_float, _vp, _vp, _vp, _vp, _vp,
+                           _vp]),
     "vf_policy_partial_floats": (_i, [_i, _i, _i]),
     "vf_policy_last_error": (ctypes.c_char_p, []),
     "vf_env_step_fwd": (_i, [_P(VfParams), _P(VfEnvSpec), _i, _i, _i, _i, _u, _u, ctypes.c_ulonglong, _vp,
@@ -297,36 +298,44 @@ def _policy_check(rc: int):
         raise RuntimeError("visfly_b200: " + load().vf_policy_last_error().decode())
 
 
-def policy_fwd(xa: th.Tensor, xb: Optional[th.Tensor], params, lo: float, hi: float) -> th.Tensor:
-    """Binding of ``vf_policy_fwd``: observation pieces ``xa (n, da)`` [, ``xb (n, db)``], ``params`` =
-    (W1, b1, W2, b2, W3, b3), all contiguous float32 CUDA tensors."""
+def policy_pack(params) -> th.Tensor:
+    """Binding of ``vf_policy_pack``: (W1, b1, W2, b2, W3, b3) -> the packed weight block the actor kernels read."""
+    lib = load(require_cuda=True)
+    h, d = params[0].shape
+    packed = th.empty((lib.vf_policy_packed_floats(h),), dtype=th.float32, device=params[0].device)
+    with th.cuda.device(packed.device):
+        _policy_check(lib.vf_policy_pack(d, h, *[_dev_ptr(p.detach(), "param") for p in params], packed.data_ptr(),
+                                         _stream(packed.device)))
+    return packed
+
+
+def policy_fwd(xa: th.Tensor, xb: Optional[th.Tensor], packed: th.Tensor, h: int, lo: float, hi: float) -> th.Tensor:
+    """Binding of ``vf_policy_fwd``: observation pieces ``xa (n, da)`` [, ``xb (n, db)``] (contiguous float32 CUDA
+    tensors) and the packed weight block of ``policy_pack``."""
     lib = load(require_cuda=True)
     n, da = xa.shape
     db = 0 if xb is None else xb.shape[1]
-    h = params[0].shape[0]
     action = th.empty((n, 4), dtype=th.float32, device=xa.device)
     with th.cuda.device(xa.device):
-        _policy_check(lib.vf_policy_fwd(n, da, db, h, _dev_ptr(xa, "xa"), _dev_ptr(xb, "xb"),
-                                        *[_dev_ptr(p, "param") for p in params], float(lo), float(hi),
-                                        action.data_ptr(), _stream(xa.device)))
+        _policy_check(lib.vf_policy_fwd(n, da, db, h, _dev_ptr(xa, "xa"), _dev_ptr(xb, "xb"), packed.data_ptr(),
+                                        float(lo), float(hi), action.data_ptr(), _stream(xa.device)))
     return action
 
 
-def policy_bwd(xa: th.Tensor, xb: Optional[th.Tensor], params, lo: float, hi: float, g_action: th.Tensor,
-               want_ga: bool, want_gb: bool):
+def policy_bwd(xa: th.Tensor, xb: Optional[th.Tensor], packed: th.Tensor, h: int, lo: float, hi: float,
+               g_action: th.Tensor, want_ga: bool, want_gb: bool):
     """Binding of ``vf_policy_bwd``: returns ``(grad_xa | None, grad_xb | None, flat parameter gradients)``."""
     lib = load(require_cuda=True)
     n, da = xa.shape
     db = 0 if xb is None else xb.shape[1]
-    d, h = da + db, params[0].shape[0]
+    d = da + db
     g_a = th.empty_like(xa) if want_ga else None
     g_b = th.empty_like(xb) if (want_gb and xb is not None) else None
     partial = th.empty((lib.vf_policy_partial_floats(n, d, h),), dtype=th.float32, device=xa.device)
     flat = th.empty((h * d + h + h * h + h + 4 * h + 4,), dtype=th.float32, device=xa.device)
     with th.cuda.device(xa.device):
-        _policy_check(lib.vf_policy_bwd(n, da, db, h, _dev_ptr(xa, "xa"), _dev_ptr(xb, "xb"),
-                                        *[_dev_ptr(p, "param") for p in params], float(lo), float(hi),
-                                        _dev_ptr(g_action, "grad_action"), _dev_ptr(g_a, "grad_xa"),
-                                        _dev_ptr(g_b, "grad_xb"), partial.data_ptr(), flat.data_ptr(),
-                                        _stream(xa.device)))
+        _policy_check(lib.vf_policy_bwd(n, da, db, h, _dev_ptr(xa, "xa"), _dev_ptr(xb, "xb"), packed.data_ptr(),
+                                        float(lo), float(hi), _dev_ptr(g_action, "grad_action"),
+                                        _dev_ptr(g_a, "grad_xa"), _dev_ptr(g_b, "grad_xb"), partial.data_ptr(),
+                                        flat.data_ptr(), _stream(xa.device)))
     return g_a, g_b, flat

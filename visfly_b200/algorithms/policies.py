@@ -101,28 +101,31 @@ class _FusedActorFn(th.autograd.Function):
     the activations from the inputs, nothing else is saved."""
 
     @staticmethod
-    def forward(ctx, xa, xb, lo, hi, w1, b1, w2, b2, w3, b3):
+    def forward(ctx, xa, xb, lo, hi, packed, w1, b1, w2, b2, w3, b3):
         from .. import _lib
-        params = tuple(p.contiguous() for p in (w1, b1, w2, b2, w3, b3))
         xa = xa.contiguous()
         xb = None if xb is None else xb.contiguous()
-        ctx.save_for_backward(xa, *params, *(() if xb is None else (xb,)))
-        ctx.lo, ctx.hi, ctx.two = lo, hi, xb is not None
-        return _lib.policy_fwd(xa, xb, params, lo, hi)
+        ctx.save_for_backward(xa, packed, *(() if xb is None else (xb,)))
+        ctx.lo, ctx.hi, ctx.two, ctx.h = lo, hi, xb is not None, w1.shape[0]
+        ctx.shapes = [tuple(p.shape) for p in (w1, b1, w2, b2, w3, b3)]
+        return _lib.policy_fwd(xa, xb, packed, ctx.h, lo, hi)
 
     @staticmethod
     @th.autograd.function.once_differentiable
     def backward(ctx, g_action):
         from .. import _lib
         saved = ctx.saved_tensors
-        xa, params, xb = saved[0], saved[1:7], (saved[7] if ctx.two else None)
-        g_a, g_b, flat = _lib.policy_bwd(xa, xb, params, ctx.lo, ctx.hi, g_action.contiguous(),
+        xa, packed, xb = saved[0], saved[1], (saved[2] if ctx.two else None)
+        g_a, g_b, flat = _lib.policy_bwd(xa, xb, packed, ctx.h, ctx.lo, ctx.hi, g_action.contiguous(),
                                          ctx.needs_input_grad[0], ctx.needs_input_grad[1])
         grads, off = [], 0
-        for p in params:
-            grads.append(flat[off:off + p.numel()].view_as(p))
-            off += p.numel()
-        return (g_a, g_b, None, None, *grads)
+        for shape in ctx.shapes:
+            k = 1
+            for v in shape:
+                k *= v
+            grads.append(flat[off:off + k].view(shape))
+            off += k
+        return (g_a, g_b, None, None, None, *grads)
 
 
 class Actor(nn.Module):
@@ -165,9 +168,23 @@ class Actor(nn.Module):
             xa, xb = flatten_obs(obs), None
         if self.fused_ok(xa):
             l1, l2 = self.body[0], self.body[2]
-            return _FusedActorFn.apply(xa, xb, float(lo), float(hi), l1.weight, l1.bias, l2.weight, l2.bias,
-                                       self.mu.weight, self.mu.bias)
+            params = (l1.weight, l1.bias, l2.weight, l2.bias, self.mu.weight, self.mu.bias)
+            return _FusedActorFn.apply(xa, xb, float(lo), float(hi), self._packed_weights(params), *params)
         return th.clip(th.tanh(self.mu(self.body(xa))), lo, hi)
+
+    def _packed_weights(self, params) -> th.Tensor:
+        """The weights in the kernels' tile layouts (``vf_policy_pack``), rebuilt when a parameter has changed (its
+        version counter moves with every optimiser step / ``load_state_dict`` / in-place edit): once per update, not
+        once per env step.  Under CUDA-graph capture the cache is bypassed, so that the pack launch is part of the
+        captured update and every replay repacks the weights its optimiser step has just written."""
+        from .. import _lib
+        key = tuple((p.data_ptr(), p._version) for p in params)
+        cache = self.__dict__.get("_packed")
+        capturing = th.cuda.is_current_stream_capturing()
+        if cache is None or cache[0] != key or capturing != cache[2]:
+            cache = (key, _lib.policy_pack(params), capturing)
+            self.__dict__["_packed"] = cache
+        return cache[1]
 
     def _dist(self, obs) -> Tuple[th.Tensor, th.Tensor]:
         h = self.body(flatten_obs(obs))

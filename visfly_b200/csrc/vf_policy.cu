@@ -49,50 +49,80 @@ __device__ __forceinline__ float fast_tanh(float x) {
     return copysignf(ax < 0.04f ? small : big, x);
 }
 
-template <int H> struct Smem {
-    float x[DP][TS];         // inputs, k-major (backward: finally the dx tile)
-    float h1[H][TS];         // layer-1 activations, row = neuron (backward: overwritten by dZ1)
-    float h2[H][TS];         // layer-2 activations (backward: overwritten by dZ2)
-    float w1t[DP][H];        // w1t[k][c] = W1[column_at(c)][k]
+// The weights in the layouts the tiles want, as ONE block: vf_policy_pack writes it to global memory once per weight
+// update, and every CTA of the forward / backward kernels copies it into shared memory with straight 128-bit loads
+// (transposing 21 KB per CTA on the fly cost as much as the products: 32-way bank conflicts on the strided stores).
+template <int H> struct PackedFwd {
+    float w1t[DP][H];        // w1t[k][c] = W1[column_at(c)][k]   (rows k >= d are zero)
     float w2t[H][H];         // w2t[k][c] = W2[column_at(c)][k]
     float w3t[H][NA];        // w3t[k][o] = W3[o][k]
     float b1[H], b2[H], b3[NA];   // b1 / b2 in weight-row order
 };
-template <int H> struct SmemBwd : Smem<H> {
-    float w1n[H][DP];        // w1n[j][c] = W1[j][column_at<DP>(c)]
+template <int H> struct PackedBwd {
+    float w1n[H][DP];        // w1n[j][c] = W1[j][column_at<DP>(c)]   (columns >= d are zero)
     float w2n[H][H];         // w2n[j][c] = W2[j][column_at<H>(c)]
     float w3n[NA][H];
+};
+template <int H> struct Packed {
+    PackedFwd<H> f;
+    PackedBwd<H> b;
+};
+template <int H> struct Smem : PackedFwd<H> {
+    float x[DP][TS];         // inputs, k-major (backward: finally the dx tile)
+    float h1[H][TS];         // layer-1 activations, row = neuron (backward: overwritten by dZ1)
+    float h2[H][TS];         // layer-2 activations (backward: overwritten by dZ2)
+};
+template <int H> struct SmemBwd : Smem<H> {
+    PackedBwd<H> nat;
     float dz3[NA][TS];
 };
+static_assert(sizeof(PackedFwd<64>) % 16 == 0 && sizeof(PackedBwd<64>) % 16 == 0 && sizeof(PackedFwd<32>) % 16 == 0 &&
+              sizeof(PackedBwd<32>) % 16 == 0, "packed blocks are copied with 128-bit accesses");
 
 __device__ __forceinline__ float4 lds4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 
-// weights + input tile -> shared memory.  x = [xa (n, da) | xb (n, db)] row-major pieces, d = da + db.
-template <int H, class S>
-__device__ void load_tile(S& s, int n, int da, int db, int first, const float* __restrict__ xa,
-                          const float* __restrict__ xb, const float* __restrict__ w1, const float* __restrict__ b1,
-                          const float* __restrict__ w2, const float* __restrict__ b2, const float* __restrict__ w3,
-                          const float* __restrict__ b3) {
+// one thread per element of the packed block (run once per weight update)
+template <int H>
+__global__ void vf_policy_pack_kernel(int d, const float* __restrict__ w1, const float* __restrict__ b1,
+                                      const float* __restrict__ w2, const float* __restrict__ b2,
+                                      const float* __restrict__ w3, const float* __restrict__ b3,
+                                      Packed<H>* __restrict__ out) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    Packed<H>& p = *out;
+    if (e < DP * H) {
+        const int k = e / H, c = e % H;
+        p.f.w1t[k][c] = k < d ? w1[column_at<H>(c) * d + k] : 0.f;
+        const int j = e / DP, cc = e % DP, kk = column_at<DP>(cc);
+        p.b.w1n[j][cc] = kk < d ? w1[j * d + kk] : 0.f;
+    }
+    if (e < H * H) {
+        const int k = e / H, c = e % H;
+        p.f.w2t[k][c] = w2[column_at<H>(c) * H + k];
+        p.b.w2n[k][c] = w2[k * H + column_at<H>(c)];
+    }
+    if (e < NA * H) {
+        p.f.w3t[e % H][e / H] = w3[e];
+        p.b.w3n[e / H][e % H] = w3[e];
+    }
+    if (e < H) {
+        p.f.b1[e] = b1[column_at<H>(e)];
+        p.f.b2[e] = b2[column_at<H>(e)];
+    }
+    if (e < NA) p.f.b3[e] = b3[e];
+}
+
+template <class T> __device__ __forceinline__ void copy_block(T& dst, const T& src) {
+    const float4* g = reinterpret_cast<const float4*>(&src);
+    float4* s4 = reinterpret_cast<float4*>(&dst);
+    for (int i = threadIdx.x; i < int(sizeof(T) / 16); i += NT) s4[i] = __ldg(g + i);
+}
+
+// input tile -> shared memory.  x = [xa (n, da) | xb (n, db)] row-major pieces, d = da + db.
+template <class S>
+__device__ void load_inputs(S& s, int n, int da, int db, int first, const float* __restrict__ xa,
+                            const float* __restrict__ xb) {
     const int t = threadIdx.x, d = da + db;
-    for (int e = t; e < H * DP; e += NT) {               // W1 (H, d) row-major -> w1t[k][c]
-        const int c = e / DP, k = e % DP;
-        s.w1t[k][c] = k < d ? __ldg(w1 + column_at<H>(c) * d + k) : 0.f;
-    }
-    for (int e = t; e < H * H; e += NT) {
-        const int c = e / H, k = e % H;
-        s.w2t[k][c] = __ldg(w2 + column_at<H>(c) * H + k);
-    }
-    for (int e = t; e < NA * H; e += NT) {
-        const int o = e / H, k = e % H;
-        s.w3t[k][o] = __ldg(w3 + e);
-    }
-    for (int e = t; e < H; e += NT) {
-        s.b1[e] = __ldg(b1 + column_at<H>(e));
-        s.b2[e] = __ldg(b2 + column_at<H>(e));
-    }
-    if (t < NA) s.b3[t] = __ldg(b3 + t);
-    // inputs: two threads per agent, each takes every other feature
-    const int la = t % TM, a = first + la;
+    const int la = t % TM, a = first + la;               // two threads per agent, each takes every other feature
     for (int k = t / TM; k < DP; k += NT / TM) {
         float v = 0.f;
         if (a < n) {
@@ -175,13 +205,12 @@ template <int H, class S> __device__ void forward_tile(S& s, float a[NA]) {
 template <int H>
 __global__ void __launch_bounds__(NT)
 vf_policy_fwd_kernel(int n, int da, int db, const float* __restrict__ xa, const float* __restrict__ xb,
-                     const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ w2,
-                     const float* __restrict__ b2, const float* __restrict__ w3, const float* __restrict__ b3,
-                     float lo, float hi, float* __restrict__ action) {
+                     const Packed<H>* __restrict__ packed, float lo, float hi, float* __restrict__ action) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Smem<H>& s = *reinterpret_cast<Smem<H>*>(smem_raw);
     const int first = blockIdx.x * TM;
-    load_tile<H>(s, n, da, db, first, xa, xb, w1, b1, w2, b2, w3, b3);
+    copy_block<PackedFwd<H>>(s, packed->f);
+    load_inputs(s, n, da, db, first, xa, xb);
     __syncthreads();
     float a[NA];
     forward_tile<H>(s, a);
@@ -200,21 +229,15 @@ __host__ __device__ inline int partial_size(int h, int d) { return h * d + h + h
 template <int H>
 __global__ void __launch_bounds__(NT)
 vf_policy_bwd_kernel(int n, int da, int db, const float* __restrict__ xa, const float* __restrict__ xb,
-                     const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ w2,
-                     const float* __restrict__ b2, const float* __restrict__ w3, const float* __restrict__ b3,
-                     float lo, float hi, const float* __restrict__ g_action, float* __restrict__ g_xa,
-                     float* __restrict__ g_xb, float* __restrict__ partial) {
+                     const Packed<H>* __restrict__ packed, float lo, float hi, const float* __restrict__ g_action,
+                     float* __restrict__ g_xa, float* __restrict__ g_xb, float* __restrict__ partial) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SmemBwd<H>& s = *reinterpret_cast<SmemBwd<H>*>(smem_raw);
     const int t = threadIdx.x, d = da + db;
     const int first = blockIdx.x * TM;
-    load_tile<H>(s, n, da, db, first, xa, xb, w1, b1, w2, b2, w3, b3);
-    for (int e = t; e < H * DP; e += NT) {
-        const int j = e / DP, c = e % DP, k = column_at<DP>(c);
-        s.w1n[j][c] = k < d ? __ldg(w1 + j * d + k) : 0.f;
-    }
-    for (int e = t; e < H * H; e += NT) s.w2n[e / H][e % H] = __ldg(w2 + (e / H) * H + column_at<H>(e % H));
-    for (int e = t; e < NA * H; e += NT) s.w3n[e / H][e % H] = __ldg(w3 + e);
+    copy_block<PackedFwd<H>>(s, packed->f);
+    copy_block<PackedBwd<H>>(s.nat, packed->b);
+    load_inputs(s, n, da, db, first, xa, xb);
     __syncthreads();
     float a[NA];
     forward_tile<H>(s, a);
@@ -261,7 +284,7 @@ vf_policy_bwd_kernel(int n, int da, int db, const float* __restrict__ xa, const 
 #pragma unroll 8
         for (int k = t / TM; k < H; k += NT / TM) {
             const float h = s.h2[k][la];
-            const float dh = z0 * s.w3n[0][k] + z1 * s.w3n[1][k] + z2 * s.w3n[2][k] + z3 * s.w3n[3][k];
+            const float dh = z0 * s.nat.w3n[0][k] + z1 * s.nat.w3n[1][k] + z2 * s.nat.w3n[2][k] + z3 * s.nat.w3n[3][k];
             s.h2[k][la] = dh * (1.f - h * h);
         }
     }
@@ -305,7 +328,7 @@ vf_policy_bwd_kernel(int n, int da, int db, const float* __restrict__ xa, const 
         constexpr int NJ = H / 16;
         const int ty = t / 16, tx = t % 16;
         float acc[8][NJ];
-        tile_gemm<H, H>(s.h2, s.w2n, acc);
+        tile_gemm<H, H>(s.h2, s.nat.w2n, acc);
         __syncthreads();                                   // every thread is done reading h1 (dW2) before it changes
 #pragma unroll
         for (int j = 0; j < NJ; ++j) {
@@ -351,7 +374,7 @@ vf_policy_bwd_kernel(int n, int da, int db, const float* __restrict__ xa, const 
     // ---- dx[a][k] = sum_j dz1[j][a] W1[j][k]: tile product into the x tile, then one contiguous row per agent -----
     if (g_xa || g_xb) {
         float acc[8][DP / 16];
-        tile_gemm<DP, H>(s.h1, s.w1n, acc);
+        tile_gemm<DP, H>(s.h1, s.nat.w1n, acc);
         __syncthreads();                                   // dW1 has read the x tile
         store_tile<DP, false>(s.x, acc, nullptr);
         __syncthreads();
@@ -412,7 +435,7 @@ template <class K> int allow_smem(K kernel, size_t bytes) {
 int check_shapes(int n, int da, int db, int h, const void* xb) {
     if (n < 0) return policy_fail("n must be >= 0");
     if (da < 1 || db < 0 || da + db > DP) return policy_fail("policy input width must be in 1..32");
-    if (db > 0 && !xb) return policy_fail("second input piece is NULL");
+    if (db > 0 && !xb && n > 0) return policy_fail("second input piece is NULL");
     if (h != 32 && h != 64) return policy_fail("policy hidden width must be 32 or 64");
     return 0;
 }
@@ -425,46 +448,66 @@ const char* vf_policy_last_error(void) { return g_policy_error.c_str(); }
 
 int vf_policy_partial_floats(int n, int d, int h) { return ((n + TM - 1) / TM) * partial_size(h, d); }
 
-int vf_policy_fwd(int n, int da, int db, int h, const float* xa, const float* xb, const float* w1, const float* b1,
-                  const float* w2, const float* b2, const float* w3, const float* b3, float lo, float hi,
-                  float* action, void* stream) {
+int vf_policy_packed_floats(int h) { return int((h == 64 ? sizeof(Packed<64>) : sizeof(Packed<32>)) / sizeof(float)); }
+
+int vf_policy_pack(int d, int h, const float* w1, const float* b1, const float* w2, const float* b2, const float* w3,
+                   const float* b3, float* packed, void* stream) {
+    if (check_shapes(0, d, 0, h, nullptr)) return 1;
+    if (!w1 || !b1 || !w2 || !b2 || !w3 || !b3 || !packed) return policy_fail("vf_policy_pack: NULL buffer");
+    if (reinterpret_cast<size_t>(packed) & 15u) return policy_fail("packed must be 16-byte aligned");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int threads = h * (h > DP ? h : DP);
+    if (h == 64)
+        vf_policy_pack_kernel<64><<<(threads + 255) / 256, 256, 0, st>>>(d, w1, b1, w2, b2, w3, b3,
+                                                                         reinterpret_cast<Packed<64>*>(packed));
+    else
+        vf_policy_pack_kernel<32><<<(threads + 255) / 256, 256, 0, st>>>(d, w1, b1, w2, b2, w3, b3,
+                                                                         reinterpret_cast<Packed<32>*>(packed));
+    const cudaError_t err = cudaGetLastError();
+    return err == cudaSuccess ? 0 : policy_fail("vf_policy_pack launch failed", err);
+}
+
+int vf_policy_fwd(int n, int da, int db, int h, const float* xa, const float* xb, const float* packed, float lo,
+                  float hi, float* action, void* stream) {
     if (check_shapes(n, da, db, h, xb)) return 1;
     if (n == 0) return 0;
-    if (!xa || !w1 || !b1 || !w2 || !b2 || !w3 || !b3 || !action) return policy_fail("vf_policy_fwd: NULL buffer");
-    if (reinterpret_cast<size_t>(action) & 15u) return policy_fail("action must be 16-byte aligned");
+    if (!xa || !packed || !action) return policy_fail("vf_policy_fwd: NULL buffer");
+    if ((reinterpret_cast<size_t>(action) | reinterpret_cast<size_t>(packed)) & 15u)
+        return policy_fail("action and packed must be 16-byte aligned");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int grid = (n + TM - 1) / TM;
     if (h == 64) {
         if (allow_smem(vf_policy_fwd_kernel<64>, sizeof(Smem<64>))) return 1;
-        vf_policy_fwd_kernel<64><<<grid, NT, sizeof(Smem<64>), st>>>(n, da, db, xa, xb, w1, b1, w2, b2, w3, b3, lo, hi, action);
+        vf_policy_fwd_kernel<64><<<grid, NT, sizeof(Smem<64>), st>>>(n, da, db, xa, xb,
+                                                                    reinterpret_cast<const Packed<64>*>(packed), lo, hi, action);
     } else {
         if (allow_smem(vf_policy_fwd_kernel<32>, sizeof(Smem<32>))) return 1;
-        vf_policy_fwd_kernel<32><<<grid, NT, sizeof(Smem<32>), st>>>(n, da, db, xa, xb, w1, b1, w2, b2, w3, b3, lo, hi, action);
+        vf_policy_fwd_kernel<32><<<grid, NT, sizeof(Smem<32>), st>>>(n, da, db, xa, xb,
+                                                                    reinterpret_cast<const Packed<32>*>(packed), lo, hi, action);
     }
     const cudaError_t err = cudaGetLastError();
     return err == cudaSuccess ? 0 : policy_fail("vf_policy_fwd launch failed", err);
 }
 
-int vf_policy_bwd(int n, int da, int db, int h, const float* xa, const float* xb, const float* w1, const float* b1,
-                  const float* w2, const float* b2, const float* w3, const float* b3, float lo, float hi,
-                  const float* grad_action, float* grad_xa, float* grad_xb, float* partial, float* grad_params,
-                  void* stream) {
+int vf_policy_bwd(int n, int da, int db, int h, const float* xa, const float* xb, const float* packed, float lo,
+                  float hi, const float* grad_action, float* grad_xa, float* grad_xb, float* partial,
+                  float* grad_params, void* stream) {
     if (check_shapes(n, da, db, h, xb)) return 1;
-    if (!xa || !w1 || !b1 || !w2 || !b2 || !w3 || !b3 || !grad_action || !partial || !grad_params)
-        return policy_fail("vf_policy_bwd: NULL buffer");
-    if (reinterpret_cast<size_t>(grad_action) & 15u) return policy_fail("grad_action must be 16-byte aligned");
+    if (!xa || !packed || !grad_action || !partial || !grad_params) return policy_fail("vf_policy_bwd: NULL buffer");
+    if ((reinterpret_cast<size_t>(grad_action) | reinterpret_cast<size_t>(packed)) & 15u)
+        return policy_fail("grad_action and packed must be 16-byte aligned");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int grid = (n + TM - 1) / TM;
     const int size = partial_size(h, da + db);
     if (n > 0) {
         if (h == 64) {
             if (allow_smem(vf_policy_bwd_kernel<64>, sizeof(SmemBwd<64>))) return 1;
-            vf_policy_bwd_kernel<64><<<grid, NT, sizeof(SmemBwd<64>), st>>>(n, da, db, xa, xb, w1, b1, w2, b2, w3, b3, lo, hi,
-                                                                          grad_action, grad_xa, grad_xb, partial);
+            vf_policy_bwd_kernel<64><<<grid, NT, sizeof(SmemBwd<64>), st>>>(
+                n, da, db, xa, xb, reinterpret_cast<const Packed<64>*>(packed), lo, hi, grad_action, grad_xa, grad_xb, partial);
         } else {
             if (allow_smem(vf_policy_bwd_kernel<32>, sizeof(SmemBwd<32>))) return 1;
-            vf_policy_bwd_kernel<32><<<grid, NT, sizeof(SmemBwd<32>), st>>>(n, da, db, xa, xb, w1, b1, w2, b2, w3, b3, lo, hi,
-                                                                          grad_action, grad_xa, grad_xb, partial);
+            vf_policy_bwd_kernel<32><<<grid, NT, sizeof(SmemBwd<32>), st>>>(
+                n, da, db, xa, xb, reinterpret_cast<const Packed<32>*>(packed), lo, hi, grad_action, grad_xa, grad_xb, partial);
         }
     }
     vf_policy_reduce_kernel<<<(size + RED_E - 1) / RED_E, RED_E * RED_S, 0, st>>>(grid, size, partial, grad_params);
