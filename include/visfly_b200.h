@@ -203,6 +203,7 @@ int vf_export_pose_habitat(const VfParams* params, int n, const float* state, fl
 #define VF_TASK_HOVER      0
 #define VF_TASK_NAVIGATION 1
 #define VF_TASK_RACING     2
+#define VF_TASK_CUSTOM     3   /* task code lives with the caller: only vf_env_finish accepts it */
 
 #define VF_OBS_STATE13  0   /* [p q v w]                                    reference `state`, dynamics.py:778-786 */
 #define VF_OBS_RACING16 1   /* [gate-p, gate2-p]/10, q, v/10, w/10          reference RacingEnv.py:254-262          */
@@ -344,6 +345,25 @@ int vf_env_step_bwd(const VfParams* params, const VfEnvSpec* spec, int n, int su
                     const float* action, const float* wind, const int* status_in, const float* grad_state_out,
                     const float* grad_obs, const float* grad_reward, float* grad_state_in, float* grad_action,
                     void* stream);
+
+/*
+ * The wrapper tail WITHOUT the task: for envs whose success / failure / reward are the caller's own tensor code
+ * (subclasses of the reference's DroneGymEnvsBase overriding get_success / get_failure / get_reward).  The caller runs
+ * vf_step_fwd, evaluates its task on the state reached, and hands the three per-agent results to this launch, which
+ * does the rest of `DroneGymEnvsBase.step` (envs/base/droneGymEnv.py:163-208): step count, bounding-box collision and
+ * out-of-bounds flags (droneEnv.py:345-369), return accumulation, episode_done / done, the episode record, and the
+ * auto-reset of finished agents from the state generator (same sampler, same spec fields as vf_env_step_fwd; spec.task
+ * may be VF_TASK_CUSTOM, target / gates are not read).  Two launches + the caller's task ops per env step instead of
+ * ~100 small tensor kernels.
+ *   state_in   [5][n][4]  state AFTER the control step            reward float[n]   success / failure uint8[n]
+ *   state_out  [5][n][4]  = state_in, finished agents re-initialised (must not alias state_in)
+ *   obs_out    [n][13] or NULL: the reference `state` after the reset      done_out uint8[n]     record_out float[n][4]
+ */
+int vf_env_finish(const VfParams* params, const VfEnvSpec* spec, int n, unsigned env_flags,
+                  unsigned long long step_index, const unsigned long long* step_base, const float* state_in,
+                  const float* wind, const float* reset_table, const int* status_in, const float* reward,
+                  const unsigned char* success, const unsigned char* failure, float* state_out, int* status_out,
+                  float* obs_out, unsigned char* done_out, float* record_out, void* stream);
 
 /* =====================================================================================================
  * Deterministic actor of the analytic-gradient trainers (SURVEY.md §8 row n3 / BASELINE configs[2]): the policy the

@@ -40,6 +40,8 @@ SIGNATURES = {
     "vf_export_pose_habitat": (_i, [_P(VfParams), _i, _vp, _vp, _vp, _vp]),
     "vf_env_spec_size": (_i, []),
     "vf_wait_flag": (_i, [_vp, _u, ctypes.c_longlong]),
+    "vf_env_finish": (_i, [_P(VfParams), _P(VfEnvSpec), _i, _u, ctypes.c_ulonglong, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                           _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "vf_policy_packed_floats": (_i, [_i]),
     "vf_policy_pack": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "vf_policy_fwd": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, ctypes.c_float, ctypes.c_float, _vp, _vp]),
@@ -270,6 +272,29 @@ def env_step_bwd(params: VfParams, spec: VfEnvSpec, substeps: int, integrator: i
             _any_ptr(status_in, "status_in", th.int32),
             _dev_ptr(g_state_out, "grad_state_out"), _dev_ptr(g_obs, "grad_obs"), _dev_ptr(g_reward, "grad_reward"),
             _dev_ptr(g_state_in, "grad_state_in"), _dev_ptr(g_action, "grad_action"), _stream(state_in.device)))
+
+
+def env_finish(params: VfParams, spec: VfEnvSpec, env_flags: int, step_index: int, state_in: th.Tensor,
+               status_in: th.Tensor, reward: th.Tensor, success: Optional[th.Tensor], failure: Optional[th.Tensor],
+               want_obs: bool = True, wind: Optional[th.Tensor] = None, reset_table: Optional[th.Tensor] = None,
+               step_base: Optional[th.Tensor] = None):
+    """Binding of ``vf_env_finish`` (wrapper tail for caller-defined tasks).  Allocates and returns
+    ``(state_out, status_out, obs | None, done, record)``."""
+    lib = load(require_cuda=True)
+    n, dev = state_in.shape[1], state_in.device
+    state_out, status_out = th.empty_like(state_in), th.empty_like(status_in)
+    obs = th.empty((n, 13), dtype=th.float32, device=dev) if want_obs else None
+    done = th.empty((n,), dtype=th.bool, device=dev)
+    record = th.empty((n, 4), dtype=th.float32, device=dev)
+    with th.cuda.device(dev):
+        _check(lib.vf_env_finish(
+            ctypes.byref(params), ctypes.byref(spec), n, env_flags, step_index,
+            _any_ptr(step_base, "step_base", th.int64), _dev_ptr(state_in, "state_in"), _dev_ptr(wind, "wind"),
+            _dev_ptr(reset_table, "reset_table"), _any_ptr(status_in, "status_in", th.int32),
+            _dev_ptr(reward, "reward"), _any_ptr(success, "success", th.bool), _any_ptr(failure, "failure", th.bool),
+            state_out.data_ptr(), status_out.data_ptr(), None if obs is None else obs.data_ptr(), done.data_ptr(),
+            record.data_ptr(), _stream(dev)))
+    return state_out, status_out, obs, done, record
 
 
 def wait_flag(flag_addr: int, value: int, timeout_us: int = 10_000_000) -> None:

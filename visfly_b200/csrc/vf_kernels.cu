@@ -395,6 +395,80 @@ vf_env_step_fwd_kernel(const __grid_constant__ VfParams params, const __grid_con
 }
 
 // ---------------------------------------------------------------------------------------------
+// wrapper tail for caller-defined tasks: collision flags, accumulation, termination, record, auto-reset
+// ---------------------------------------------------------------------------------------------
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+vf_env_finish_kernel(const __grid_constant__ VfParams params, const __grid_constant__ VfEnvSpec E, int n,
+                     unsigned env_flags, unsigned long long step_index,
+                     const unsigned long long* __restrict__ step_base, const float* __restrict__ state_in,
+                     const float* __restrict__ wind, const float* __restrict__ reset_table,
+                     const int* __restrict__ status_in, const float* __restrict__ reward_in,
+                     const unsigned char* __restrict__ success_in, const unsigned char* __restrict__ failure_in,
+                     float* __restrict__ state_out, int* __restrict__ status_out, float* __restrict__ obs_out,
+                     unsigned char* __restrict__ done_out, float* __restrict__ record_out) {
+    __shared__ __align__(16) float s_obs[(BLOCK / 32) * kWarpObs];
+    const vf::Params<float>& P = reinterpret_cast<const vf::Params<float>&>(params);
+    const int i = blockIdx.x * BLOCK + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int warp_first = i - lane;
+    const bool live = i < n;
+    pdl_trigger();
+    pdl_wait();
+    vf::State<float> s;
+    float wd[3] = {P.wind[0], P.wind[1], P.wind[2]};
+    if (live) {
+        load_state(state_in, n, i, s);
+        const int4 st4 = __ldg(reinterpret_cast<const int4*>(status_in) + i);
+        const float reward = __ldg(reward_in + i);
+        const bool success = success_in && __ldg(success_in + i) != 0;
+        const bool failure = failure_in && __ldg(failure_in + i) != 0;
+        if (wind) {
+            const float4 w4 = ldg4(wind, size_t(i));
+            wd[0] = w4.x; wd[1] = w4.y; wd[2] = w4.z;
+        }
+        int sc = st4.x + 1;
+        const unsigned eb = unsigned(st4.z) & 0xFFu;
+        const vf::BoxHit<float> hit = vf::box_hit<float>(s.p, E.bbox_lo, E.bbox_hi);
+        const bool is_col = hit.dis < E.uav_radius;
+        bool once = (eb & VF_EBIT_ONCE_COLLIDED) || is_col;
+        float ret = __int_as_float(st4.y) + reward;
+        // droneGymEnv.py:188-193
+        bool ep_done = (eb & VF_EBIT_EPISODE_DONE) || success || failure || hit.out || (E.collision_reset && is_col);
+        const bool done = ep_done || sc >= E.max_episode_steps;
+        const unsigned rbits = (done ? VF_RBIT_DONE : 0u) | (ep_done ? VF_RBIT_EPISODE_DONE : 0u) |
+                               (success ? VF_RBIT_SUCCESS : 0u) | (sc >= E.max_episode_steps ? VF_RBIT_TRUNCATED : 0u) |
+                               (once ? VF_RBIT_COLLIDED : 0u);
+        stg4(record_out, size_t(i), make_float4(ret, float(sc), float(rbits), 0.f));
+        done_out[i] = done ? 1 : 0;
+        if (done && !(env_flags & VF_ENV_FLAG_NO_RESET)) {
+            const unsigned long long step = step_index + (step_base ? *step_base : 0ull);
+            float rp[3], rq[4], rv[3], rw[3];
+            vf::sample_reset(E, E.agent_offset + unsigned(i), step, reset_table ? reset_table + size_t(i) * 13 : nullptr,
+                             rp, rq, rv, rw);
+            for (int j = 0; j < 3; ++j) { s.p[j] = rp[j]; s.v[j] = rv[j]; s.w[j] = rw[j]; }
+            for (int j = 0; j < 4; ++j) { s.q[j] = rq[j]; s.mot[j] = E.init_motor_omega; }
+            s.al[0] = s.al[1] = s.al[2] = 0.f;
+            sc = 0; ret = 0.f; ep_done = false; once = false;
+        }
+        store_state(state_out, n, i, s);
+        const int ebo = int((ep_done ? VF_EBIT_EPISODE_DONE : 0u) | (once ? VF_EBIT_ONCE_COLLIDED : 0u));
+        reinterpret_cast<int4*>(status_out)[i] = make_int4(sc, __float_as_int(ret), ebo | (st4.z & 0xFF00), st4.w);
+    }
+    if (obs_out) {
+        float o[kObs];
+        if (live) {
+            o[0] = s.p[0]; o[1] = s.p[1]; o[2] = s.p[2];
+            o[3] = s.q[0]; o[4] = s.q[1]; o[5] = s.q[2]; o[6] = s.q[3];
+            o[7] = s.v[0] + wd[0]; o[8] = s.v[1] + wd[1]; o[9] = s.v[2] + wd[2];
+            o[10] = s.w[0]; o[11] = s.w[1]; o[12] = s.w[2];
+        }
+        warp_store_obs(obs_out, s_obs + warp * kWarpObs, n, warp_first, lane, o);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // reverse mode of the fused env step
 // ---------------------------------------------------------------------------------------------
 template <int INTEG, int ACT, bool LAG, int SMAX, int BLOCK>
@@ -618,9 +692,10 @@ int check_common(const VfParams* params, int n, int substeps, int integrator, in
     return 0;
 }
 
-int check_spec(const VfEnvSpec* spec) {
+int check_spec(const VfEnvSpec* spec, bool allow_custom = false) {
     if (!spec) return fail("spec is NULL");
-    if (spec->task < VF_TASK_HOVER || spec->task > VF_TASK_RACING) return fail("spec.task must be a VF_TASK_* value");
+    if (spec->task < VF_TASK_HOVER || spec->task > (allow_custom ? VF_TASK_CUSTOM : VF_TASK_RACING))
+        return fail("spec.task must be a VF_TASK_* value (VF_TASK_CUSTOM only for vf_env_finish)");
     if (spec->obs_kind != VF_OBS_STATE13 && spec->obs_kind != VF_OBS_RACING16)
         return fail("spec.obs_kind must be a VF_OBS_* value");
     if (spec->gen_kind < VF_GEN_UNIFORM || spec->gen_kind > VF_GEN_TABLE) return fail("spec.gen_kind must be a VF_GEN_* value");
@@ -922,6 +997,31 @@ int vf_env_step_bwd(const VfParams* params, const VfEnvSpec* spec, int n, int su
                 grad_state_out, grad_obs, grad_reward, grad_state_in, grad_action, st);
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return fail("vf_env_step_bwd launch failed", err);
+    return 0;
+}
+
+int vf_env_finish(const VfParams* params, const VfEnvSpec* spec, int n, unsigned env_flags,
+                  unsigned long long step_index, const unsigned long long* step_base, const float* state_in,
+                  const float* wind, const float* reset_table, const int* status_in, const float* reward,
+                  const unsigned char* success, const unsigned char* failure, float* state_out, int* status_out,
+                  float* obs_out, unsigned char* done_out, float* record_out, void* stream) {
+    if (!params) return fail("params is NULL");
+    if (check_spec(spec, true)) return 1;
+    if (n < 0) return fail("n must be >= 0");
+    if (n == 0) return 0;
+    if (!state_in || !status_in || !reward || !state_out || !status_out || !done_out || !record_out)
+        return fail("vf_env_finish: a required buffer is NULL");
+    if (spec->gen_kind == VF_GEN_TABLE && !reset_table) return fail("VF_GEN_TABLE needs reset_table");
+    if (state_in == state_out) return fail("state_out must not alias state_in");
+    if (!aligned16(state_in) || !aligned16(state_out) || !aligned16(status_in) || !aligned16(status_out) ||
+        !aligned16(obs_out) || !aligned16(record_out) || !aligned16(wind))
+        return fail("all float4 / int4 buffers must be 16-byte aligned");
+    const int grid = (n + kBlock - 1) / kBlock;
+    launch_pdl(vf_env_finish_kernel<kBlock>, grid, kBlock, static_cast<cudaStream_t>(stream), *params, *spec, n,
+               env_flags, step_index, step_base, state_in, wind, reset_table, status_in, reward, success, failure,
+               state_out, status_out, obs_out, done_out, record_out);
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return fail("vf_env_finish launch failed", err);
     return 0;
 }
 

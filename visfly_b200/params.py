@@ -242,7 +242,7 @@ def build_vf_params(model: DroneModel, action_type: ACTION_TYPE, scaling: Dict[s
 # ---------------------------------------------------------------------------------------------------
 # fused env step: ctypes mirror of ``struct VfEnvSpec`` (include/visfly_b200.h)
 # ---------------------------------------------------------------------------------------------------
-TASK_HOVER, TASK_NAVIGATION, TASK_RACING = 0, 1, 2
+TASK_HOVER, TASK_NAVIGATION, TASK_RACING, TASK_CUSTOM = 0, 1, 2, 3
 OBS_STATE13, OBS_RACING16 = 0, 1
 GEN_UNIFORM, GEN_NORMAL, GEN_TABLE = 0, 1, 2
 GEN_MAX_BOXES = 4
