@@ -158,6 +158,7 @@ class DroneGymEnvsBase(VecEnv):
         self.host_ring_depth = 4                  # numpy mode: arrays returned by a step stay valid for depth-1 more steps
         self.use_fused_step = True                # False: force the generic tensor-op path (debugging / comparison)
         self._fused = None                        # FusedEnvStep, created by built-in tasks (_make_fused)
+        self._split = None                        # FusedEnvStep(TASK_CUSTOM) for user-defined tasks (_make_split)
         self.render_mode = ["None"] * n
         self._is_initial = False
 
@@ -186,6 +187,10 @@ class DroneGymEnvsBase(VecEnv):
             if fused:
                 return self._step_fused()
             self._fused.leave()
+        elif self._split is not None:
+            if not is_test and self._split.refresh():
+                return self._step_split()
+            self._split.leave()
         with self._grad_ctx():
             self.envs.step(self._action)
             self.get_full_observation()
@@ -213,6 +218,55 @@ class DroneGymEnvsBase(VecEnv):
             self._info = info
             if not is_test:
                 self._auto_reset(done)
+        return self._format_step_output(reward, done, info)
+
+    # -- two-launch path for user-defined tasks ---------------------------------------------------------------
+    def _make_split(self):
+        """Task envs that define their own ``get_success / get_failure / get_reward`` as tensor code get the split env
+        step: launch 1 = the control step (``vf_step_fwd``), then the task's tensor ops on the state reached, launch 2 =
+        the rest of the wrapper (``vf_env_finish``: collision flags, accumulation, termination, episode record,
+        auto-reset with the in-kernel sampler) — instead of the ~100 small kernels of the generic path.  Rewards
+        returned as dicts (per-term logging) keep the generic path."""
+        from ... import params as P
+        from .fused import FusedEnvStep
+        if self._indiv_rewards is not None or type(self)._extra_info is not DroneGymEnvsBase._extra_info:
+            return None
+        return FusedEnvStep(self, P.TASK_CUSTOM, P.OBS_STATE13)
+
+    def _step_split(self):
+        global _RecordInfo
+        if _RecordInfo is None:
+            from .fused import RecordInfo as _RecordInfo
+        fz, envs = self._split, self.envs
+        dyn = envs.dynamics
+        if not fz.active:
+            fz.enter()
+        with self._grad_ctx():
+            dyn.step(self._action)                             # launch 1 (FIFO, wind, autograd history)
+            envs._collision_stale = True                       # collision views: recomputed only if the task reads them
+            envs.update_observation()
+            self.get_full_observation()
+            pre_obs = self._obs_tensors
+            fz.sc_mid = fz.sc + 1                              # what `self._step_count` shows to the task code
+            self._success = self.get_success()
+            self._failure = self.get_failure()
+            reward = self.get_reward(predicted_obs={})
+            if not isinstance(reward, th.Tensor):
+                raise ValueError("get_reward changed its return type after reset()")
+            fz.sc_mid = None
+            state_out, obs13, done, record = fz.finish(dyn._state, reward, self._success, self._failure,
+                                                       self.requires_grad)             # launch 2
+            dyn._state, dyn._obs_t = state_out, obs13
+            dyn._ext, dyn._fresh = None, done
+            if dyn._pre_action:                                # FIFO rows of re-initialised agents (dynamics.py:262-263)
+                m1 = done.view(-1, 1)
+                dyn._pre_action = [th.where(m1, 0.0, a) for a in dyn._pre_action]
+            envs._collision_stale = True
+            self._reward, self._done = reward, done
+            self._on_reset_where(done)                         # task hook for its own per-agent state
+            self.get_full_observation()                        # observation after the auto-reset
+        info = _RecordInfo(self.num_agent, record, pre_obs.detach(), dyn.ctrl_dt, False)
+        self._info = info
         return self._format_step_output(reward, done, info)
 
     # -- one-kernel path (built-in tasks, no autograd) -------------------------------------------------------
@@ -415,9 +469,10 @@ class DroneGymEnvsBase(VecEnv):
     # -- reset ---------------------------------------------------------------------------------------------
     def reset(self, state=None, predicted_obs=None, is_test=False, stoch=None, deter=None):
         self._is_initial = True
-        if self._fused is not None:
-            self._fused.active = False            # a full reset re-initialises everything the fused path owns
-            self.envs._fused = None
+        for f in (self._fused, self._split):
+            if f is not None:
+                f.active = False                  # a full reset re-initialises everything the fused path owns
+        self.envs._fused = None
         with self._grad_ctx():
             self.envs.reset(state=state)
             self._on_reset_where(th.ones(self.num_agent, dtype=th.bool, device=self.device))
@@ -432,14 +487,14 @@ class DroneGymEnvsBase(VecEnv):
             else:
                 raise ValueError(f"get_reward should return a dict or a tensor, but got {type(probe)}")
         self._fused = self._make_fused()
+        self._split = None if self._fused is not None else self._make_split()
         self._observations = self._format_obs(self._obs_tensors)
         return self._observations
 
     def reset_agent_by_id(self, agent_indices=None, state=None, reset_obs=None):
         """Index-based reset of selected agents (reference droneGymEnv.py:339-349)."""
         assert not isinstance(agent_indices, bool)
-        if self._fused is not None:
-            self._fused.leave()
+        self.get_state_for_generic_path()
         with self._grad_ctx():
             if agent_indices is None:
                 mask = th.ones(self.num_agent, dtype=th.bool, device=self.device)
@@ -459,8 +514,7 @@ class DroneGymEnvsBase(VecEnv):
         return self.reset_agent_by_id(agents)
 
     def examine(self):
-        if self._fused is not None:
-            self._fused.leave()
+        self.get_state_for_generic_path()
         self._auto_reset(self._done)
         self._observations = self._format_obs(self._obs_tensors)
         return self._observations
@@ -499,8 +553,9 @@ class DroneGymEnvsBase(VecEnv):
 
     def get_state_for_generic_path(self):
         """Make sure the per-agent attributes (``_step_count``, ``_rewards``, ...) are the live ones."""
-        if self._fused is not None:
-            self._fused.leave()
+        for f in (self._fused, self._split):
+            if f is not None:
+                f.leave()
 
     def simple_detach(self):
         self._rewards = self._rewards.detach()
@@ -578,7 +633,7 @@ class DroneGymEnvsBase(VecEnv):
     # While the fused path is active these read straight from the kernel's records (no per-step copies); otherwise
     # they are the plain tensors the generic path maintains.
     def _fused_live(self):
-        f = self.__dict__.get("_fused")
+        f = self.__dict__.get("_fused") or self.__dict__.get("_split")
         return f if (f is not None and f.active) else None
 
     def _record_bit(self, bit, fallback):

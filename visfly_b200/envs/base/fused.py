@@ -163,6 +163,7 @@ class FusedEnvStep:
         self.record: Optional[th.Tensor] = None      # episode record of the last step (success / failure views)
         self.t_off: Optional[th.Tensor] = None       # per-agent time offsets given at reset (None: all zero)
         self.step_base: Optional[th.Tensor] = None   # device word added to the Philox step index (graph replays)
+        self.sc_mid: Optional[th.Tensor] = None      # split path: the step count task code sees while a step is open
         self.peer_next = 0                           # address of a VfPeerScatter for the NEXT launch (fused all-gather)
         self.peer_done = False                       # ... and whether that launch has happened
         self._views = (None, None)
@@ -228,7 +229,7 @@ class FusedEnvStep:
             cache[k] = v
         return v
 
-    sc = property(lambda self: self._field(0))
+    sc = property(lambda self: self._field(0) if self.sc_mid is None else self.sc_mid)
     ret = property(lambda self: self._field(1))
     eb = property(lambda self: self._field(2))
     gate = property(lambda self: self._field(3) if self.task == P.TASK_RACING else None)
@@ -275,8 +276,8 @@ class FusedEnvStep:
             ok = False
         if not envs.dynamics.is_quat_output or "_generate_state" in vars(envs):
             ok = False
-        if any(m in vars(env) for m in _TASK_METHODS):      # instance-level override of a task method
-            ok = False
+        if self.task != P.TASK_CUSTOM and any(m in vars(env) for m in _TASK_METHODS):
+            ok = False                                      # instance-level override of a built-in task method
         s.max_episode_steps = int(env.max_episode_steps)
         s.collision_reset = int(bool(env.is_collision_reset))
         s.uav_radius = float(envs.uav_radius)
@@ -298,7 +299,7 @@ class FusedEnvStep:
                 for a in range(g.shape[0]):
                     for j in range(3):
                         s.gates[a][j] = float(g[a, j])
-        else:
+        elif self.task != P.TASK_CUSTOM:
             tgt = env.target
             watch.append(tgt)
             if bool((tgt != tgt[0]).any()):                 # per-agent targets: tensor-op path
@@ -455,6 +456,27 @@ class FusedEnvStep:
         return obs, reward, done, record, term
 
 
+    # -- split path: caller-defined task between two launches --------------------------------------------------------
+    def finish(self, state: th.Tensor, reward: th.Tensor, success: th.Tensor, failure: th.Tensor, grad: bool):
+        """Second launch of the split env step (``vf_env_finish``): step count, collision flags, accumulation,
+        termination, episode record and auto-reset, given the task's ``reward / success / failure`` on the state the
+        control step reached.  Returns ``(state', obs13 | None, done, record)``; with ``grad`` the state passes its
+        gradient through for agents that were not re-initialised (the reference's in-place overwrite cuts it for the
+        others, dynamics.py:249-263)."""
+        dyn = self.env.envs.dynamics
+        cfg = dyn._cfg
+        state_out, status, obs, done, record = _lib.env_finish(
+            cfg.params, self.spec, 0, self.global_step, state.detach(), self.status,
+            reward.detach().to(th.float32).contiguous(), success.contiguous(), failure.contiguous(),
+            want_obs=not grad, wind=dyn._wind_rows, reset_table=self.table, step_base=self.step_base)
+        self.global_step += 1
+        if grad and state.requires_grad:
+            state_out = _ResetBlend.apply(state, state_out, done)
+        self.status, self.record = status, record
+        if self.t_off is not None:
+            self.t_off = th.where(done, 0.0, self.t_off)
+        return state_out, obs, done, record
+
     # -- host-driven mode: one step ahead of the caller ---------------------------------------------------------
     # With a comm-delay FIFO of depth d >= 1 the action handed to call t is consumed by step t+d, so when call t
     # arrives everything step t+1 needs is already known.  step_host therefore launches step t+1 BEFORE it waits for
@@ -511,6 +533,21 @@ class FusedEnvStep:
         env.envs._collision_stale = True
         env._reward, env._done = reward, done
         return obs, reward, done, record, term, slot
+
+
+class _ResetBlend(th.autograd.Function):
+    """``where(done, fresh, state)`` as computed by ``vf_env_finish``: value = the kernel's output, gradient = the
+    incoming one for agents that kept their state, zero for re-initialised ones."""
+
+    @staticmethod
+    def forward(ctx, state, state_out, done):
+        ctx.save_for_backward(done)
+        return state_out.view_as(state_out)
+
+    @staticmethod
+    def backward(ctx, g):
+        done, = ctx.saved_tensors
+        return th.where(done.view(1, -1, 1), 0.0, g), None, None
 
 
 class EnvControlStep(th.autograd.Function):
