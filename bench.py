@@ -418,6 +418,42 @@ def racing_leg(n_weak, dev, rank, world, K, W, stream, barrier):
     return out
 
 
+def custom_task_leg(n, dev, K, W, stream, barrier):
+    """A task env as a user would write it — HoverEnv's reward re-stated in a subclass, so that the env no longer
+    qualifies for the one-kernel step — on the two-launch path (control step kernel + the task's tensor ops +
+    vf_env_finish) and on the generic tensor-op path beside it (what such envs ran on in round 1)."""
+    from visfly_b200.envs import HoverEnv
+
+    class UserHover(HoverEnv):
+        def get_reward(self, predicted_obs=None):
+            return (0.1 - (self.position - self.target).norm(dim=1) * (0.1 / 9)
+                    - (self.orientation - self._unit_quat).norm(dim=1) * 1e-5
+                    - self.velocity.norm(dim=1) * 0.002 - self.angular_velocity.norm(dim=1) * 0.002)
+
+    out = {"workload": "HoverEnv subclass with its own get_reward (tensor code), 65536 agents, RK4 x8"}
+    acts = list(hover_actions(n, 4, dev, seed=3).unbind(0))
+    for name, split in (("two_launch_path", True), ("generic_path", False)):
+        env = UserHover(num_agent_per_scene=n, visual=False, device=dev, dynamics_kwargs=dict(DYN), seed=77,
+                        max_episode_steps=256, tensor_output=True)
+        env.use_fused_step = split
+        env.reset()
+        for i in range(max(W, 30)):
+            env.step(acts[i % 4])
+        steps = max(K, 50)
+        barrier()
+        e0, e1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record(stream)
+        for i in range(steps):
+            env.step(acts[i % 4])
+        e1.record(stream)
+        e1.synchronize()
+        ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)
+        out[name] = {"value": n * steps / (ms * 1e-3), "unit": UNIT, "us_per_step": ms * 1e3 / steps,
+                     "active": bool(env._split is not None and env._split.active)}
+    return out
+
+
 def run_ours(args):
     import torch.distributed as dist
     from visfly_b200 import _lib
@@ -714,6 +750,7 @@ def run_ours(args):
             apg = eager
 
     racing = None if args.no_racing else racing_leg(n, dev, rank, world, K, W, stream, barrier)
+    custom = None if args.no_racing else custom_task_leg(n, dev, K, W, stream, barrier)
     clk.__exit__(None, None, None)
 
     ref_gpu = None
@@ -739,7 +776,7 @@ def run_ours(args):
                 "hot_l2_bracketed_value": "one env back to back (12 MB working set resident in L2)",
                 "host_affinity": None if numa_cpus is None else f"rank 0 pinned to {len(numa_cpus)} CPUs next to its GPU"},
             "clocks": clk.summary(), "e2e": e2e, "gpu_launches": K * env_launches_per_step(env), "apg": apg,
-            "racing": racing, "roofline": roofline, "cpu_baseline": cpu, "reference_dynamics_on_gpu": ref_gpu,
+            "racing": racing, "custom_task": custom, "roofline": roofline, "cpu_baseline": cpu, "reference_dynamics_on_gpu": ref_gpu,
             "rollout_collective_us": collective_us,
             "rollout_collective": {"fused_into_last_step": gather.fused, "why_not": gather.why_not,
                                    "us_added_to_the_bracket": collective_us,
