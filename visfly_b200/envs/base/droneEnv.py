@@ -21,7 +21,19 @@ from ...type import Normal, Uniform
 IS_BBOX_COLLISION = True
 
 
+def _watched(name):
+    from .fused import watched
+    return watched(name)
+
+
 class DroneEnvsBase:
+    # settings the one-kernel env step bakes into its spec: assigning one is noticed on the next step (fused.watched)
+    _gen = 0
+    stateGenerator = _watched("stateGenerator")
+    _reset_table = _watched("_reset_table")
+    uav_radius = _watched("uav_radius")
+    _bboxes = _watched("_bboxes")
+
     def __init__(
             self,
             num_agent_per_scene: int = 1,

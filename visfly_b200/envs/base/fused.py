@@ -136,6 +136,24 @@ def _ver(t):
     return -1 if t is None else t._version
 
 
+def watched(name: str) -> property:
+    """Attribute whose assignment bumps the owner's ``_gen`` counter (see ``FusedEnvStep.refresh``)."""
+    key = "_w_" + name
+
+    def get(self):
+        try:
+            return self.__dict__[key]
+        except KeyError:
+            raise AttributeError(name) from None
+
+    def put(self, value):
+        d = self.__dict__
+        d[key] = value
+        d["_gen"] = d.get("_gen", 0) + 1
+
+    return property(get, put)
+
+
 class FusedEnvStep:
     """Owns the spec and the per-agent env status records of one env object while the fused path is active.
 
@@ -167,7 +185,7 @@ class FusedEnvStep:
         self.peer_next = 0                           # address of a VfPeerScatter for the NEXT launch (fused all-gather)
         self.peer_done = False                       # ... and whether that launch has happened
         self._views = (None, None)
-        self._key, self._watch, self._watch_sum, self._ok = None, (), 0, False
+        self._gen_seen, self._ndict, self._watch, self._watch_sum, self._ok = -1, None, (), 0, False
         # host-driven (numpy) mode runs one step ahead of its caller: steps launched but not yet handed out, and the
         # (state, status) the next launch starts from.  See step_host / rewind.
         self._ahead = collections.deque()
@@ -242,26 +260,22 @@ class FusedEnvStep:
     # -- eligibility ------------------------------------------------------------------------------------
     def refresh(self) -> bool:
         """Re-read the settings that may change between steps; False => the generic path must be used.
-        The answer is cached on the identity of every object it was derived from plus the version counters of the
-        tensors among them, so in-place edits (``env.target[:] = ...``, generator tables) are seen as well as
-        re-assignments.  Runs once per step: straight-line identity tests, about a microsecond."""
-        env = self.env
-        envs = env.envs
-        d = env.__dict__
-        k = self._key
-        if k is not None and envs.stateGenerator is k[0] and envs._reset_table is k[1] \
-                and env.max_episode_steps == k[2] and env.is_collision_reset == k[3] and env.use_fused_step == k[4] \
-                and d.get("target") is k[5] and d.get("targets") is k[6] and d.get("success_radius") == k[7] \
-                and envs.uav_radius == k[8] and envs._bboxes[0] is k[9] and (envs.dynamics._wind_fn is None) == k[10]:
+        The settings the spec is built from are *watched* attributes of the env objects (``watched`` below): assigning
+        one bumps a generation counter, and in-place edits of the tensors among them (``env.target[:] = ...``, generator
+        tables) show in their version counters.  Runs once per step: two integer compares and a short sum."""
+        d, de = self.env.__dict__, self.env.envs.__dict__
+        # instance-level overrides (a monkeypatched task method, a replaced state generator function) are plain
+        # attributes: their presence is part of the key
+        inst = ("_generate_state" in de, "get_reward" in d or "get_success" in d or "get_failure" in d
+                or "get_observation" in d)
+        if d.get("_gen", 0) + de.get("_gen", 0) == self._gen_seen and inst == self._ndict:
             vsum = 0
             for t in self._watch:
                 vsum += t._version
             if vsum == self._watch_sum:
                 return self._ok
-        self._key = (envs.stateGenerator, envs._reset_table, env.max_episode_steps, env.is_collision_reset,
-                     env.use_fused_step, d.get("target"), d.get("targets"), d.get("success_radius"), envs.uav_radius,
-                     envs._bboxes[0], envs.dynamics._wind_fn is None)
         self._ok = self._refresh()
+        self._gen_seen, self._ndict = d.get("_gen", 0) + de.get("_gen", 0), inst
         self._watch_sum = sum(t._version for t in self._watch)
         return self._ok
 
