@@ -220,6 +220,8 @@ class FusedEnvStep:
     def _make_stepper(self):
         """Bind what does not change from step to step (parameter blocks, kernel variant, reset table, the device
         word of the Philox step base) into the C++ stepper; rebuilt whenever one of those is replaced."""
+        if self._fn is None:                  # a deep copy re-binds its ctypes handles on first use
+            self._bind()
         cfg = self.env.envs.dynamics._cfg
         self._stepper = self._fn(self._params_addr, self._spec_addr, cfg.substeps, cfg.integrator, cfg.action_type,
                                  cfg.flags, self.n, self.table, self.obs_width, self.step_base)
