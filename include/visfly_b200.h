@@ -365,6 +365,20 @@ int vf_env_finish(const VfParams* params, const VfEnvSpec* spec, int n, unsigned
                   const unsigned char* success, const unsigned char* failure, float* state_out, int* status_out,
                   float* obs_out, unsigned char* done_out, float* record_out, void* stream);
 
+/*
+ * Renderer hand-off, ingestion side: what the reference does on the host, per agent and sensor,
+ * to the images a renderer returns (envs/base/droneEnv.py:296-331: np.stack, expand_dims / transpose,
+ * np.where(depth == 0, 20, depth)) — as one streaming launch per sensor over a batched image buffer.  `src` is device
+ * memory or the page-locked host buffer the renderer wrote (read zero-copy); `dst` is device memory.
+ *   vf_ingest_depth : float (n, H, W) -> (n, 1, H, W), zeros (no return) replaced by `background` (the reference uses 20)
+ *   vf_ingest_color : uint8 (n, H, W, 4) RGBA -> (n, 3, H, W), alpha dropped; H * W must be a multiple of 4
+ */
+int vf_ingest_depth(long long n_images, int height, int width, const float* src, float* dst, float background,
+                    void* stream);
+int vf_ingest_color(long long n_images, int height, int width, const unsigned char* src, unsigned char* dst,
+                    void* stream);
+const char* vf_sensor_last_error(void);
+
 /* =====================================================================================================
  * Deterministic actor of the analytic-gradient trainers (SURVEY.md §8 row n3 / BASELINE configs[2]): the policy the
  * reference's BPTT / SHAC loops evaluate once per env step (utils/algorithms/BPTT.py:107-115, shac.py:213-222)

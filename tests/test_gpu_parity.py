@@ -556,3 +556,39 @@ def test_diagnostics_notice_an_overwritten_action_without_a_fifo():
         d.acceleration
     d.step(buf)
     assert d.acceleration.shape == acc.shape
+
+
+@pytest.mark.parametrize("host", [True, False])
+def test_sensor_ingest_matches_the_reference_post_processing(host):
+    """Renderer hand-off, ingestion side: per-agent frames -> observation tensors exactly as the
+    reference's `update_observation` builds them on the host (envs/base/droneEnv.py:296-312: np.stack, expand_dims /
+    transpose, np.where(depth == 0, 20, depth)), from page-locked host buffers (zero-copy) and from device buffers."""
+    from visfly_b200.render_handoff import SensorIngest
+    rng = np.random.default_rng(4)
+    for n, h, w in ((37, 64, 64), (5, 9, 7), (4096, 64, 64) if not host else (300, 48, 36)):
+        per_agent = []
+        for _ in range(n if n < 400 else 3):           # per-agent dicts as a renderer returns them
+            d = rng.random((h, w), dtype=np.float32) * 8
+            d[rng.random((h, w)) < 0.2] = 0.0           # no-return pixels
+            per_agent.append({"depth": d, "color": rng.integers(0, 256, (h, w, 4), dtype=np.uint8),
+                              "semantic": rng.integers(0, 40, (h, w)).astype(np.float32)})
+        per_agent = (per_agent * (n // len(per_agent) + 1))[:n]
+        # the reference's lines, verbatim in numpy
+        ref_depth = np.expand_dims(np.stack([o["depth"] for o in per_agent]), 1)
+        ref_depth = np.where(ref_depth == 0, 20, ref_depth)
+        ref_color = np.transpose(np.stack([o["color"] for o in per_agent])[..., :3], (0, 3, 1, 2))
+        ref_sem = np.expand_dims(np.stack([o["semantic"] for o in per_agent]), 1)
+        sensors = {"depth": (h, w), "semantic": (h, w)}
+        if (h * w) % 4 == 0:
+            sensors["color"] = (h, w)
+        ing = SensorIngest(n, sensors, device="cuda", host=host)
+        for uuid in sensors:
+            ing.buffer(uuid).copy_(th.from_numpy(np.stack([o[uuid] for o in per_agent])))
+        out = ing.ingest()
+        th.cuda.synchronize()
+        assert out["depth"].shape == (n, 1, h, w) and np.array_equal(out["depth"].cpu().numpy(), ref_depth)
+        assert np.array_equal(out["semantic"].cpu().numpy(), ref_sem)
+        if "color" in sensors:
+            assert out["color"].dtype == th.uint8 and np.array_equal(out["color"].cpu().numpy(), ref_color)
+    with pytest.raises(KeyError):
+        SensorIngest(4, {"lidar": (8, 8)})

@@ -40,6 +40,9 @@ SIGNATURES = {
     "vf_export_pose_habitat": (_i, [_P(VfParams), _i, _vp, _vp, _vp, _vp]),
     "vf_env_spec_size": (_i, []),
     "vf_wait_flag": (_i, [_vp, _u, ctypes.c_longlong]),
+    "vf_ingest_depth": (_i, [ctypes.c_longlong, _i, _i, _vp, _vp, ctypes.c_float, _vp]),
+    "vf_ingest_color": (_i, [ctypes.c_longlong, _i, _i, _vp, _vp, _vp]),
+    "vf_sensor_last_error": (ctypes.c_char_p, []),
     "vf_env_finish": (_i, [_P(VfParams), _P(VfEnvSpec), _i, _u, ctypes.c_ulonglong, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                            _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "vf_policy_packed_floats": (_i, [_i]),
@@ -364,3 +367,22 @@ def policy_bwd(xa: th.Tensor, xb: Optional[th.Tensor], packed: th.Tensor, h: int
                                         _dev_ptr(g_a, "grad_xa"), _dev_ptr(g_b, "grad_xb"), partial.data_ptr(),
                                         flat.data_ptr(), _stream(xa.device)))
     return g_a, g_b, flat
+
+
+def ingest_depth(src: th.Tensor, dst: th.Tensor, background: float = 20.0) -> None:
+    """Binding of ``vf_ingest_depth``: ``src`` float32 (n,H,W) on the device or in page-locked host memory, ``dst``
+    float32 (n,1,H,W) on the device."""
+    lib = load(require_cuda=True)
+    n, h, w = src.shape
+    with th.cuda.device(dst.device):
+        if lib.vf_ingest_depth(n, h, w, src.data_ptr(), dst.data_ptr(), float(background), _stream(dst.device)):
+            raise RuntimeError("visfly_b200: " + lib.vf_sensor_last_error().decode())
+
+
+def ingest_color(src: th.Tensor, dst: th.Tensor) -> None:
+    """Binding of ``vf_ingest_color``: ``src`` uint8 (n,H,W,4), ``dst`` uint8 (n,3,H,W) on the device."""
+    lib = load(require_cuda=True)
+    n, h, w, _ = src.shape
+    with th.cuda.device(dst.device):
+        if lib.vf_ingest_color(n, h, w, src.data_ptr(), dst.data_ptr(), _stream(dst.device)):
+            raise RuntimeError("visfly_b200: " + lib.vf_sensor_last_error().decode())

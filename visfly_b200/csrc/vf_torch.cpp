@@ -7,6 +7,8 @@
 // tensor contents: allocation, pointer extraction, launch.
 #include <torch/extension.h>
 
+#include <chrono>
+
 #include <c10/cuda/CUDACachingAllocator.h>
 #include <c10/cuda/CUDAGuard.h>
 #include <c10/cuda/CUDAStream.h>
@@ -172,6 +174,44 @@ class EnvStepper {
         return {state_out, status, obs, reward, done, record, term, copy, gate};
     }
 
+    // host-cost breakdown of step() (diagnostic, tools/host_profile.py): microseconds per call of (allocation + carving),
+    // (the C-ABI launch alone, outputs reused), over `iters` repetitions
+    std::tuple<double, double> profile(const at::Tensor& state_in, const at::Tensor& action, const at::Tensor& status_in,
+                                       int64_t iters) {
+        c10::cuda::CUDAGuard guard(state_in.device());
+        const auto t0 = std::chrono::steady_clock::now();
+        for (int64_t i = 0; i < iters; ++i) {
+            const Slab slab{alloc_slab(o_copy_ + sz_copy_ + sz_term_), state_in.key_set()};
+            at::Tensor a = carve(slab, 0, at::kFloat, {VF_STATE_PLANES, n_, 4});
+            at::Tensor b = carve(slab, o_status_, at::kInt, {n_, VF_STATUS_WORDS});
+            at::Tensor c = carve(slab, o_obs_, at::kFloat, {n_, obs_width_});
+            at::Tensor d = carve(slab, o_rew_, at::kFloat, {n_});
+            at::Tensor e = carve(slab, o_rec_, at::kFloat, {n_, 4});
+            at::Tensor f = carve(slab, o_done_, at::kBool, {n_});
+            at::Tensor g = carve(slab, o_copy_, at::kFloat, {n_, 4});
+            at::Tensor h = carve(slab, o_copy_ + sz_copy_, at::kFloat, {n_, obs_width_});
+        }
+        const auto t1 = std::chrono::steady_clock::now();
+        const Slab slab{alloc_slab(o_copy_ + sz_copy_ + sz_term_), state_in.key_set()};
+        at::Tensor so = carve(slab, 0, at::kFloat, {VF_STATE_PLANES, n_, 4});
+        at::Tensor st = carve(slab, o_status_, at::kInt, {n_, VF_STATUS_WORDS});
+        at::Tensor ob = carve(slab, o_obs_, at::kFloat, {n_, obs_width_});
+        at::Tensor rw = carve(slab, o_rew_, at::kFloat, {n_});
+        at::Tensor rc = carve(slab, o_rec_, at::kFloat, {n_, 4});
+        at::Tensor dn = carve(slab, o_done_, at::kBool, {n_});
+        auto stream = c10::cuda::getCurrentCUDAStream(state_in.device().index()).stream();
+        for (int64_t i = 0; i < iters; ++i)
+            vf_env_step_fwd(params_, spec_, int(n_), substeps_, integrator_, action_type_, flags_, 0u,
+                            (unsigned long long)i, nullptr, state_in.data_ptr<float>(), action.data_ptr<float>(), nullptr,
+                            nullptr, static_cast<const float*>(ptr(reset_table_)), status_in.data_ptr<int>(),
+                            so.data_ptr<float>(), st.data_ptr<int>(), nullptr, ob.data_ptr<float>(), rw.data_ptr<float>(),
+                            reinterpret_cast<unsigned char*>(dn.data_ptr<bool>()), rc.data_ptr<float>(), nullptr, nullptr,
+                            nullptr, nullptr, stream);
+        const auto t2 = std::chrono::steady_clock::now();
+        const double us = 1e6 / double(iters);
+        return {std::chrono::duration<double>(t1 - t0).count() * us, std::chrono::duration<double>(t2 - t1).count() * us};
+    }
+
   private:
     const VfParams* params_;
     const VfEnvSpec* spec_;
@@ -202,6 +242,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
           py::arg("wind") = py::none(), py::arg("push") = py::none());
     py::class_<EnvStepper>(m, "EnvStepper")
         .def(py::init<int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, OptTensor, int64_t, OptTensor>())
+        .def("profile", &EnvStepper::profile)
         .def("step", &EnvStepper::step, py::arg("state_in"), py::arg("action"), py::arg("status_in"),
              py::arg("step_index"), py::arg("env_flags"), py::arg("want_term"), py::arg("host_mirror"),
              py::arg("wind") = py::none(), py::arg("push") = py::none(), py::arg("peer_returns") = 0);
