@@ -332,10 +332,7 @@ VF_HD void euler_to_quat(const float e[3], float q[4]) {
 }
 
 // Fresh initial state of one agent (position, quaternion, velocity, body rates).
-// Deliberately NOT inlined on the device: an agent restarts once per episode (one step in a few hundred), while the
-// sampler — ten Philox rounds per draw, Box-Muller with the slow paths of logf / cosf — is a third of the env
-// kernel's code.  Kept out of line, the per-step path stays contiguous in the instruction cache and keeps its
-// registers.
+// (An out-of-line version of this function was measured and dropped, see VF_HD_COLD in vf_math.cuh.)
 VF_HD_COLD void sample_reset(const VfEnvSpec& E, unsigned agent, unsigned long long step, const float* table_row,
                         float p[3], float q[4], float v[3], float w[3]) {
     if (E.gen_kind == VF_GEN_TABLE) {

@@ -30,7 +30,10 @@
 
 #if defined(__CUDACC__)
 #define VF_HD __host__ __device__ __forceinline__
-#define VF_HD_COLD __host__ __device__ __noinline__
+// "cold" helpers (the reset sampler) stay INLINE: an out-of-line call made the per-step text contiguous, but a kernel
+// with a call stack no longer overlaps its launch with the previous grid under programmatic dependent launch — the
+// step loop lost 1.1 us per step (hot 10.5 -> 11.7 us, cold 12.4 -> 13.8; tools/ab_loop.py, same box)
+#define VF_HD_COLD __host__ __device__ __forceinline__
 #else
 #define VF_HD inline
 #define VF_HD_COLD inline
