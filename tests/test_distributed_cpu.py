@@ -67,3 +67,31 @@ def test_bind_host_to_gpu_degrades_to_a_no_op_without_a_gpu():
     assert got is None or set(got) <= before
     if got is None:
         assert os.sched_getaffinity(0) == before
+
+
+def _fused_fallback_worker(rank, world, port, n_total, out):
+    import types
+    from visfly_b200.distributed import FusedReturnsGather
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        lo, hi = shard_range(n_total, rank, world)
+        g = FusedReturnsGather(hi - lo, n_total, rank, world, "cpu")     # no peer-mapped memory on CPU: NCCL-style path
+        env = types.SimpleNamespace(_fused=None, use_fused_step=True, num_agent=hi - lo,
+                                    _rewards=th.arange(lo, hi, dtype=th.float32) * 2.0)
+        g.arm(env)
+        full = g.finish(env)
+        out[rank] = (g.fused, bool(th.equal(full, th.arange(n_total, dtype=th.float32) * 2.0)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_fused_returns_gather_falls_back_to_the_collective_without_peer_memory():
+    """`FusedReturnsGather` (episode returns scattered by the rollout's last env step over NVLink peer mappings) must
+    degrade to the one-shot all-gather on every rank where peer mappings do not exist — here: CPU tensors over gloo,
+    ragged shards."""
+    world, n_total = 2, 11
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_fused_fallback_worker, args=(world, _free_port(), n_total, out), nprocs=world, join=True)
+        assert dict(out) == {0: (False, True), 1: (False, True)}
