@@ -420,8 +420,9 @@ def racing_leg(n_weak, dev, rank, world, K, W, stream, barrier):
 
 def custom_task_leg(n, dev, K, W, stream, barrier):
     """A task env as a user would write it — HoverEnv's reward re-stated in a subclass, so that the env no longer
-    qualifies for the one-kernel step — on the two-launch path (control step kernel + the task's tensor ops +
-    vf_env_finish) and on the generic tensor-op path beside it (what such envs ran on in round 1)."""
+    qualifies for the one-kernel step — as one CUDA-graph replay per step (env.capture_task_step), on the eager
+    two-launch path (control step kernel + the task's tensor ops + vf_env_finish) and on the generic tensor-op path
+    (what such envs ran on in round 1)."""
     from visfly_b200.envs import HoverEnv
 
     class UserHover(HoverEnv):
@@ -432,10 +433,12 @@ def custom_task_leg(n, dev, K, W, stream, barrier):
 
     out = {"workload": "HoverEnv subclass with its own get_reward (tensor code), 65536 agents, RK4 x8"}
     acts = list(hover_actions(n, 4, dev, seed=3).unbind(0))
-    for name, split in (("two_launch_path", True), ("generic_path", False)):
+    for name, split, capture in (("recorded_step", True, True), ("recorded_step_copied_outputs", True, "copy"),
+                                 ("two_launch_path", True, False), ("generic_path", False, False)):
         env = UserHover(num_agent_per_scene=n, visual=False, device=dev, dynamics_kwargs=dict(DYN), seed=77,
                         max_episode_steps=256, tensor_output=True)
         env.use_fused_step = split
+        env.capture_task_step = capture
         env.reset()
         for i in range(max(W, 30)):
             env.step(acts[i % 4])
@@ -450,7 +453,8 @@ def custom_task_leg(n, dev, K, W, stream, barrier):
         e1.synchronize()
         ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)
         out[name] = {"value": n * steps / (ms * 1e-3), "unit": UNIT, "us_per_step": ms * 1e3 / steps,
-                     "active": bool(env._split is not None and env._split.active)}
+                     "active": bool(env._split is not None and env._split.active),
+                     "graph_replays": 0 if env._task_graph is None else env._task_graph.replays}
     return out
 
 

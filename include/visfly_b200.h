@@ -45,7 +45,7 @@
 extern "C" {
 #endif
 
-#define VF_ABI_VERSION 7
+#define VF_ABI_VERSION 8
 
 /* integrator: reference `integrator=` kwarg, utils/maths.py:331 (euler) and :353 (rk4, repaired R1-R3) */
 #define VF_INTEGRATOR_EULER 0
@@ -129,6 +129,22 @@ int vf_step_fwd(const VfParams* params, int n, int substeps, int integrator, int
                 unsigned flags, const float* state_in, const float* action,
                 float* state_out, float* obs_out, float* ext_out, const float* wind,
                 const float* fifo_push, float* fifo_copy, void* stream);
+
+/* The comm-delay FIFO as a device-resident ring: `depth` engine-owned rows of [n][4] floats (16-byte aligned), row[0]
+ * the oldest.  Used where addresses must not change from step to step (a step recorded as a CUDA graph):
+ *   vf_step_fwd_ring consumes row[0] as the delayed action, moves row[r+1] -> row[r] and stores fifo_push into
+ *                    row[depth-1] — per agent, in place, in the step's own launch (dynamics.py:323-328);
+ *   vf_env_finish    zeroes the rows of the agents it re-initialises (dynamics.py:262-263). */
+#define VF_FIFO_MAX_ROWS 8
+typedef struct VfFifoRows {
+    float* row[VF_FIFO_MAX_ROWS];
+    int    depth;              /* 1..VF_FIFO_MAX_ROWS */
+} VfFifoRows;
+
+/* vf_step_fwd with the FIFO shifted inside the launch: arguments as vf_step_fwd, `action` replaced by the ring. */
+int vf_step_fwd_ring(const VfParams* params, int n, int substeps, int integrator, int action_type, unsigned flags,
+                     const float* state_in, const VfFifoRows* fifo_rows, const float* fifo_push, float* state_out,
+                     float* obs_out, float* ext_out, const float* wind, void* stream);
 
 /*
  * Reverse-mode gradient of vf_step_fwd: re-runs the substeps from (state_in, action) in registers /
@@ -358,12 +374,14 @@ int vf_env_step_bwd(const VfParams* params, const VfEnvSpec* spec, int n, int su
  *   state_in   [5][n][4]  state AFTER the control step            reward float[n]   success / failure uint8[n]
  *   state_out  [5][n][4]  = state_in, finished agents re-initialised (must not alias state_in)
  *   obs_out    [n][13] or NULL: the reference `state` after the reset      done_out uint8[n]     record_out float[n][4]
+ *   fifo_rows  NULL, or the comm-delay FIFO rows to zero for re-initialised agents (VfFifoRows above)
  */
 int vf_env_finish(const VfParams* params, const VfEnvSpec* spec, int n, unsigned env_flags,
                   unsigned long long step_index, const unsigned long long* step_base, const float* state_in,
                   const float* wind, const float* reset_table, const int* status_in, const float* reward,
                   const unsigned char* success, const unsigned char* failure, float* state_out, int* status_out,
-                  float* obs_out, unsigned char* done_out, float* record_out, void* stream);
+                  float* obs_out, unsigned char* done_out, float* record_out, const VfFifoRows* fifo_rows,
+                  void* stream);
 
 /*
  * Renderer hand-off, ingestion side: what the reference does on the host, per agent and sensor,

@@ -41,12 +41,13 @@ def test_abi_version_and_struct_layout():
     body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
     fields = re.findall(r"float\s+([A-Za-z_]+)", body)
     assert fields == [f[0] for f in VfParams._fields_]
-    from visfly_b200.params import VfEnvMirror, VfEnvSpec
+    from visfly_b200.params import VfEnvMirror, VfEnvSpec, VfFifoRows, VfPeerScatter
     assert lib.vf_env_spec_size() == ctypes.sizeof(VfEnvSpec)
-    for name, cls in (("VfEnvSpec", VfEnvSpec), ("VfEnvMirror", VfEnvMirror)):
+    for name, cls in (("VfEnvSpec", VfEnvSpec), ("VfEnvMirror", VfEnvMirror), ("VfFifoRows", VfFifoRows),
+                      ("VfPeerScatter", VfPeerScatter)):
         body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (name, name), hdr, flags=re.S).group(1)
         body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
-        fields = re.findall(r"(?:float|int|unsigned long long|unsigned)\s*\*?\s+([A-Za-z_]+)", body)
+        fields = re.findall(r"(?:float|int|unsigned long long|long long|unsigned)\s*\*?\s+([A-Za-z_]+)", body)
         assert fields == [f[0] for f in cls._fields_], name
 
 
@@ -71,6 +72,23 @@ def test_argument_validation_needs_no_gpu():
     x = ctypes.c_void_p(16)
     assert lib.vf_step_fwd(ctypes.byref(p), 4, 4, 0, 1, 1, x, x, ctypes.c_void_p(32), None, None, None, x, None, None) != 0
     assert b"fifo_push and fifo_copy" in lib.vf_last_error()
+    # the device-resident FIFO ring
+    from visfly_b200.params import VfFifoRows
+    ring = VfFifoRows()
+    assert lib.vf_step_fwd_ring(ctypes.byref(p), 4, 4, 0, 1, 1, x, None, x, ctypes.c_void_p(32), None, None, None, None) != 0
+    assert b"fifo_rows" in lib.vf_last_error()
+    ring.depth = 9
+    assert lib.vf_step_fwd_ring(ctypes.byref(p), 4, 4, 0, 1, 1, x, ctypes.byref(ring), x, ctypes.c_void_p(32), None, None,
+                                None, None) != 0
+    assert b"VF_FIFO_MAX_ROWS" in lib.vf_last_error()
+    ring.depth, ring.row[0], ring.row[1] = 2, 64, 64
+    assert lib.vf_step_fwd_ring(ctypes.byref(p), 4, 4, 0, 1, 1, x, ctypes.byref(ring), x, ctypes.c_void_p(32), None, None,
+                                None, None) != 0
+    assert b"distinct" in lib.vf_last_error()
+    ring.row[1] = 16
+    assert lib.vf_step_fwd_ring(ctypes.byref(p), 4, 4, 0, 1, 1, x, ctypes.byref(ring), x, ctypes.c_void_p(32), None, None,
+                                None, None) != 0
+    assert b"alias a FIFO row" in lib.vf_last_error()
     assert lib.vf_wait_flag(None, 1, 10) != 0
     flag = ctypes.c_uint(7)
     assert lib.vf_wait_flag(ctypes.byref(flag), 7, 10) == 0                 # already raised

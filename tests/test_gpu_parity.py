@@ -542,6 +542,46 @@ def test_comm_delay_fifo_owns_a_copy_of_every_action_like_the_reference():
     assert rel_l2(ga.cpu(), go) < GRAD_TOL
 
 
+def test_fifo_ring_entry_point_flies_the_list_fifo_trajectory_and_finish_zeroes_rows():
+    """``vf_step_fwd_ring`` (the comm-delay FIFO as a device-resident ring, shifted in place by the step launch) against
+    ``Dynamics.step`` with its list-of-tensors FIFO: same states, same diagnostics, entries keep their addresses; and
+    ``vf_env_finish`` zeroes the ring rows of exactly the agents it re-initialises (reference dynamics.py:262-263)."""
+    from visfly_b200 import _lib
+    from visfly_b200 import params as P
+    n = 200
+    kw = dict(action_type="bodyrate", integrator="rk4", dt=0.0025, ctrl_dt=0.02, comm_delay=0.06)
+    g = th.Generator().manual_seed(11)
+    acts = (th.rand(9, n, 4, generator=g) * 2 - 1).cuda()
+    a, b = make_dynamics(n, **kw), make_dynamics(n, **kw)
+    b._fifo_ring = True
+    ptrs = [t.data_ptr() for t in b._pre_action]
+    with th.no_grad():
+        for t in range(9):
+            sa, sb = a.step(acts[t]), b.step(acts[t])
+            assert th.equal(sa, sb) and th.equal(a.acceleration, b.acceleration) and th.equal(a.thrusts, b.thrusts)
+            assert [x.data_ptr() for x in b._pre_action] == ptrs
+            for x, y in zip(a._pre_action, b._pre_action):
+                assert th.equal(x, y)
+    # wrapper tail: rows of the agents that end here (time limit for odd agents) are zeroed in every FIFO entry
+    spec = P.VfEnvSpec()
+    spec.task, spec.obs_kind, spec.max_episode_steps, spec.fifo_depth = P.TASK_CUSTOM, P.OBS_STATE13, 5, 3
+    spec.uav_radius, spec.success_radius, spec.init_motor_omega, spec.seed = 0.1, 0.5, float(b._init_motor_omega), 9
+    for j in range(3):
+        spec.bbox_lo[j], spec.bbox_hi[j] = -1e3, 1e3
+        spec.gen_mean[0][0][j], spec.gen_half[0][0][j] = 0.0, 1.0
+    spec.gen_kind, spec.gen_boxes = P.GEN_UNIFORM, 1
+    sc = th.where(th.arange(n, device="cuda") % 2 == 1, 4, 0).to(th.int32)
+    status = _lib.pack_status(sc, th.zeros(n, device="cuda"), th.zeros(n, dtype=th.int32, device="cuda"))
+    before = [x.clone() for x in b._pre_action]
+    state_out, status_out, obs, done, record = _lib.env_finish(
+        b._cfg.params, spec, 0, 0, b._state, status, th.zeros(n, device="cuda"), None, None, fifo=b._pre_action,
+        status_out=status)
+    assert status_out is status and th.equal(done, sc == 4) and bool(done.any()) and not bool(done.all())
+    for x, y in zip(before, b._pre_action):
+        assert th.equal(y, th.where(done.view(-1, 1), 0.0, x))
+    assert th.equal(status[:, 0], th.where(done, 0, sc + 1).to(th.int32))
+
+
 def test_diagnostics_notice_an_overwritten_action_without_a_fifo():
     """comm_delay=0 keeps no copy of the action; the on-demand diagnostics re-run the step on its inputs and must
     refuse if the caller has overwritten the action buffer in the meantime (instead of reporting a different step)."""

@@ -11,11 +11,11 @@ from typing import Optional
 
 import torch as th
 
-from .params import VfEnvMirror, VfEnvSpec, VfParams, VfPeerScatter
+from .params import FIFO_MAX_ROWS, VfEnvMirror, VfEnvSpec, VfFifoRows, VfParams, VfPeerScatter
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvisfly_b200.so")
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 INTEGRATOR_ID = {"euler": 0, "rk4": 1}
 FLAG_CTRL_DELAY = 1
@@ -33,6 +33,7 @@ SIGNATURES = {
     "vf_params_size": (_i, []),
     "vf_device_sm_count": (_i, []),
     "vf_step_fwd": (_i, [_P(VfParams), _i, _i, _i, _i, _u, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "vf_step_fwd_ring": (_i, [_P(VfParams), _i, _i, _i, _i, _u, _vp, _P(VfFifoRows), _vp, _vp, _vp, _vp, _vp, _vp]),
     "vf_step_bwd": (_i, [_P(VfParams), _i, _i, _i, _i, _u, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "vf_step_fwd_host": (_i, [_P(VfParams), _i, _i, _i, _i, _u, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "vf_pack_state": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
@@ -44,7 +45,7 @@ SIGNATURES = {
     "vf_ingest_color": (_i, [ctypes.c_longlong, _i, _i, _vp, _vp, _vp]),
     "vf_sensor_last_error": (ctypes.c_char_p, []),
     "vf_env_finish": (_i, [_P(VfParams), _P(VfEnvSpec), _i, _u, ctypes.c_ulonglong, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
-                           _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+                           _vp, _vp, _vp, _vp, _vp, _vp, _P(VfFifoRows), _vp]),
     "vf_policy_packed_floats": (_i, [_i]),
     "vf_policy_pack": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "vf_policy_fwd": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, ctypes.c_float, ctypes.c_float, _vp, _vp]),
@@ -146,6 +147,36 @@ def step_fwd(params: VfParams, substeps: int, integrator: int, action_type: int,
                                _dev_ptr(ext_out, "ext_out"), _dev_ptr(wind, "wind"),
                                _dev_ptr(fifo_push, "fifo_push"), _dev_ptr(fifo_copy, "fifo_copy"),
                                _stream(state_in.device)))
+
+
+def fifo_rows(rows) -> Optional[VfFifoRows]:
+    """``struct VfFifoRows`` over a list of engine-owned (n,4) FIFO entries (oldest first); None for an empty list."""
+    if not rows:
+        return None
+    if len(rows) > FIFO_MAX_ROWS:
+        raise ValueError(f"comm-delay FIFO deeper than VF_FIFO_MAX_ROWS ({FIFO_MAX_ROWS})")
+    r = VfFifoRows()
+    for j, t in enumerate(rows):
+        r.row[j] = _dev_ptr(t, "fifo row")
+    r.depth = len(rows)
+    return r
+
+
+def step_fwd_ring(params: VfParams, substeps: int, integrator: int, action_type: int, flags: int,
+                  state_in: th.Tensor, rows, fifo_push: th.Tensor, state_out: th.Tensor,
+                  obs_out: Optional[th.Tensor], ext_out: Optional[th.Tensor] = None,
+                  wind: Optional[th.Tensor] = None) -> None:
+    """Binding of ``vf_step_fwd_ring``: the control step with the comm-delay FIFO (``rows``, oldest first) shifted in
+    place by the launch — consumes ``rows[0]``, appends ``fifo_push``."""
+    lib = load(require_cuda=True)
+    n = state_in.shape[1]
+    ring = fifo_rows(rows)
+    with th.cuda.device(state_in.device):
+        _check(lib.vf_step_fwd_ring(ctypes.byref(params), n, substeps, integrator, action_type, flags,
+                                    _dev_ptr(state_in, "state_in"), None if ring is None else ctypes.byref(ring),
+                                    _dev_ptr(fifo_push, "fifo_push"), _dev_ptr(state_out, "state_out"),
+                                    _dev_ptr(obs_out, "obs_out"), _dev_ptr(ext_out, "ext_out"), _dev_ptr(wind, "wind"),
+                                    _stream(state_in.device)))
 
 
 def step_bwd(params: VfParams, substeps: int, integrator: int, action_type: int, flags: int,
@@ -280,12 +311,17 @@ def env_step_bwd(params: VfParams, spec: VfEnvSpec, substeps: int, integrator: i
 def env_finish(params: VfParams, spec: VfEnvSpec, env_flags: int, step_index: int, state_in: th.Tensor,
                status_in: th.Tensor, reward: th.Tensor, success: Optional[th.Tensor], failure: Optional[th.Tensor],
                want_obs: bool = True, wind: Optional[th.Tensor] = None, reset_table: Optional[th.Tensor] = None,
-               step_base: Optional[th.Tensor] = None):
+               step_base: Optional[th.Tensor] = None, fifo=None, state_out: Optional[th.Tensor] = None,
+               status_out: Optional[th.Tensor] = None):
     """Binding of ``vf_env_finish`` (wrapper tail for caller-defined tasks).  Allocates and returns
-    ``(state_out, status_out, obs | None, done, record)``."""
+    ``(state_out, status_out, obs | None, done, record)``.  ``fifo``: engine-owned comm-delay FIFO entries whose rows
+    are zeroed in place for re-initialised agents; ``state_out / status_out``: write there instead of allocating
+    (``status_out`` may be ``status_in`` itself)."""
     lib = load(require_cuda=True)
     n, dev = state_in.shape[1], state_in.device
-    state_out, status_out = th.empty_like(state_in), th.empty_like(status_in)
+    state_out = th.empty_like(state_in) if state_out is None else state_out
+    status_out = th.empty_like(status_in) if status_out is None else status_out
+    ring = fifo_rows(fifo)
     obs = th.empty((n, 13), dtype=th.float32, device=dev) if want_obs else None
     done = th.empty((n,), dtype=th.bool, device=dev)
     record = th.empty((n, 4), dtype=th.float32, device=dev)
@@ -295,8 +331,9 @@ def env_finish(params: VfParams, spec: VfEnvSpec, env_flags: int, step_index: in
             _any_ptr(step_base, "step_base", th.int64), _dev_ptr(state_in, "state_in"), _dev_ptr(wind, "wind"),
             _dev_ptr(reset_table, "reset_table"), _any_ptr(status_in, "status_in", th.int32),
             _dev_ptr(reward, "reward"), _any_ptr(success, "success", th.bool), _any_ptr(failure, "failure", th.bool),
-            state_out.data_ptr(), status_out.data_ptr(), None if obs is None else obs.data_ptr(), done.data_ptr(),
-            record.data_ptr(), _stream(dev)))
+            _dev_ptr(state_out, "state_out"), _any_ptr(status_out, "status_out", th.int32),
+            None if obs is None else obs.data_ptr(), done.data_ptr(), record.data_ptr(),
+            None if ring is None else ctypes.byref(ring), _stream(dev)))
     return state_out, status_out, obs, done, record
 
 

@@ -138,7 +138,7 @@ vf_step_fwd_kernel(const __grid_constant__ VfParams params, int n, int substeps,
                    const float* __restrict__ state_in, const float* __restrict__ action,
                    float* __restrict__ state_out, float* __restrict__ obs_out, float* __restrict__ ext_out,
                    const float* __restrict__ wind, const float* __restrict__ fifo_push,
-                   float* __restrict__ fifo_copy) {
+                   float* __restrict__ fifo_copy, const __grid_constant__ VfFifoRows ring) {
     __shared__ __align__(16) float s_obs[(BLOCK / 32) * kWarpObs];
     const vf::Params<float>& P = reinterpret_cast<const vf::Params<float>&>(params);
     const int i = blockIdx.x * BLOCK + threadIdx.x;
@@ -154,14 +154,23 @@ vf_step_fwd_kernel(const __grid_constant__ VfParams params, int n, int substeps,
     float wd[3] = {P.wind[0], P.wind[1], P.wind[2]};
     if (live) {
         load_state(state_in, n, i, s);
-        const float4 a4 = ldg4(action, size_t(i));
+        float4 a4;
+        if (ring.depth > 0) {
+            // device-resident FIFO ring (vf_step_fwd_ring): consume the oldest row, shift, append — this agent's rows only
+            a4 = *(reinterpret_cast<const float4*>(ring.row[0]) + i);
+            for (int r = 0; r + 1 < ring.depth; ++r)
+                stg4(ring.row[r], size_t(i), *(reinterpret_cast<const float4*>(ring.row[r + 1]) + i));
+            stg4(ring.row[ring.depth - 1], size_t(i), ldg4(fifo_push, size_t(i)));
+        } else {
+            a4 = ldg4(action, size_t(i));
+            // comm-delay FIFO: the engine-owned copy of the action that arrived this step (dynamics.py:324 `clone()`)
+            if (fifo_copy) stg4(fifo_copy, size_t(i), ldg4(fifo_push, size_t(i)));
+        }
         const float a[4] = {a4.x, a4.y, a4.z, a4.w};
         if (wind) {                                  // per-agent wind of this control step (wind functions)
             const float4 w4 = ldg4(wind, size_t(i));
             wd[0] = w4.x; wd[1] = w4.y; wd[2] = w4.z;
         }
-        // comm-delay FIFO: the engine-owned copy of the action that arrived this step (dynamics.py:324 `clone()`)
-        if (fifo_copy) stg4(fifo_copy, size_t(i), ldg4(fifo_push, size_t(i)));
         vf::step_fwd<float>(P, substeps, INTEG, ACT, LAG, a, s, k, wd);
         store_state(state_out, n, i, s);
         if (ext_out) {
@@ -406,7 +415,8 @@ vf_env_finish_kernel(const __grid_constant__ VfParams params, const __grid_const
                      const int* __restrict__ status_in, const float* __restrict__ reward_in,
                      const unsigned char* __restrict__ success_in, const unsigned char* __restrict__ failure_in,
                      float* __restrict__ state_out, int* __restrict__ status_out, float* __restrict__ obs_out,
-                     unsigned char* __restrict__ done_out, float* __restrict__ record_out) {
+                     unsigned char* __restrict__ done_out, float* __restrict__ record_out,
+                     const __grid_constant__ VfFifoRows ring) {
     __shared__ __align__(16) float s_obs[(BLOCK / 32) * kWarpObs];
     const vf::Params<float>& P = reinterpret_cast<const vf::Params<float>&>(params);
     const int i = blockIdx.x * BLOCK + threadIdx.x;
@@ -451,6 +461,8 @@ vf_env_finish_kernel(const __grid_constant__ VfParams params, const __grid_const
             for (int j = 0; j < 4; ++j) { s.q[j] = rq[j]; s.mot[j] = E.init_motor_omega; }
             s.al[0] = s.al[1] = s.al[2] = 0.f;
             sc = 0; ret = 0.f; ep_done = false; once = false;
+            for (int r = 0; r < ring.depth; ++r)         // actions still in flight to a re-initialised agent: dropped
+                stg4(ring.row[r], size_t(i), make_float4(0.f, 0.f, 0.f, 0.f));
         }
         store_state(state_out, n, i, s);
         const int ebo = int((ep_done ? VF_EBIT_EPISODE_DONE : 0u) | (once ? VF_EBIT_ONCE_COLLIDED : 0u));
@@ -706,15 +718,15 @@ int check_spec(const VfEnvSpec* spec, bool allow_custom = false) {
 
 template <int INTEG, int ACT, bool LAG>
 void launch_fwd(const VfParams& p, int n, int substeps, const float* si, const float* a, float* so, float* obs,
-                float* ext, const float* wind, const float* push, float* copy, cudaStream_t st) {
+                float* ext, const float* wind, const float* push, float* copy, const VfFifoRows& ring, cudaStream_t st) {
     switch (block_override()) {
-        case 32: launch_pdl(vf_step_fwd_kernel<INTEG, ACT, LAG, 32>, (n + 31) / 32, 32, st, p, n, substeps, si, a, so, obs, ext, wind, push, copy); return;
-        case 128: launch_pdl(vf_step_fwd_kernel<INTEG, ACT, LAG, 128>, (n + 127) / 128, 128, st, p, n, substeps, si, a, so, obs, ext, wind, push, copy); return;
-        case 256: launch_pdl(vf_step_fwd_kernel<INTEG, ACT, LAG, 256>, (n + 255) / 256, 256, st, p, n, substeps, si, a, so, obs, ext, wind, push, copy); return;
+        case 32: launch_pdl(vf_step_fwd_kernel<INTEG, ACT, LAG, 32>, (n + 31) / 32, 32, st, p, n, substeps, si, a, so, obs, ext, wind, push, copy, ring); return;
+        case 128: launch_pdl(vf_step_fwd_kernel<INTEG, ACT, LAG, 128>, (n + 127) / 128, 128, st, p, n, substeps, si, a, so, obs, ext, wind, push, copy, ring); return;
+        case 256: launch_pdl(vf_step_fwd_kernel<INTEG, ACT, LAG, 256>, (n + 255) / 256, 256, st, p, n, substeps, si, a, so, obs, ext, wind, push, copy, ring); return;
         default: break;
     }
     const int grid = (n + kBlock - 1) / kBlock;
-    launch_pdl(vf_step_fwd_kernel<INTEG, ACT, LAG, kBlock>, grid, kBlock, st, p, n, substeps, si, a, so, obs, ext, wind, push, copy);
+    launch_pdl(vf_step_fwd_kernel<INTEG, ACT, LAG, kBlock>, grid, kBlock, st, p, n, substeps, si, a, so, obs, ext, wind, push, copy, ring);
 }
 
 template <int INTEG, int ACT, bool LAG>
@@ -837,10 +849,45 @@ int vf_step_fwd(const VfParams* params, int n, int substeps, int integrator, int
         !aligned16(ext_out) || !aligned16(wind) || !aligned16(fifo_push) || !aligned16(fifo_copy))
         return fail("all buffers must be 16-byte aligned");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const VfFifoRows ring = {};
     VF_DISPATCH_FWD(launch_fwd, *params, n, substeps, state_in, action, state_out, obs_out, ext_out, wind, fifo_push,
-                    fifo_copy, st);
+                    fifo_copy, ring, st);
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return fail("vf_step_fwd launch failed", err);
+    return 0;
+}
+
+static int check_ring(const VfFifoRows* r) {
+    if (r->depth < 1 || r->depth > VF_FIFO_MAX_ROWS) return fail("fifo_rows: depth must be in 1..VF_FIFO_MAX_ROWS");
+    for (int j = 0; j < r->depth; ++j) {
+        if (!r->row[j] || !aligned16(r->row[j])) return fail("fifo_rows: every row must be a 16-byte aligned device pointer");
+        for (int k = 0; k < j; ++k)
+            if (r->row[k] == r->row[j]) return fail("fifo_rows: rows must be distinct buffers");
+    }
+    return 0;
+}
+
+int vf_step_fwd_ring(const VfParams* params, int n, int substeps, int integrator, int action_type, unsigned flags,
+                     const float* state_in, const VfFifoRows* fifo_rows, const float* fifo_push, float* state_out,
+                     float* obs_out, float* ext_out, const float* wind, void* stream) {
+    if (check_common(params, n, substeps, integrator, action_type)) return 1;
+    if (n == 0) return 0;
+    if (!state_in || !state_out || !fifo_rows || !fifo_push)
+        return fail("state_in, state_out, fifo_rows and fifo_push must not be NULL");
+    if (state_in == state_out) return fail("state_out must not alias state_in");
+    if (check_ring(fifo_rows)) return 1;
+    for (int j = 0; j < fifo_rows->depth; ++j)
+        if (fifo_rows->row[j] == fifo_push) return fail("fifo_push must not alias a FIFO row");
+    if (!aligned16(state_in) || !aligned16(state_out) || !aligned16(obs_out) || !aligned16(ext_out) || !aligned16(wind) ||
+        !aligned16(fifo_push))
+        return fail("all buffers must be 16-byte aligned");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const float* action = nullptr;
+    float* fifo_copy = nullptr;
+    VF_DISPATCH_FWD(launch_fwd, *params, n, substeps, state_in, action, state_out, obs_out, ext_out, wind, fifo_push,
+                    fifo_copy, *fifo_rows, st);
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return fail("vf_step_fwd_ring launch failed", err);
     return 0;
 }
 
@@ -1004,9 +1051,12 @@ int vf_env_finish(const VfParams* params, const VfEnvSpec* spec, int n, unsigned
                   unsigned long long step_index, const unsigned long long* step_base, const float* state_in,
                   const float* wind, const float* reset_table, const int* status_in, const float* reward,
                   const unsigned char* success, const unsigned char* failure, float* state_out, int* status_out,
-                  float* obs_out, unsigned char* done_out, float* record_out, void* stream) {
+                  float* obs_out, unsigned char* done_out, float* record_out, const VfFifoRows* fifo_rows,
+                  void* stream) {
     if (!params) return fail("params is NULL");
     if (check_spec(spec, true)) return 1;
+    if (fifo_rows && check_ring(fifo_rows)) return 1;
+    const VfFifoRows ring = fifo_rows ? *fifo_rows : VfFifoRows{};
     if (n < 0) return fail("n must be >= 0");
     if (n == 0) return 0;
     if (!state_in || !status_in || !reward || !state_out || !status_out || !done_out || !record_out)
@@ -1019,7 +1069,7 @@ int vf_env_finish(const VfParams* params, const VfEnvSpec* spec, int n, unsigned
     const int grid = (n + kBlock - 1) / kBlock;
     launch_pdl(vf_env_finish_kernel<kBlock>, grid, kBlock, static_cast<cudaStream_t>(stream), *params, *spec, n,
                env_flags, step_index, step_base, state_in, wind, reset_table, status_in, reward, success, failure,
-               state_out, status_out, obs_out, done_out, record_out);
+               state_out, status_out, obs_out, done_out, record_out, ring);
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return fail("vf_env_finish launch failed", err);
     return 0;

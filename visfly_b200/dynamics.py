@@ -339,9 +339,13 @@ class Dynamics:
         return action, owned
 
     # ------------------------------------------------------------------------------------------
+    _fifo_ring = False          # True while a step is being recorded as a CUDA graph (see _step_ring)
+
     def step(self, action) -> th.Tensor:
         """One control step; ``action`` is (N,4) in ``action_space``; returns ``state`` (reference :319-372)."""
         action, owned = self._as_device_action(action)
+        if self._fifo_ring and self._comm_delay_steps and not th.is_grad_enabled():
+            return self._step_ring(action)
         push = None
         if self._comm_delay_steps:                                   # dynamics.py:323-326
             if owned:
@@ -373,6 +377,26 @@ class Dynamics:
             assert bool(th.isfinite(self._obs).all()), "non-finite state after step"
         return self.state
 
+    def _step_ring(self, action: th.Tensor) -> th.Tensor:
+        """``step`` with the comm-delay FIFO as a device-resident ring (a step being recorded as a CUDA graph,
+        envs/base/task_graph.py): the launch consumes the oldest entry, shifts the others and appends this step's
+        action, all in place — the entries keep their addresses.  The diagnostics come out of the same launch (the
+        consumed action is gone afterwards)."""
+        state, cfg = self._state, self._cfg
+        if self._wind_fn is not None:
+            self.update_wind()
+        state_out = th.empty_like(state)
+        obs = th.empty((self.num, 13), dtype=th.float32, device=self.device)
+        ext = th.empty((self.num, 8), dtype=th.float32, device=self.device)
+        _lib.step_fwd_ring(cfg.params, cfg.substeps, cfg.integrator, cfg.action_type, cfg.flags, state, self._pre_action,
+                           action if action.is_contiguous() else action.contiguous(), state_out, obs, ext,
+                           self._wind_rows)
+        self._prev = ("ext", ext)
+        self._state, self._obs = state_out, obs
+        self._n_steps += 1
+        self._ext, self._fresh, self._thrusts_given = None, None, None
+        return self.state
+
     def _extras(self) -> th.Tensor:
         """(N,8) [acc, 0, thrusts] of the last sub-step; produced on demand by re-running the step kernel on
         the saved inputs (the hot loop never pays for diagnostics nobody reads)."""
@@ -381,6 +405,11 @@ class Dynamics:
             rest = self._model.thrust_from_rotor_omega(self._state[4].detach())
             if self._prev is None:
                 ext[:, 4:] = rest
+            elif len(self._prev) == 2:                       # ("ext", tensor): written by the step's own launch
+                ext = self._prev[1]
+                if self._fresh is not None:
+                    m1 = self._fresh.view(-1, 1)
+                    ext = th.cat([th.where(m1, 0.0, ext[:, :4]), th.where(m1, rest, ext[:, 4:])], 1)
             else:
                 state_in, action, version, status = self._prev
                 if status is not None and self._comm_delay_steps:

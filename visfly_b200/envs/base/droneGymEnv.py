@@ -16,6 +16,7 @@ World-model latent hooks (``world``, ``deter``/``stoch``) are not part of this p
 from __future__ import annotations
 
 import contextlib
+import os
 from collections.abc import Sequence
 from typing import Dict, List, Optional
 
@@ -109,6 +110,11 @@ class DroneGymEnvsBase(VecEnv):
     max_episode_steps = _watched("max_episode_steps")
     is_collision_reset = _watched("is_collision_reset")
     use_fused_step = _watched("use_fused_step")
+    # task envs with their own reward / success / failure code: True records the whole step (control step kernel, the
+    # task's tensor ops, wrapper-tail kernel) as a CUDA graph and replays it per step (task_graph.py); the returned
+    # tensors are then the graph's buffers, overwritten by the next step — "copy" hands out fresh copies instead
+    capture_task_step = bool(os.environ.get("VISFLY_B200_CAPTURE_TASK_STEP"))
+    _task_graph, _split_warm = None, 0
 
     def __init__(
             self,
@@ -208,6 +214,9 @@ class DroneGymEnvsBase(VecEnv):
             self._fused.leave()
         elif self._split is not None:
             if not is_test and self._split.refresh():
+                if self.capture_task_step and self.tensor_output and not self.requires_grad \
+                        and not self.debug_checks and self._action.shape == (self.num_agent, 4):
+                    return self._step_split_graph()
                 return self._step_split()
             self._split.leave()
         with self._grad_ctx():
@@ -266,18 +275,18 @@ class DroneGymEnvsBase(VecEnv):
             envs.update_observation()
             self.get_full_observation()
             pre_obs = self._obs_tensors
-            fz.sc_mid = fz.sc + 1                              # what `self._step_count` shows to the task code
+            fz.sc_open, fz.sc_mid = True, None                 # `self._step_count` as the task code sees it: +1
             self._success = self.get_success()
             self._failure = self.get_failure()
             reward = self.get_reward(predicted_obs={})
             if not isinstance(reward, th.Tensor):
                 raise ValueError("get_reward changed its return type after reset()")
-            fz.sc_mid = None
+            fz.sc_open, fz.sc_mid = False, None
             state_out, obs13, done, record = fz.finish(dyn._state, reward, self._success, self._failure,
                                                        self.requires_grad)             # launch 2
             dyn._state, dyn._obs_t = state_out, obs13
             dyn._ext, dyn._fresh = None, done
-            if dyn._pre_action:                                # FIFO rows of re-initialised agents (dynamics.py:262-263)
+            if dyn._pre_action and not fz.fifo_zeroed:         # FIFO rows of re-initialised agents (dynamics.py:262-263)
                 m1 = done.view(-1, 1)
                 dyn._pre_action = [th.where(m1, 0.0, a) for a in dyn._pre_action]
             envs._collision_stale = True
@@ -287,6 +296,28 @@ class DroneGymEnvsBase(VecEnv):
         info = _RecordInfo(self.num_agent, record, pre_obs.detach(), dyn.ctrl_dt, False)
         self._info = info
         return self._format_step_output(reward, done, info)
+
+    def _step_split_graph(self):
+        """``_step_split`` as one CUDA-graph replay (task_graph.py); the first steps after a reset, a spec change or an
+        env the recording does not fit run the eager two-launch path."""
+        from . import task_graph as tg
+        g, fz = self._task_graph, self._split
+        if g is not None and not fz.active:
+            fz.enter()                        # back from the generic path (reset_agent_by_id, examine, ...)
+        if g is not None and g.matches(self._action):
+            return g.replay(self._action, self.capture_task_step == "copy")
+        self._task_graph = None
+        if self._split_warm < 3 or not fz.active or fz.t_off is not None or self.envs.dynamics._wind_fn is not None:
+            self._split_warm += 1
+            return self._step_split()
+        action = self._action
+        g = tg.capture_or_none(self, action)
+        if g is None:
+            self.capture_task_step = False
+            self._action, self._action_owned = action, False
+            return self._step_split()
+        self._task_graph, self._split_warm = g, 0
+        return g.replay(action, self.capture_task_step == "copy")
 
     # -- one-kernel path (built-in tasks, no autograd) -------------------------------------------------------
     def _make_fused(self):
@@ -519,7 +550,8 @@ class DroneGymEnvsBase(VecEnv):
         self._act_evt.record(th.cuda.current_stream(self.device))
         return dev
 
-    _TRANSIENT = ("_host_ring", "_host_turn", "_act_pin", "_act_evt", "_np_const", "_copy_stream", "_h2d_evt")
+    _TRANSIENT = ("_host_ring", "_host_turn", "_act_pin", "_act_evt", "_np_const", "_copy_stream", "_h2d_evt",
+                  "_task_graph", "_split_warm")
 
     def __deepcopy__(self, memo):
         """Deep-copyable like the reference env (utils/algorithms/shac.py:121); host staging buffers and CUDA
@@ -561,6 +593,7 @@ class DroneGymEnvsBase(VecEnv):
                 raise ValueError(f"get_reward should return a dict or a tensor, but got {type(probe)}")
         self._fused = self._make_fused()
         self._split = None if self._fused is not None else self._make_split()
+        self._task_graph, self._split_warm = None, 0
         self._observations = self._format_obs(self._obs_tensors)
         return self._observations
 

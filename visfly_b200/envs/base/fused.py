@@ -182,8 +182,11 @@ class FusedEnvStep:
         self.t_off: Optional[th.Tensor] = None       # per-agent time offsets given at reset (None: all zero)
         self.step_base: Optional[th.Tensor] = None   # device word added to the Philox step index (graph replays)
         self.sc_mid: Optional[th.Tensor] = None      # split path: the step count task code sees while a step is open
+        self.sc_open = False                         # ... built on first read (most task code never looks at it)
+        self.finish_out = None                       # (state, status) tensors vf_env_finish writes into (recorded steps)
         self.peer_next = 0                           # address of a VfPeerScatter for the NEXT launch (fused all-gather)
         self.peer_done = False                       # ... and whether that launch has happened
+        self.spec_gen = 0                            # bumped whenever the spec is rebuilt (recorded steps go stale)
         self._views = (None, None)
         self._gen_seen, self._ndict, self._watch, self._watch_sum, self._ok = -1, None, (), 0, False
         # host-driven (numpy) mode runs one step ahead of its caller: steps launched but not yet handed out, and the
@@ -249,7 +252,14 @@ class FusedEnvStep:
             cache[k] = v
         return v
 
-    sc = property(lambda self: self._field(0) if self.sc_mid is None else self.sc_mid)
+    @property
+    def sc(self):
+        if not self.sc_open:
+            return self._field(0)
+        if self.sc_mid is None:
+            self.sc_mid = self._field(0) + 1
+        return self.sc_mid
+
     ret = property(lambda self: self._field(1))
     eb = property(lambda self: self._field(2))
     gate = property(lambda self: self._field(3) if self.task == P.TASK_RACING else None)
@@ -286,6 +296,7 @@ class FusedEnvStep:
         env, envs, s = self.env, self.env.envs, self.spec
         self.rewind()                     # a step launched ahead saw the old settings
         self._stepper = None
+        self.spec_gen += 1
         watch = []
         ok = True
         if os.environ.get("VISFLY_B200_NO_FUSED_ENV") or not env.use_fused_step or not envs._imu_noise_free:
@@ -481,10 +492,18 @@ class FusedEnvStep:
         others, dynamics.py:249-263)."""
         dyn = self.env.envs.dynamics
         cfg = dyn._cfg
+        # comm-delay FIFO rows of re-initialised agents (dynamics.py:262-263): zeroed by the launch itself where the
+        # entries are plain engine-owned tensors; with autograd history in the FIFO the caller blends them (where)
+        fifo = dyn._pre_action if dyn._pre_action and not grad else None
+        if fifo is not None and any(a.requires_grad or not a.is_contiguous() for a in fifo):
+            fifo = None
+        out_state, out_status = self.finish_out if (self.finish_out is not None and not grad) else (None, None)
         state_out, status, obs, done, record = _lib.env_finish(
             cfg.params, self.spec, 0, self.global_step, state.detach(), self.status,
             reward.detach().to(th.float32).contiguous(), success.contiguous(), failure.contiguous(),
-            want_obs=not grad, wind=dyn._wind_rows, reset_table=self.table, step_base=self.step_base)
+            want_obs=not grad, wind=dyn._wind_rows, reset_table=self.table, step_base=self.step_base, fifo=fifo,
+            state_out=out_state, status_out=out_status)
+        self.fifo_zeroed = fifo is not None
         self.global_step += 1
         if grad and state.requires_grad:
             state_out = _ResetBlend.apply(state, state_out, done)

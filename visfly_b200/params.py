@@ -290,3 +290,11 @@ class VfPeerScatter(ctypes.Structure):
     """ctypes mirror of ``struct VfPeerScatter``: peer-mapped gather buffers the rollout's last env step scatters the
     per-agent episode returns into (the fused all-gather of SURVEY.md §8e)."""
     _fields_ = [("dst", ctypes.c_void_p * MAX_PEERS), ("offset", ctypes.c_longlong), ("world", ctypes.c_int)]
+
+
+FIFO_MAX_ROWS = 8
+
+
+class VfFifoRows(ctypes.Structure):
+    """ctypes mirror of ``struct VfFifoRows``: the comm-delay FIFO as a device-resident ring of (n,4) rows."""
+    _fields_ = [("row", ctypes.c_void_p * FIFO_MAX_ROWS), ("depth", ctypes.c_int)]
