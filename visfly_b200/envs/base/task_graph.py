@@ -62,10 +62,14 @@ class TaskStepGraph:
             env._action, env._action_owned = self.a_in, False
             # recorded steps keep every carried tensor at its address: the FIFO is shifted in place by the control
             # step's launch, vf_env_finish writes the state / status records it read from
-            dyn._fifo_ring, fz.finish_out = True, (dyn._state, fz.status)
+            state_holder, status_holder = dyn._state, fz.status
+            dyn._fifo_ring, fz.finish_out = True, (state_holder, status_holder)
             with th.cuda.graph(graph):
                 obs, reward, done, info = env._step_split()
-                carried = []
+                if dyn._state is not state_holder or fz.status is not status_holder:
+                    raise CaptureUnsupported("the step did not write its state / status records in place")
+                # written in place by the recorded launches: no copy, but replays must find them where they were
+                carried = [(dyn, "_state", state_holder), (fz, "status", status_holder)]
                 for name, o in owners.items():
                     for k, old in saved[name].items():
                         new = o.__dict__.get(k)
