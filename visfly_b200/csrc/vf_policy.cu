@@ -16,6 +16,8 @@
 // cores would need TF32 / bf16 operands; the trainers' gradient parity is stated in fp32).
 #include <cuda_runtime.h>
 
+#include <cstdint>
+#include <cstdlib>
 #include <string>
 
 #include "../../include/visfly_b200.h"
@@ -63,9 +65,16 @@ template <int H> struct PackedBwd {
     float w2n[H][H];         // w2n[j][c] = W2[j][column_at<H>(c)]
     float w3n[NA][H];
 };
+}  // namespace
+// per-CTA partial weight gradients, in this order: dW1 (H, d) | db1 (H) | dW2 (H, H) | db2 (H) | dW3 (4, H) | db3 (4)
+__host__ __device__ inline int partial_size(int h, int d) { return h * d + h + h * h + h + 4 * h + 4; }
+namespace {
+#include "vf_policy_tc.cuh"
+
 template <int H> struct Packed {
     PackedFwd<H> f;
     PackedBwd<H> b;
+    tc::PackedTc<H> t;
 };
 template <int H> struct Smem : PackedFwd<H> {
     float x[DP][TS];         // inputs, k-major (backward: finally the dx tile)
@@ -112,6 +121,7 @@ __global__ void vf_policy_pack_kernel(int d, const float* __restrict__ w1, const
         p.f.b2[e] = b2[column_at<H>(e)];
     }
     if (e < NA) p.f.b3[e] = b3[e];
+    tc::pack_tc<H>(e, d, w1, b1, w2, b2, w3, b3, p.t);
 }
 
 template <class T> __device__ __forceinline__ void copy_block(T& dst, const T& src) {
@@ -225,9 +235,6 @@ vf_policy_fwd_kernel(int n, int da, int db, const float* __restrict__ xa, const 
         reinterpret_cast<float4*>(action)[agent] = make_float4(a[0], a[1], a[2], a[3]);
     }
 }
-
-// per-CTA partial weight gradients, in this order: dW1 (H, d) | db1 (H) | dW2 (H, H) | db2 (H) | dW3 (4, H) | db3 (4)
-__host__ __device__ inline int partial_size(int h, int d) { return h * d + h + h * h + h + NA * h + NA; }
 
 template <int H>
 __global__ void __launch_bounds__(NT)
@@ -437,6 +444,26 @@ template <class K> int allow_smem(K kernel, size_t bytes) {
     return err == cudaSuccess ? 0 : policy_fail("cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed", err);
 }
 
+// VF_POLICY_NO_TC=1 keeps the CUDA-core kernels (A/B measurements, profiles/)
+bool use_tensor_cores() {
+    static const bool on = [] {
+        const char* e = getenv("VF_POLICY_NO_TC");
+        return !(e && e[0] && e[0] != '0');
+    }();
+    return on;
+}
+
+// persistent CTAs: `per_sm` per SM of the current device, never more than there are tiles
+int tc_grid(int tiles, int per_sm) {
+    static const int sms = [] {
+        int dev = 0, count = 148;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&count, cudaDevAttrMultiProcessorCount, dev);
+        return count;
+    }();
+    const int cap = sms * per_sm;
+    return tiles < cap ? tiles : cap;
+}
+
 int check_shapes(int n, int da, int db, int h, const void* xb) {
     if (n < 0) return policy_fail("n must be >= 0");
     if (da < 1 || db < 0 || da + db > DP) return policy_fail("policy input width must be in 1..32");
@@ -481,6 +508,20 @@ int vf_policy_fwd(int n, int da, int db, int h, const float* xa, const float* xb
         return policy_fail("action and packed must be 16-byte aligned");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int grid = (n + TM - 1) / TM;
+    if (use_tensor_cores()) {
+        const int d = da + db;
+#define VF_TC_FWD(H_, DK_)                                                                                            \
+        do {                                                                                                          \
+            if (allow_smem(tc::vf_policy_fwd_tc_kernel<H_, DK_>, sizeof(tc::FwdSmem<H_, DK_>))) return 1;             \
+            tc::vf_policy_fwd_tc_kernel<H_, DK_><<<tc_grid(grid, 2), tc::FWD_THREADS, sizeof(tc::FwdSmem<H_, DK_>), st>>>( \
+                n, da, db, xa, xb, &reinterpret_cast<const Packed<H_>*>(packed)->t, lo, hi, action);                  \
+        } while (0)
+        if (h == 64) { if (d <= 16) VF_TC_FWD(64, 16); else VF_TC_FWD(64, 32); }
+        else { if (d <= 16) VF_TC_FWD(32, 16); else VF_TC_FWD(32, 32); }
+#undef VF_TC_FWD
+        const cudaError_t err = cudaGetLastError();
+        return err == cudaSuccess ? 0 : policy_fail("vf_policy_fwd (tensor-core kernel) launch failed", err);
+    }
     if (h == 64) {
         if (allow_smem(vf_policy_fwd_kernel<64>, sizeof(Smem<64>))) return 1;
         vf_policy_fwd_kernel<64><<<grid, NT, sizeof(Smem<64>), st>>>(n, da, db, xa, xb,
