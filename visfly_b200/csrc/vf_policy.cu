@@ -543,9 +543,22 @@ int vf_policy_bwd(int n, int da, int db, int h, const float* xa, const float* xb
     if ((reinterpret_cast<size_t>(grad_action) | reinterpret_cast<size_t>(packed)) & 15u)
         return policy_fail("grad_action and packed must be 16-byte aligned");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const int grid = (n + TM - 1) / TM;
+    int grid = (n + TM - 1) / TM;
     const int size = partial_size(h, da + db);
-    if (n > 0) {
+    if (n > 0 && use_tensor_cores() && da + db <= 16) {
+        grid = tc_grid(grid, 1);                       // persistent CTAs: one partial per CTA
+        if (h == 64) {
+            if (allow_smem(tc::vf_policy_bwd_tc_kernel<64>, sizeof(tc::BwdSmem<64>))) return 1;
+            tc::vf_policy_bwd_tc_kernel<64><<<grid, tc::BWD_THREADS, sizeof(tc::BwdSmem<64>), st>>>(
+                n, da, db, xa, xb, &reinterpret_cast<const Packed<64>*>(packed)->t, lo, hi, grad_action, grad_xa, grad_xb,
+                partial);
+        } else {
+            if (allow_smem(tc::vf_policy_bwd_tc_kernel<32>, sizeof(tc::BwdSmem<32>))) return 1;
+            tc::vf_policy_bwd_tc_kernel<32><<<grid, tc::BWD_THREADS, sizeof(tc::BwdSmem<32>), st>>>(
+                n, da, db, xa, xb, &reinterpret_cast<const Packed<32>*>(packed)->t, lo, hi, grad_action, grad_xa, grad_xb,
+                partial);
+        }
+    } else if (n > 0) {
         if (h == 64) {
             if (allow_smem(vf_policy_bwd_kernel<64>, sizeof(SmemBwd<64>))) return 1;
             vf_policy_bwd_kernel<64><<<grid, NT, sizeof(SmemBwd<64>), st>>>(
