@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(128) probe(int test, int variant, int passes, 
                     acc = 1;
                 }
             } else {          // test 4: both operands K-major (K = 128 agents) in 128-byte-swizzled rows; A has 64 rows, M = 128
-                constexpr uint32_t idesc = make_idesc(128, 32, 0, 0);
+                const uint32_t idesc = make_idesc(test == 5 ? 64 : 128, 32, 0, 0);        // test 5: M = 64
                 for (int k = 0; k < 128 / 8; ++k) {
                     umma_tf32(tmem, make_desc_sw128(smem_u32(a) + (k / 4) * 64 * 128 + (k % 4) * 32),
                               make_desc_sw128(smem_u32(b) + (k / 4) * 32 * 128 + (k % 4) * 32), idesc, acc);
@@ -204,7 +204,7 @@ int main() {
     srand(7);
     auto rnd = [] { return float(rand()) / RAND_MAX * 2.f - 1.f; };
     cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(Smem)));
-    for (int test = 1; test <= 4; ++test) {
+    for (int test = 1; test <= 5; ++test) {
         const bool fwd = test == 1 || test == 3;
         const int ar = 128, ac = fwd ? 32 : 64, br = fwd ? 64 : 128, bc = 32;
         std::vector<float> A(ar * ac), B(br * bc), Ab(ar * ac), Bb(br * bc);
@@ -213,12 +213,12 @@ int main() {
     for (int variant = 0; variant < (test == 2 ? 2 : 1); ++variant) {
         if (test == 2 && (variant & 4) && !(variant & 3)) continue;
         for (int r = 0; r < ar; ++r) for (int c = 0; c < ac; ++c) {
-            if (test == 4) Ab[sw128_off(c, r, ac) / 4] = A[r * ac + c];
+            if (test >= 4) Ab[sw128_off(c, r, ac) / 4] = A[r * ac + c];
             else if (test == 2 && !(variant & 1)) Ab[blk(c, r, ar)] = A[r * ac + c];       // transposed copy, K-major operand
             else Ab[blk(r, c, ac)] = A[r * ac + c];
         }
         for (int r = 0; r < br; ++r) for (int c = 0; c < bc; ++c) {
-            if (test == 4) Bb[sw128_off(c, r, bc) / 4] = B[r * bc + c];
+            if (test >= 4) Bb[sw128_off(c, r, bc) / 4] = B[r * bc + c];
             else if (test == 2 && !(variant & 2)) Bb[blk(c, r, br)] = B[r * bc + c];
             else Bb[blk(r, c, bc)] = B[r * bc + c];
         }
@@ -249,6 +249,20 @@ int main() {
                     worst = fmax(worst, fabs(D[i * dn + j] - ref[i * dn + j]));
                     scale = fmax(scale, fabs(ref[i * dn + j]));
                 }
+            if (test == 5) {          // which tensor-memory lane holds which row of the M = 64 accumulator
+                printf("test 5 passes %d lane->row:", passes);
+                for (int lane = 0; lane < 128; ++lane) {
+                    int hit = -1;
+                    for (int i = 0; i < 64; ++i) {
+                        bool same = true;
+                        for (int j = 0; j < dn; ++j) same = same && fabs(D[lane * dn + j] - ref[i * dn + j]) < 5e-3 * (1 + fabs(ref[i * dn + j]));
+                        if (same) hit = i;
+                    }
+                    printf(" %d", hit);
+                }
+                printf("\n");
+                continue;
+            }
             printf("test %d variant %d passes %d: max |err| %.3e (max |ref| %.3f)  D[0][0..3] = %.5f %.5f %.5f %.5f  ref %.5f %.5f %.5f %.5f\n",
                    test, variant, passes, worst, scale, D[0], D[1], D[2], D[3], ref[0], ref[1], ref[2], ref[3]);
         }

@@ -341,47 +341,50 @@ vf_policy_fwd_tc_kernel(int n, int da, int db, const float* __restrict__ xa, con
 }
 
 // ---- backward --------------------------------------------------------------------------------------------------------
-// One persistent CTA of 512 threads per SM, all 512 tensor-memory columns, d <= 16.  Per tile of 128 agents:
+// One persistent CTA of 512 threads per SM, all of its tensor memory, d <= 16.  Per tile of 128 agents:
 //   P0  x -> tensor memory (A of layer 1) and shared memory (K = agents, B of dW1)              MMA: Z1 = x W1^T
 //   P1  h1 = tanh(Z1 + b1) -> tensor memory (A of layer 2), shared memory (B of dW2)            MMA: Z2 = h1 W2^T
 //   P2  h2 = tanh(Z2 + b2) -> shared memory (A of dW3); output layer + dz3 on the CUDA cores    MMA: dW3 += h2^T dz3
 //       dZ2 = (dz3 W3)(1 - h2^2) -> tensor memory (A of dZ1), shared memory (A of dW2, over h2)  MMA: dZ1' = dZ2 W2,
-//                                                                                                    dW2 += dZ2^T h1, db2
+//                                                                                                    [dW2 | db2] += dZ2^T [h1 | 1]
 //   P3  dZ1 = dZ1' (1 - h1^2) -> tensor memory (A of dx), shared memory (A of dW1, over dZ2)    MMA: dx = dZ1 W1,
-//                                                                                                    dW1 += dZ1^T x, db1
+//                                                                                                    [dW1 | db1] += dZ1^T [x | 1]
 //   P4  dx -> global memory
-// The weight-gradient accumulators stay in tensor memory across the CTA's tiles and are written out once, as this CTA's
-// partial; vf_policy_reduce_kernel adds the partials in a fixed order.  W2 and W2^T take turns in one shared-memory
-// buffer (cp.async from the packed block, L2-resident) — both plus the K = agents operands do not fit in 227 KB.
+// Two completion barriers: A for the products the next phase consumes (agents as rows), B for the weight-gradient
+// products (contracted over agents, M = 64: the accumulator row j sits in tensor-memory lane 32 (j / 16) + j % 16),
+// which only have to be finished before their shared-memory operands are overwritten — they run under the next phase's
+// CUDA-core work.  Their accumulators stay in tensor memory across the CTA's tiles and are written out once, as this
+// CTA's partial; vf_policy_reduce_kernel adds the partials in a fixed order.  The bias gradients ride along as one more
+// operand row of ones.  W2 and W2^T take turns in one shared-memory buffer (cp.async from the packed block,
+// L2-resident): both plus the K = agents operands do not fit in 227 KB.
 constexpr int BWD_THREADS = 512;
 template <int H> struct BwdSmem {
     // K = agents operands, [hi | lo][4 groups of 32 agents][F rows][32 floats], 16-byte chunks XOR row % 8
-    float kx[2][4 * 16 * 32];        // x (16 rows)
-    float kh1[2][4 * H * 32];        // h1
-    float kh2[2][4 * H * 32];        // h2, then dZ2, then dZ1
-    float kz3[2][4 * 8 * 32];        // dz3 (rows 0..3; 4..7 zero)
-    float ones[4 * 16 * 32];         // B operand of the bias gradients
-    float w1[2][H * 16];             // blocked (H x 16)
-    float w1t[2][16 * H];            // blocked (16 x H)
-    float w2[2][H * H];              // blocked W2 (layer 2) / W2^T (dZ1), swapped per tile
+    float kx[2][4 * 24 * 32];          // x (16 rows) + a row group whose hi part is ones
+    float kh1[2][4 * (H + 8) * 32];    // h1 (H rows) + a row group whose hi part is ones
+    float kh2[2][4 * H * 32];          // h2, then dZ2, then dZ1
+    float kz3[2][4 * 8 * 32];          // dz3 (rows 0..3; 4..7 zero)
+    float w1[2][H * 16];               // blocked (H x 16)
+    float w1t[2][16 * H];              // blocked (16 x H)
+    float w2[2][H * H];                // blocked W2 (layer 2) / W2^T (dZ1), swapped per tile
     float w3n[NA][H];
     float b1s[H], b2s[H], b3[4];
-    float4 mu[4][TILE];
+    float4 mu[3][TILE];                // output-layer partial sums of column groups 1..3
     float4 dz3[TILE];
     float db3[4][NA];
     uint64_t bar[2];
     uint32_t tmem;
 };
 
-// D[128 x N] (+)= A^T-role product over the tile's 128 agents: A (FA rows) and B (FB rows) are K = agents operands;
-// b_lo == nullptr: B is exact in tf32 (the ones operand), two passes
+// D[64 x N] (+)= A B^T contracted over the tile's 128 agents: A (FA rows per agent group, the first 64 used) and B (FB
+// rows per group, the first N used) are K = agents operands
 template <int N, int FA, int FB>
 __device__ __forceinline__ void issue_kk(uint32_t d, const float* a_hi, const float* a_lo, const float* b_hi, const float* b_lo,
                                          bool accumulate) {
-    constexpr uint32_t idesc = idesc_tf32(TILE, N);
+    constexpr uint32_t idesc = idesc_tf32(64, N);
     uint32_t acc = accumulate ? 1u : 0u;
-    const int passes = b_lo ? 3 : 2;
-    for (int p = 0; p < passes; ++p) {
+#pragma unroll
+    for (int p = 0; p < 3; ++p) {
         const uint32_t a = smem_u32(p == 1 ? a_lo : a_hi);
         const uint32_t b = smem_u32(p == 2 ? b_lo : b_hi);
 #pragma unroll
@@ -393,14 +396,13 @@ __device__ __forceinline__ void issue_kk(uint32_t d, const float* a_hi, const fl
     }
 }
 
-// this thread's 16 features [16 q, 16 q + 16) of agent r into a K = agents operand with F rows
+// this thread's 16 features [16 q, 16 q + 16) of agent r into a K = agents operand with F rows per agent group
 template <int F>
 __device__ __forceinline__ void store_krole(float* hi_buf, float* lo_buf, int q, int r, const float v[16]) {
-    const int l = r & 31, base = (r >> 5) * F * 32;
+    const int l = r & 31, base = (r >> 5) * F * 32 + 16 * q * 32;
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
-        const int f = 16 * q + i;
-        const int idx = base + f * 32 + ((((l >> 2) ^ (f & 7)) << 2) | (l & 3));
+        const int idx = base + i * 32 + ((((l >> 2) ^ (i & 7)) << 2) | (l & 3));
         float hi, lo;
         split(v[i], hi, lo);
         hi_buf[idx] = hi;
@@ -424,9 +426,8 @@ vf_policy_bwd_tc_kernel(int n, int da, int db, const float* __restrict__ xa, con
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     BwdSmem<H>& s = *reinterpret_cast<BwdSmem<H>*>(smem_raw);
     constexpr int DK = 16;
-    constexpr uint32_t ACC0 = 0, ACC1 = H, OPA = 2 * H, OPB = 4 * H, DW2 = 6 * H, DW3 = 7 * H, DB2 = 7 * H + 16,
-                       DW1 = 7 * H + 32, DB1 = 7 * H + 48;
-    static_assert(7 * H + 64 <= 512, "tensor-memory columns");
+    constexpr uint32_t ACC0 = 0, ACC1 = H, OPA = 2 * H, OPB = 4 * H, DW2 = 6 * H, DW3 = 7 * H + 8, DW1 = 7 * H + 16;
+    static_assert(7 * H + 40 <= 512, "tensor-memory columns");
     const int t = threadIdx.x, warp = t >> 5, q = t >> 7, r = t & 127, d = da + db;
     const int tiles = (n + TILE - 1) / TILE;
     copy_floats<BWD_THREADS>(&s.w1[0][0], &packed->w1_16[0][0], 2 * H * 16);
@@ -435,7 +436,13 @@ vf_policy_bwd_tc_kernel(int n, int da, int db, const float* __restrict__ xa, con
     copy_floats<BWD_THREADS>(&s.w1t[1][0], &packed->w1t[1][0], 16 * H);
     copy_floats<BWD_THREADS>(&s.w2[0][0], &packed->w2[0][0], 2 * H * H);
     copy_floats<BWD_THREADS>(&s.w3n[0][0], &packed->w3n[0][0], NA * H);
-    for (int i = t; i < 4 * 16 * 32; i += BWD_THREADS) s.ones[i] = 1.f;
+    for (int i = t; i < 4 * 8 * 32; i += BWD_THREADS) {       // the row groups of ones (hi) / zeros (lo), per agent group
+        const int grp = i / (8 * 32), e = i % (8 * 32);
+        s.kx[0][grp * 24 * 32 + 16 * 32 + e] = 1.f;
+        s.kx[1][grp * 24 * 32 + 16 * 32 + e] = 0.f;
+        s.kh1[0][grp * (H + 8) * 32 + H * 32 + e] = 1.f;
+        s.kh1[1][grp * (H + 8) * 32 + H * 32 + e] = 0.f;
+    }
     for (int i = t; i < 2 * 4 * 8 * 32; i += BWD_THREADS) (&s.kz3[0][0])[i] = 0.f;
     if (t < H) { s.b1s[t] = packed->b1[t] * TANH_SCALE; s.b2s[t] = packed->b2[t] * TANH_SCALE; }
     if (t < NA) s.b3[t] = packed->b3[t];
@@ -454,15 +461,16 @@ vf_policy_bwd_tc_kernel(int n, int da, int db, const float* __restrict__ xa, con
     bool first = true;
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, first = false) {
         const int agent = tile * TILE + r;
-        float4 g_now = g;
+        const float4 g_now = g;
         // ---- P0 ------------------------------------------------------------------------------------------------
+        if (!first) { mbar_wait(&s.bar[1], phase_b); phase_b ^= 1; }       // dW1 of the previous tile has read kx / kh2
         if (q == 0) {
             float xh[16], xl[16];
 #pragma unroll
             for (int k = 0; k < 16; ++k) split(x[k], xh[k], xl[k]);
             tmem_st16(lane_base + OPA, xh);
             tmem_st16(lane_base + OPA + DK, xl);
-            store_krole<16>(s.kx[0], s.kx[1], 0, r, x);
+            store_krole<24>(s.kx[0], s.kx[1], 0, r, x);
             const int next = (tile + int(gridDim.x)) * TILE + r;
             if (tile + int(gridDim.x) < tiles) {
                 load_cols(x, 0, n, da, db, next, xa, xb);
@@ -481,7 +489,7 @@ vf_policy_bwd_tc_kernel(int n, int da, int db, const float* __restrict__ xa, con
             float h[16];
             hidden_values<H>(lane_base, ACC0, s.b1s, q, h);
             store_operand<H>(lane_base, OPA, q, h);
-            store_krole<H>(s.kh1[0], s.kh1[1], q, r, h);
+            store_krole<H + 8>(s.kh1[0], s.kh1[1], q, r, h);
         }
         publish_operands();
         if (t == 0) {
@@ -492,18 +500,18 @@ vf_policy_bwd_tc_kernel(int n, int da, int db, const float* __restrict__ xa, con
         copy_async<BWD_THREADS>(&s.w2[0][0], &packed->w2t[0][0], 2 * H * H);      // layer 2 is done with W2: W2^T moves in
         // ---- P2 ------------------------------------------------------------------------------------------------
         float h2[16];
+        float4 mine = make_float4(0.f, 0.f, 0.f, 0.f);
         if (16 * q < H) {
             hidden_values<H>(lane_base, ACC1, s.b2s, q, h2);
-            s.mu[q][r] = output_partial<H>(s.w3n, q, h2);
+            mine = output_partial<H>(s.w3n, q, h2);
             store_krole<H>(s.kh2[0], s.kh2[1], q, r, h2);
-        } else {
-            s.mu[q][r] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
+        if (q > 0) s.mu[q - 1][r] = mine;
         __syncthreads();
         if (q == 0) {
-            const float4 m0 = s.mu[0][r], m1 = s.mu[1][r], m2 = s.mu[2][r], m3 = s.mu[3][r];
-            const float mu[NA] = {(m0.x + m1.x) + (m2.x + m3.x), (m0.y + m1.y) + (m2.y + m3.y),
-                                  (m0.z + m1.z) + (m2.z + m3.z), (m0.w + m1.w) + (m2.w + m3.w)};
+            const float4 m1 = s.mu[0][r], m2 = s.mu[1][r], m3 = s.mu[2][r];
+            const float mu[NA] = {(mine.x + m1.x) + (m2.x + m3.x), (mine.y + m1.y) + (m2.y + m3.y),
+                                  (mine.z + m1.z) + (m2.z + m3.z), (mine.w + m1.w) + (m2.w + m3.w)};
             const float gv[NA] = {g_now.x, g_now.y, g_now.z, g_now.w};
             float z[NA];
 #pragma unroll
@@ -531,12 +539,12 @@ vf_policy_bwd_tc_kernel(int n, int da, int db, const float* __restrict__ xa, con
         __syncthreads();
         if (t == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            issue_kk<16, H, 8>(tmem + DW3, s.kh2[0], s.kh2[1], s.kz3[0], s.kz3[1], !first);
+            issue_kk<8, H, 8>(tmem + DW3, s.kh2[0], s.kh2[1], s.kz3[0], s.kz3[1], !first);
             umma_commit(&s.bar[1]);
         }
+        float dz2[16];
         if (16 * q < H) {                                      // dZ2 = (dz3 W3) * (1 - h2^2), this thread's 16 columns
             const float4 z = s.dz3[r];
-            float dz2[16];
 #pragma unroll
             for (int i = 0; i < 16; i += 4) {
                 const float4 wa = *reinterpret_cast<const float4*>(&s.w3n[0][16 * q + i]);
@@ -549,25 +557,23 @@ vf_policy_bwd_tc_kernel(int n, int da, int db, const float* __restrict__ xa, con
                 dz2[i + 3] = (z.x * wa.w + z.y * wb.w + z.z * wc.w + z.w * wd.w) * (1.f - h2[i + 3] * h2[i + 3]);
             }
             store_operand<H>(lane_base, OPB, q, dz2);
-            mbar_wait(&s.bar[1], phase_b);                     // dW3 has read h2 from kh2: dZ2 may move in
-            store_krole<H>(s.kh2[0], s.kh2[1], q, r, dz2);
-        } else {
-            mbar_wait(&s.bar[1], phase_b);
         }
-        phase_b ^= 1;
+        mbar_wait(&s.bar[1], phase_b); phase_b ^= 1;           // dW3 has read h2 from kh2: dZ2 may move in
+        if (16 * q < H) store_krole<H>(s.kh2[0], s.kh2[1], q, r, dz2);
         copy_async_wait();                                     // W2^T has landed
         publish_operands();
         if (t == 0) {
             issue_ts<H, H>(tmem + ACC0, tmem + OPB, tmem + OPB + H, s.w2[0], s.w2[1], false);
-            issue_kk<H, H, H>(tmem + DW2, s.kh2[0], s.kh2[1], s.kh1[0], s.kh1[1], !first);
-            issue_kk<16, H, 16>(tmem + DB2, s.kh2[0], s.kh2[1], s.ones, nullptr, !first);
             umma_commit(&s.bar[0]);
+            issue_kk<H + 8, H, H + 8>(tmem + DW2, s.kh2[0], s.kh2[1], s.kh1[0], s.kh1[1], !first);
+            umma_commit(&s.bar[1]);
         }
         mbar_wait(&s.bar[0], phase_a); phase_a ^= 1;
         copy_async<BWD_THREADS>(&s.w2[0][0], &packed->w2[0][0], 2 * H * H);       // W2 back for the next tile's layer 2
         // ---- P3 ------------------------------------------------------------------------------------------------
+        float dz1[16];
         if (16 * q < H) {
-            float v[16], hh[16], hl[16], dz1[16];
+            float v[16], hh[16], hl[16];
             tmem_ld16(lane_base + ACC0 + 16 * q, v);
             tmem_ld16(lane_base + OPA + 16 * q, hh);
             tmem_ld16(lane_base + OPA + H + 16 * q, hl);
@@ -577,14 +583,15 @@ vf_policy_bwd_tc_kernel(int n, int da, int db, const float* __restrict__ xa, con
                 dz1[i] = v[i] * (1.f - h1 * h1);
             }
             store_operand<H>(lane_base, OPA, q, dz1);
-            store_krole<H>(s.kh2[0], s.kh2[1], q, r, dz1);
         }
+        mbar_wait(&s.bar[1], phase_b); phase_b ^= 1;           // dW2 has read dZ2 from kh2: dZ1 may move in
+        if (16 * q < H) store_krole<H>(s.kh2[0], s.kh2[1], q, r, dz1);
         publish_operands();
         if (t == 0) {
             issue_ts<16, H>(tmem + ACC1, tmem + OPA, tmem + OPA + H, s.w1t[0], s.w1t[1], false);
-            issue_kk<16, H, 16>(tmem + DW1, s.kh2[0], s.kh2[1], s.kx[0], s.kx[1], !first);
-            issue_kk<16, H, 16>(tmem + DB1, s.kh2[0], s.kh2[1], s.ones, nullptr, !first);
             umma_commit(&s.bar[0]);
+            issue_kk<24, H, 24>(tmem + DW1, s.kh2[0], s.kh2[1], s.kx[0], s.kx[1], !first);
+            umma_commit(&s.bar[1]);
         }
         mbar_wait(&s.bar[0], phase_a); phase_a ^= 1;
         // ---- P4 ------------------------------------------------------------------------------------------------
@@ -599,11 +606,12 @@ vf_policy_bwd_tc_kernel(int n, int da, int db, const float* __restrict__ xa, con
                 }
             }
         }
-        // next tile: its x overwrites operand columns / kx rows whose products were awaited above; ACC1 is rewritten by
-        // its layer 2, two barriers from here
+        // next tile: its x overwrites operand columns whose products were awaited above, kx / kh2 after barrier B;
+        // ACC1 is rewritten by its layer 2, two barriers from here
     }
+    mbar_wait(&s.bar[1], phase_b);                             // the last dW1
     copy_async_wait();
-    // ---- this CTA's partial weight gradients ----------------------------------------------------------------------
+    // ---- this CTA's partial weight gradients: accumulator row j = tensor-memory lane 32 (j / 16) + j % 16 ---------------
     float* out = partial + size_t(blockIdx.x) * partial_size(H, d);
     float* p_w1 = out;
     float* p_b1 = p_w1 + H * d;
@@ -611,29 +619,37 @@ vf_policy_bwd_tc_kernel(int n, int da, int db, const float* __restrict__ xa, con
     float* p_b2 = p_w2 + H * H;
     float* p_w3 = p_b2 + H;
     float* p_b3 = p_w3 + NA * H;
-    if (r < H) {                                               // rows of the accumulators = output features
+    {
+        const int j = 16 * (r >> 5) + (r & 31);
+        const bool row = (r & 31) < 16 && j < H;
         float v[16];
         if (16 * q < H) {
             tmem_ld16(lane_base + DW2 + 16 * q, v);
+            if (row) {
 #pragma unroll
-            for (int i = 0; i < 16; i += 4)
-                *reinterpret_cast<float4*>(p_w2 + r * H + 16 * q + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                for (int i = 0; i < 16; i += 4)
+                    *reinterpret_cast<float4*>(p_w2 + j * H + 16 * q + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            }
         }
         if (q == 0) {
-            tmem_ld16(lane_base + DW3, v);
-#pragma unroll
-            for (int o = 0; o < NA; ++o) p_w3[o * H + r] = v[o];
+            tmem_ld16(lane_base + DW2 + H, v);
+            if (row) p_b2[j] = v[0];
         } else if (q == 1) {
-            tmem_ld16(lane_base + DW1, v);
+            tmem_ld16(lane_base + DW3, v);
+            if (row) {
 #pragma unroll
-            for (int k = 0; k < 16; ++k)
-                if (k < d) p_w1[r * d + k] = v[k];
+                for (int o = 0; o < NA; ++o) p_w3[o * H + j] = v[o];
+            }
         } else if (q == 2) {
-            tmem_ld16(lane_base + DB2, v);
-            p_b2[r] = v[0];
+            tmem_ld16(lane_base + DW1, v);
+            if (row) {
+#pragma unroll
+                for (int k = 0; k < 16; ++k)
+                    if (k < d) p_w1[j * d + k] = v[k];
+            }
         } else {
-            tmem_ld16(lane_base + DB1, v);
-            p_b1[r] = v[0];
+            tmem_ld16(lane_base + DW1 + 16, v);
+            if (row) p_b1[j] = v[0];
         }
     }
     if (q == 0 && (r & 31) == 0) {
