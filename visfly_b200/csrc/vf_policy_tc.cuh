@@ -362,8 +362,7 @@ template <int H> struct BwdSmem {
     // K = agents operands, [hi | lo][4 groups of 32 agents][F rows][32 floats], 16-byte chunks XOR row % 8
     float kx[2][4 * 24 * 32];          // x (16 rows) + a row group whose hi part is ones
     float kh1[2][4 * (H + 8) * 32];    // h1 (H rows) + a row group whose hi part is ones
-    float kh2[2][4 * H * 32];          // h2, then dZ2, then dZ1
-    float kz3[2][4 * 8 * 32];          // dz3 (rows 0..3; 4..7 zero)
+    float kh2[2][4 * H * 32];          // dZ2, then dZ1
     float w1[2][H * 16];               // blocked (H x 16)
     float w1t[2][16 * H];              // blocked (16 x H)
     float w2[2][H * H];                // blocked W2 (layer 2) / W2^T (dZ1), swapped per tile
@@ -372,6 +371,7 @@ template <int H> struct BwdSmem {
     float4 mu[3][TILE];                // output-layer partial sums of column groups 1..3
     float4 dz3[TILE];
     float db3[4][NA];
+    float dw3[16][64];                 // end of the kernel: every warp's share of dW3
     uint64_t bar[2];
     uint32_t tmem;
 };
@@ -410,6 +410,39 @@ __device__ __forceinline__ void store_krole(float* hi_buf, float* lo_buf, int q,
     }
 }
 
+// ... both at once (one split per value): the A operand of the next agents-as-rows product in tensor memory and the
+// K = agents operand in shared memory
+template <int H, int F>
+__device__ __forceinline__ void store_both(uint32_t lane_base, uint32_t op_col, float* hi_buf, float* lo_buf, int q, int r,
+                                           const float v[16]) {
+    const int l = r & 31, base = (r >> 5) * F * 32 + 16 * q * 32;
+    float hi[16], lo[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const int idx = base + i * 32 + ((((l >> 2) ^ (i & 7)) << 2) | (l & 3));
+        split(v[i], hi[i], lo[i]);
+        hi_buf[idx] = hi[i];
+        lo_buf[idx] = lo[i];
+    }
+    tmem_st16(lane_base + op_col + 16 * q, hi);
+    tmem_st16(lane_base + op_col + H + 16 * q, lo);
+}
+
+// sum over the 32 lanes of a warp of 64 per-lane values: lane L ends up with the totals of values 2 L and 2 L + 1 in
+// val[0], val[1] (butterfly that halves the number of live values per step: 62 shuffles instead of 320)
+__device__ __forceinline__ void warp_sum64(float val[64], int lane) {
+#pragma unroll
+    for (int s = 16, count = 64; s > 0; s >>= 1, count >>= 1) {
+        const bool up = (lane & s) != 0;
+#pragma unroll
+        for (int k = 0; k < count / 2; ++k) {
+            const float send = up ? val[k] : val[k + count / 2];
+            const float keep = up ? val[k + count / 2] : val[k];
+            val[k] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+        }
+    }
+}
+
 template <int THREADS> __device__ __forceinline__ void copy_async(float* dst, const float* src, int count) {
     const uint32_t d = smem_u32(dst);
     for (int i = threadIdx.x; i < count / 4; i += THREADS)
@@ -426,8 +459,8 @@ vf_policy_bwd_tc_kernel(int n, int da, int db, const float* __restrict__ xa, con
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     BwdSmem<H>& s = *reinterpret_cast<BwdSmem<H>*>(smem_raw);
     constexpr int DK = 16;
-    constexpr uint32_t ACC0 = 0, ACC1 = H, OPA = 2 * H, OPB = 4 * H, DW2 = 6 * H, DW3 = 7 * H + 8, DW1 = 7 * H + 16;
-    static_assert(7 * H + 40 <= 512, "tensor-memory columns");
+    constexpr uint32_t ACC0 = 0, ACC1 = H, OPA = 2 * H, OPB = 4 * H, DW2 = 6 * H, DW1 = 7 * H + 8;
+    static_assert(7 * H + 32 <= 512, "tensor-memory columns");
     const int t = threadIdx.x, warp = t >> 5, q = t >> 7, r = t & 127, d = da + db;
     const int tiles = (n + TILE - 1) / TILE;
     copy_floats<BWD_THREADS>(&s.w1[0][0], &packed->w1_16[0][0], 2 * H * 16);
@@ -443,7 +476,6 @@ vf_policy_bwd_tc_kernel(int n, int da, int db, const float* __restrict__ xa, con
         s.kh1[0][grp * (H + 8) * 32 + H * 32 + e] = 1.f;
         s.kh1[1][grp * (H + 8) * 32 + H * 32 + e] = 0.f;
     }
-    for (int i = t; i < 2 * 4 * 8 * 32; i += BWD_THREADS) (&s.kz3[0][0])[i] = 0.f;
     if (t < H) { s.b1s[t] = packed->b1[t] * TANH_SCALE; s.b2s[t] = packed->b2[t] * TANH_SCALE; }
     if (t < NA) s.b3[t] = packed->b3[t];
     if (t == 0) { mbar_init(&s.bar[0]); mbar_init(&s.bar[1]); }
@@ -451,6 +483,7 @@ vf_policy_bwd_tc_kernel(int n, int da, int db, const float* __restrict__ xa, con
     const uint32_t lane_base = tmem + (uint32_t((warp & 3) * 32) << 16);
     uint32_t phase_a = 0, phase_b = 0;
     float db3_acc[NA] = {0.f, 0.f, 0.f, 0.f};
+    float dw3_acc[2] = {0.f, 0.f};           // this lane's two entries of the warp's dW3 share (warp_sum64)
     float x[16];
     float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
     if (q == 0) {
@@ -488,8 +521,7 @@ vf_policy_bwd_tc_kernel(int n, int da, int db, const float* __restrict__ xa, con
         if (16 * q < H) {
             float h[16];
             hidden_values<H>(lane_base, ACC0, s.b1s, q, h);
-            store_operand<H>(lane_base, OPA, q, h);
-            store_krole<H + 8>(s.kh1[0], s.kh1[1], q, r, h);
+            store_both<H, H + 8>(lane_base, OPA, s.kh1[0], s.kh1[1], q, r, h);
         }
         publish_operands();
         if (t == 0) {
@@ -504,7 +536,6 @@ vf_policy_bwd_tc_kernel(int n, int da, int db, const float* __restrict__ xa, con
         if (16 * q < H) {
             hidden_values<H>(lane_base, ACC1, s.b2s, q, h2);
             mine = output_partial<H>(s.w3n, q, h2);
-            store_krole<H>(s.kh2[0], s.kh2[1], q, r, h2);
         }
         if (q > 0) s.mu[q - 1][r] = mine;
         __syncthreads();
@@ -519,32 +550,28 @@ vf_policy_bwd_tc_kernel(int n, int da, int db, const float* __restrict__ xa, con
                 const float a = tanh_scaled((mu[o] + s.b3[o]) * TANH_SCALE);
                 const float gate = (a >= lo && a <= hi) ? 1.f : 0.f;      // torch.clamp: closed interval
                 z[o] = agent < n ? gv[o] * gate * (1.f - a * a) : 0.f;
-            }
-            s.dz3[r] = make_float4(z[0], z[1], z[2], z[3]);
-            const int l = r & 31, base = (r >> 5) * 8 * 32;
-#pragma unroll
-            for (int o = 0; o < NA; ++o) {
-                const int idx = base + o * 32 + ((((l >> 2) ^ o) << 2) | (l & 3));
-                float zh, zl;
-                split(z[o], zh, zl);
-                s.kz3[0][idx] = zh;
-                s.kz3[1][idx] = zl;
                 float v = z[o];                                            // db3: fixed-order sum over the warp's agents
 #pragma unroll
                 for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
                 db3_acc[o] += v;
             }
+            s.dz3[r] = make_float4(z[0], z[1], z[2], z[3]);
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
-        if (t == 0) {
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            issue_kk<8, H, 8>(tmem + DW3, s.kh2[0], s.kh2[1], s.kz3[0], s.kz3[1], !first);
-            umma_commit(&s.bar[1]);
-        }
-        float dz2[16];
-        if (16 * q < H) {                                      // dZ2 = (dz3 W3) * (1 - h2^2), this thread's 16 columns
+        if (16 * q < H) {
             const float4 z = s.dz3[r];
+            {   // dW3[o][16 q + i] += sum over the warp's agents of dz3[o] h2[i] (4 x 16 values per lane, CUDA cores: an
+                // MMA over h2 would need a third K = agents buffer)
+                float val[64];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    val[i] = z.x * h2[i]; val[16 + i] = z.y * h2[i]; val[32 + i] = z.z * h2[i]; val[48 + i] = z.w * h2[i];
+                }
+                warp_sum64(val, t & 31);
+                dw3_acc[0] += val[0];
+                dw3_acc[1] += val[1];
+            }
+            float dz2[16];                                     // dZ2 = (dz3 W3) * (1 - h2^2), this thread's 16 columns
 #pragma unroll
             for (int i = 0; i < 16; i += 4) {
                 const float4 wa = *reinterpret_cast<const float4*>(&s.w3n[0][16 * q + i]);
@@ -556,10 +583,8 @@ vf_policy_bwd_tc_kernel(int n, int da, int db, const float* __restrict__ xa, con
                 dz2[i + 2] = (z.x * wa.z + z.y * wb.z + z.z * wc.z + z.w * wd.z) * (1.f - h2[i + 2] * h2[i + 2]);
                 dz2[i + 3] = (z.x * wa.w + z.y * wb.w + z.z * wc.w + z.w * wd.w) * (1.f - h2[i + 3] * h2[i + 3]);
             }
-            store_operand<H>(lane_base, OPB, q, dz2);
+            store_both<H, H>(lane_base, OPB, s.kh2[0], s.kh2[1], q, r, dz2);     // kh2: free since barrier B at P0
         }
-        mbar_wait(&s.bar[1], phase_b); phase_b ^= 1;           // dW3 has read h2 from kh2: dZ2 may move in
-        if (16 * q < H) store_krole<H>(s.kh2[0], s.kh2[1], q, r, dz2);
         copy_async_wait();                                     // W2^T has landed
         publish_operands();
         if (t == 0) {
@@ -582,10 +607,9 @@ vf_policy_bwd_tc_kernel(int n, int da, int db, const float* __restrict__ xa, con
                 const float h1 = hh[i] + hl[i];
                 dz1[i] = v[i] * (1.f - h1 * h1);
             }
-            store_operand<H>(lane_base, OPA, q, dz1);
         }
         mbar_wait(&s.bar[1], phase_b); phase_b ^= 1;           // dW2 has read dZ2 from kh2: dZ1 may move in
-        if (16 * q < H) store_krole<H>(s.kh2[0], s.kh2[1], q, r, dz1);
+        if (16 * q < H) store_both<H, H>(lane_base, OPA, s.kh2[0], s.kh2[1], q, r, dz1);
         publish_operands();
         if (t == 0) {
             issue_ts<16, H>(tmem + ACC1, tmem + OPA, tmem + OPA + H, s.w1t[0], s.w1t[1], false);
@@ -634,12 +658,6 @@ vf_policy_bwd_tc_kernel(int n, int da, int db, const float* __restrict__ xa, con
         if (q == 0) {
             tmem_ld16(lane_base + DW2 + H, v);
             if (row) p_b2[j] = v[0];
-        } else if (q == 1) {
-            tmem_ld16(lane_base + DW3, v);
-            if (row) {
-#pragma unroll
-                for (int o = 0; o < NA; ++o) p_w3[o * H + j] = v[o];
-            }
         } else if (q == 2) {
             tmem_ld16(lane_base + DW1, v);
             if (row) {
@@ -656,8 +674,14 @@ vf_policy_bwd_tc_kernel(int n, int da, int db, const float* __restrict__ xa, con
 #pragma unroll
         for (int o = 0; o < NA; ++o) s.db3[r >> 5][o] = db3_acc[o];
     }
+    s.dw3[warp][2 * (t & 31)] = dw3_acc[0];                   // value index o * 16 + i of column group q = warp / 4
+    s.dw3[warp][2 * (t & 31) + 1] = dw3_acc[1];
     __syncthreads();
     if (t < NA) p_b3[t] = (s.db3[0][t] + s.db3[1][t]) + (s.db3[2][t] + s.db3[3][t]);
+    if (t < NA * H) {                                          // the four warps (agent groups) of each column group, fixed order
+        const int o = t / H, k = t % H, qq = k / 16, e = o * 16 + k % 16;
+        p_w3[t] = (s.dw3[4 * qq][e] + s.dw3[4 * qq + 1][e]) + (s.dw3[4 * qq + 2][e] + s.dw3[4 * qq + 3][e]);
+    }
     tmem_free<512>(tmem, warp);
 }
 
