@@ -16,16 +16,19 @@ class BPTT(AnalyticGradientBase):
     def rollout_loss(self) -> th.Tensor:
         """One horizon with autograd history; returns the mean actor loss (reference BPTT.py:107-127)."""
         n = self.num_envs
-        actor_loss = 0.0
+        rewards, discounts = [], []
         discount = th.ones((n,), dtype=th.float32, device=self.device)
         for _ in range(self.H):
             obs = self.env.get_observation()
             action = self._act(obs)
             obs, reward, done, info = self.env.step(action)
             self.num_timesteps += n
-            actor_loss = actor_loss - reward * discount
-            discount = discount * self.gamma * ~done + done
-        return actor_loss.mean()
+            # actor_loss -= reward * discount, kept as two lists and evaluated once per horizon (two small launches per
+            # step here instead of eight with their autograd nodes); the discount restarts at 1 where an episode ended
+            rewards.append(reward)
+            discounts.append(discount)
+            discount = th.where(done, 1.0, discount * self.gamma)
+        return -(th.stack(rewards) * th.stack(discounts)).sum(0).mean()
 
     # -- the whole update as one CUDA graph -------------------------------------------------------------------------
     # What makes an update replayable: (i) everything that carries over from one update to the next — packed state,
@@ -77,6 +80,8 @@ class BPTT(AnalyticGradientBase):
         import gc
         self.actor.optimizer.zero_grad(set_to_none=True)
         env.detach()
+        if hasattr(self.actor, "release_graph"):
+            self.actor.release_graph()
         gc.collect()            # no autograd graph of an earlier (default-stream) update may survive into the capture
         fz.step_base = th.full((1,), int(fz.global_step), dtype=th.int64, device=self.device)
         fz.global_step = 0

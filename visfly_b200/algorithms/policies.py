@@ -7,6 +7,8 @@ from __future__ import annotations
 from copy import deepcopy
 from typing import Dict, Optional, Sequence, Tuple, Type
 
+import weakref
+
 import torch as th
 from torch import nn
 
@@ -94,6 +96,9 @@ def mlp(sizes: Sequence[int], activation: Type[nn.Module], out_activation: Optio
     return nn.Sequential(*layers)
 
 
+_FLAT_CACHE = weakref.WeakKeyDictionary()
+
+
 class _FusedActorFn(th.autograd.Function):
     """``clip(tanh(W3 tanh(W2 tanh(W1 x + b1) + b2) + b3), lo, hi)`` as ONE launch forward (``vf_policy_fwd``) and one
     backward (``vf_policy_bwd`` + a fixed-order reduction of the per-tile weight gradients) instead of ~40 library
@@ -101,14 +106,13 @@ class _FusedActorFn(th.autograd.Function):
     the activations from the inputs, nothing else is saved."""
 
     @staticmethod
-    def forward(ctx, xa, xb, lo, hi, packed, w1, b1, w2, b2, w3, b3):
+    def forward(ctx, xa, xb, lo, hi, packed, flat, h):
         from .. import _lib
         xa = xa.contiguous()
         xb = None if xb is None else xb.contiguous()
         ctx.save_for_backward(xa, packed, *(() if xb is None else (xb,)))
-        ctx.lo, ctx.hi, ctx.two, ctx.h = lo, hi, xb is not None, w1.shape[0]
-        ctx.shapes = [tuple(p.shape) for p in (w1, b1, w2, b2, w3, b3)]
-        return _lib.policy_fwd(xa, xb, packed, ctx.h, lo, hi)
+        ctx.lo, ctx.hi, ctx.two, ctx.h = lo, hi, xb is not None, h
+        return _lib.policy_fwd(xa, xb, packed, h, lo, hi)
 
     @staticmethod
     @th.autograd.function.once_differentiable
@@ -118,14 +122,9 @@ class _FusedActorFn(th.autograd.Function):
         xa, packed, xb = saved[0], saved[1], (saved[2] if ctx.two else None)
         g_a, g_b, flat = _lib.policy_bwd(xa, xb, packed, ctx.h, ctx.lo, ctx.hi, g_action.contiguous(),
                                          ctx.needs_input_grad[0], ctx.needs_input_grad[1])
-        grads, off = [], 0
-        for shape in ctx.shapes:
-            k = 1
-            for v in shape:
-                k *= v
-            grads.append(flat[off:off + k].view(shape))
-            off += k
-        return (g_a, g_b, None, None, None, *grads)
+        # `flat` = [dW1 | db1 | dW2 | db2 | dW3 | db3]: the gradient of the concatenated parameter vector the forward
+        # was given (Actor._flat_params) — ONE accumulation per env step instead of six
+        return g_a, g_b, None, None, None, flat, None
 
 
 class Actor(nn.Module):
@@ -157,7 +156,7 @@ class Actor(nn.Module):
         matrices (e.g. ``{"state": (N,13), "target": (N,3)}``) is handed to the kernel piecewise, in ``flatten_obs``'s
         key order, without being concatenated."""
         pieces = None
-        if not isinstance(obs, th.Tensor) and len(obs) == 2:
+        if not isinstance(obs, th.Tensor) and len(obs.keys()) == 2:      # (len() of a TensorDict is its batch size)
             pieces = [obs[k] for k in sorted(obs.keys())]
             if not all(p.dim() == 2 and p.dtype is th.float32 and p.is_cuda for p in pieces) or \
                     pieces[0].shape[1] + pieces[1].shape[1] != self.body[0].in_features:
@@ -169,7 +168,8 @@ class Actor(nn.Module):
         if self.fused_ok(xa):
             l1, l2 = self.body[0], self.body[2]
             params = (l1.weight, l1.bias, l2.weight, l2.bias, self.mu.weight, self.mu.bias)
-            return _FusedActorFn.apply(xa, xb, float(lo), float(hi), self._packed_weights(params), *params)
+            return _FusedActorFn.apply(xa, xb, float(lo), float(hi), self._packed_weights(params), self._flat_params(params),
+                                       l1.out_features)
         return th.clip(th.tanh(self.mu(self.body(xa))), lo, hi)
 
     def _packed_weights(self, params) -> th.Tensor:
@@ -185,6 +185,24 @@ class Actor(nn.Module):
             cache = (key, _lib.policy_pack(params), capturing)
             self.__dict__["_packed"] = cache
         return cache[1]
+
+    def _flat_params(self, params) -> th.Tensor:
+        """``cat`` of the six parameter tensors, in the order of the kernels' gradient vector — the one autograd input
+        through which ``_FusedActorFn`` hands the parameter gradients back (the horizon's H contributions are summed on
+        this one tensor, the split into per-parameter gradients happens once per update).  Rebuilt with the packed
+        weights, and whenever the autograd mode differs from the one it was built under."""
+        key = (tuple((p.data_ptr(), p._version) for p in params), th.is_grad_enabled(),
+               th.cuda.is_current_stream_capturing())
+        cache = _FLAT_CACHE.get(self)          # not an attribute: a tensor with autograd history cannot be deep-copied
+        if cache is None or cache[0] != key:
+            cache = (key, th.cat([p.reshape(-1) for p in params]))
+            _FLAT_CACHE[self] = cache
+        return cache[1]
+
+    def release_graph(self):
+        """Drop the cached parameter vector (and with it the autograd nodes it keeps alive); the trainers call this
+        after every backward pass."""
+        _FLAT_CACHE.pop(self, None)
 
     def _dist(self, obs) -> Tuple[th.Tensor, th.Tensor]:
         h = self.body(flatten_obs(obs))

@@ -88,6 +88,8 @@ class AnalyticGradientBase:
     def _actor_update(self, actor_loss: th.Tensor):
         self.actor.optimizer.zero_grad()
         actor_loss.backward()
+        if hasattr(self.actor, "release_graph"):
+            self.actor.release_graph()
         all_reduce_gradients(self.actor.parameters())
         th.nn.utils.clip_grad_norm_(self.actor.parameters(), self.max_grad_norm)
         self.actor.optimizer.step()
