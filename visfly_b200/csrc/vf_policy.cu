@@ -1,5 +1,9 @@
 // vf_policy.cu — the deterministic actor of the analytic-gradient trainers, forward and backward, one launch each.
 //
+// Two kernel families behind vf_policy_fwd / vf_policy_bwd: the tensor-core kernels of vf_policy_tc.cuh (tcgen05,
+// accumulators in tensor memory, 3xTF32 — the default wherever they apply) and the CUDA-core kernels of this file
+// (VF_POLICY_NO_TC=1, and the backward for observation widths above 16).
+//
 // Why it is here: BASELINE configs[2] (NavigationEnv, 65 536 agents, requires_grad=True, APG) spends 8 % of its GPU
 // time in the env-step kernels and the rest in the policy MLP as ~80 library launches per env step (SIMT sgemm with one
 // output tile, elementwise tanh / bias / clip kernels, split-K weight gradients) — profiles/r01_s3_launches_apg.txt.
