@@ -64,5 +64,34 @@ for cls in (HoverEnv, NavigationEnv, RacingEnv2):
     env.reset_agent_by_id([0, 5, n - 1])                  # drops the step in flight (rewind) and hands over
     env.tensor_output = True
     env.step(th.zeros(n, 4, device="cuda"))
+
+# actor kernels: tensor-core path (tcgen05, default) for widths <= 16, CUDA-core backward above; two-piece observation
+from visfly_b200.algorithms.policies import Actor  # noqa: E402
+for d_obs, h in ((16, 64), (13, 32), (17, 64)):
+    actor = Actor(d_obs, 4, (h, h)).cuda()
+    xa = th.randn(n, d_obs - 3, device="cuda").requires_grad_(True)
+    xb = th.randn(n, 3, device="cuda").requires_grad_(True)
+    act = actor.deterministic_action({"a": xa, "b": xb}, -0.9, 0.9)
+    (act * th.randn(n, 4, device="cuda")).sum().backward()
+    actor.release_graph()
+
+# task env with its own reward code: control step + vf_env_finish (FIFO rows zeroed in the launch), and the FIFO ring
+class UserHover(HoverEnv):
+    def get_reward(self, predicted_obs=None):
+        return 0.1 - (self.position - self.target).norm(dim=1) * 0.01 - 0.001 * self._step_count
+
+
+env = UserHover(num_agent_per_scene=n, visual=False, device="cuda", dynamics_kwargs=dict(dyn_kw), max_episode_steps=4,
+                tensor_output=True)
+env.reset()
+for t in range(9):
+    env.step(((th.rand(n, 4, generator=g) * 2 - 1) * 0.3).cuda())
+assert env._split.active
+ring = Dynamics(num=n, device="cuda", **dyn_kw)
+ring._fifo_ring = True
+with th.no_grad():
+    for t in range(4):
+        ring.step(((th.rand(n, 4, generator=g) * 2 - 1) * 0.3).cuda())
+_ = ring.acceleration
 th.cuda.synchronize()
 print("sanitizer driver finished")
