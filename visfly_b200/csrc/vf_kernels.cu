@@ -43,6 +43,12 @@ constexpr int kWarpObs = 32 * kObs;       // floats one warp's observations occu
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// Ahead of griddepcontrol.wait: pull this thread's input lines towards L2.  A prefetch has no architectural effect and L2
+// is the point of coherence, so it is safe even where the preceding grid is still writing those lines; where the
+// inputs come from HBM (a loop over more env replicas than fit in L2) the round trip overlaps the previous launch's tail.
+constexpr unsigned kEnvFlagPrefetch = 0x40000000u;      // internal bit of env_flags, set by vf_env_step_fwd unless VF_NO_PREFETCH=1
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
+
 __device__ __forceinline__ float4 ldg4(const float* base, size_t idx4) {
     return __ldg(reinterpret_cast<const float4*>(base) + idx4);
 }
@@ -268,6 +274,12 @@ vf_env_step_fwd_kernel(const __grid_constant__ VfParams params, const __grid_con
     const int warp_first = i - lane;
     const bool live = i < n;
     pdl_trigger();
+    if (live && (env_flags & kEnvFlagPrefetch)) {
+#pragma unroll
+        for (int pl = 0; pl < 5; ++pl) prefetch_l2(reinterpret_cast<const float4*>(state_in) + size_t(pl) * n + i);
+        prefetch_l2(reinterpret_cast<const int4*>(status_in) + i);
+        prefetch_l2(reinterpret_cast<const float4*>(action) + i);
+    }
     pdl_wait();
 
     vf::State<float> s;
@@ -1018,6 +1030,11 @@ int vf_env_step_fwd(const VfParams* params, const VfEnvSpec* spec, int n, int su
         }
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    static const bool prefetch = [] {
+        const char* e = getenv("VF_NO_PREFETCH");
+        return !(e && e[0] && e[0] != '0');
+    }();
+    env_flags = (env_flags & ~kEnvFlagPrefetch) | (prefetch ? kEnvFlagPrefetch : 0u);
     VF_DISPATCH_FWD(launch_env_fwd, *params, *spec, n, substeps, env_flags, step_index, step_base, state_in, action,
                     wind, fifo_push, reset_table, status_in, state_out, status_out, fifo_copy, obs_out, reward_out,
                     done_out, record_out, term_obs_out, gate_out, mirror, peers, st);
