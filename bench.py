@@ -405,7 +405,7 @@ def racing_leg(n_weak, dev, rank, world, K, W, stream, barrier):
         gather = FusedReturnsGather(n, n_total, rank, world, dev)
         dev_ms, wall_ms = rotating_brackets(envs, act_list, K, max(W * replicas, HOT_PREROLL), BRACKETS, stream, barrier,
                                             collective=gather)
-        ms = max_over_ranks([max(d, w) for d, w in zip(dev_ms, wall_ms)], dev, world)
+        ms = max_over_ranks(dev_ms, dev, world)
         t = median(ms)
         out[name] = {"value": n_total * K / (t * 1e-3), "unit": UNIT, "agents_total": n_total, "agents_this_gpu": n,
                      "ms_per_step": t / K, "bracket_ms": ms, "replicas": replicas,
@@ -531,7 +531,8 @@ def run_ours(args):
         #     REPLICAS independent copies of the 65 536-agent env take turns, so every step finds its state, actions
         #     and env status evicted (REPLICAS x ~17 MB per step >> 126 MB L2) while launches stay back to back.
         #     BRACKETS consecutive brackets of exactly K steps + the rollout's collective; per bracket the max over
-        #     ranks of max(device time, wall time); the reported value is the MEDIAN bracket (all are listed).
+        #     ranks of the device time between the bracket's two CUDA events (the contract's clock; the wall time, which
+        #     adds the wake-up of the closing synchronize, is listed beside it); the value is the MEDIAN bracket.
         envs = [env] + [HoverEnv(num_agent_per_scene=n, visual=False, device=dev, dynamics_kwargs=dict(DYN),
                                  seed=42 + rank + 1000 * j, max_episode_steps=256, tensor_output=True)
                         for j in range(1, REPLICAS)]
@@ -557,7 +558,7 @@ def run_ours(args):
     except BaseException:
         clk.__exit__(None, None, None)
         raise
-    bracket_ms = max_over_ranks([max(d, w) for d, w in zip(bracket_dev_ms, bracket_wall_ms)], dev, world)
+    bracket_ms = max_over_ranks(bracket_dev_ms, dev, world)       # device time (CUDA events on the launching stream)
     cold_ms, hot_ms = max_over_ranks([sum(per_step), max(hot_dev[0], hot_wall[0])], dev, world)
     total_ms = median(bracket_ms)
     cold_value = world * n * K / (cold_ms * 1e-3)
@@ -775,7 +776,7 @@ def run_ours(args):
                 "value": f"median of {BRACKETS} consecutive brackets of exactly K env.step calls + the rollout's one "
                          "all_gather; each bracket opens behind barrier + synchronize and closes by synchronising on its "
                          "last CUDA event (no barrier / extra collective inside); per bracket max over ranks of "
-                         "max(device time, wall time); bracket_ms lists them all",
+                         "the device time between the two CUDA events on the launching stream; bracket_ms lists them all, bracket_detail_rank0 has the wall times beside them (they add the wake-up of the closing synchronize, ~15 us)",
                 "cold_l2_device_value": "one env, 256 MiB flush + one CUDA-event pair per step",
                 "hot_l2_bracketed_value": "one env back to back (12 MB working set resident in L2)",
                 "host_affinity": None if numa_cpus is None else f"rank 0 pinned to {len(numa_cpus)} CPUs next to its GPU"},

@@ -6,7 +6,7 @@
 //     TENSOR MEMORY: the epilogue thread that has just produced its agent's activation row in registers stores it there
 //     (tcgen05.st), so activations never travel through shared memory in this role; B = the weights, K-major in
 //     shared memory in the un-swizzled 8 x 16-byte core-matrix layout, packed once per weight update;
-//   * every product that contracts over agents (dW3, dW2, dW1) reads both operands from shared memory, K-major with
+//   * every product that contracts over agents (dW2, dW1 and the bias gradients) reads both operands from shared memory, K-major with
 //     K = agents, in 128-byte-swizzled rows: a warp storing one feature of its 32 agents writes one 128-byte row
 //     (conflict-free scalar stores);
 //   * fp32 accuracy on kind::tf32: every operand is split into hi = tf32(x) and lo = tf32(x - hi) and every product
@@ -344,8 +344,8 @@ vf_policy_fwd_tc_kernel(int n, int da, int db, const float* __restrict__ xa, con
 // One persistent CTA of 512 threads per SM, all of its tensor memory, d <= 16.  Per tile of 128 agents:
 //   P0  x -> tensor memory (A of layer 1) and shared memory (K = agents, B of dW1)              MMA: Z1 = x W1^T
 //   P1  h1 = tanh(Z1 + b1) -> tensor memory (A of layer 2), shared memory (B of dW2)            MMA: Z2 = h1 W2^T
-//   P2  h2 = tanh(Z2 + b2) -> shared memory (A of dW3); output layer + dz3 on the CUDA cores    MMA: dW3 += h2^T dz3
-//       dZ2 = (dz3 W3)(1 - h2^2) -> tensor memory (A of dZ1), shared memory (A of dW2, over h2)  MMA: dZ1' = dZ2 W2,
+//   P2  h2 = tanh(Z2 + b2); output layer, dz3 and dW3 += h2^T dz3 (warp butterfly) on the CUDA cores
+//       dZ2 = (dz3 W3)(1 - h2^2) -> tensor memory (A of dZ1), shared memory (A of dW2)           MMA: dZ1' = dZ2 W2,
 //                                                                                                    [dW2 | db2] += dZ2^T [h1 | 1]
 //   P3  dZ1 = dZ1' (1 - h1^2) -> tensor memory (A of dx), shared memory (A of dW1, over dZ2)    MMA: dx = dZ1 W1,
 //                                                                                                    [dW1 | db1] += dZ1^T [x | 1]
