@@ -559,6 +559,13 @@ def run_ours(args):
         clk.__exit__(None, None, None)
         raise
     bracket_ms = max_over_ranks(bracket_dev_ms, dev, world)       # device time (CUDA events on the launching stream)
+    per_rank = None
+    if world > 1:                       # which rank the others wait for: every rank's median collective-free bracket
+        import torch.distributed as dist
+        mine = th.tensor([median(nocoll_dev_ms), median(bracket_dev_ms)], device=dev, dtype=th.float64)
+        allr = [th.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = {"collective_free_device_ms": [float(x[0]) for x in allr], "device_ms": [float(x[1]) for x in allr]}
     cold_ms, hot_ms = max_over_ranks([sum(per_step), max(hot_dev[0], hot_wall[0])], dev, world)
     total_ms = median(bracket_ms)
     cold_value = world * n * K / (cold_ms * 1e-3)
@@ -791,6 +798,7 @@ def run_ours(args):
             "bracket_ms": bracket_ms,
             "bracket_detail_rank0": {"device_ms": bracket_dev_ms, "wall_ms": bracket_wall_ms,
                                      "collective_free_device_ms": nocoll_dev_ms},
+            "bracket_median_per_rank": per_rank,
         }
         emit(line)
     if world > 1:
