@@ -27,5 +27,5 @@ def loop(es, k):
         e1.record(); e1.synchronize()
         out.append(e0.elapsed_time(e1) * 1e3 / k)
     return sorted(out)[2]
-print(f"delay={delay} sep={os.environ.get('VF_COPY_SEPARATE')} noterm={os.environ.get('VF_AB_NOTERM')}: "
+print(f"delay={delay} prefetch_off={os.environ.get('VF_NO_PREFETCH')} noterm={os.environ.get('VF_AB_NOTERM')}: "
       f"hot {loop(envs[:1], 400):.2f} us/step   cold(16 replicas) {loop(envs, 400):.2f} us/step")

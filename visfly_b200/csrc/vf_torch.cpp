@@ -157,15 +157,7 @@ class EnvStepper {
         at::Tensor done = carve(slab, o_done_, at::kBool, {n_});
         OptTensor term, copy, gate;
         if (racing_) gate = obs_width_ == 16 ? carve(slab, o_gate_, at::kLong, {n_, 1}) : carve(slab, o_gate_, at::kLong, {n_});
-        if (push.has_value()) {
-            static const bool separate = std::getenv("VF_COPY_SEPARATE") != nullptr;
-            if (separate) {
-                const Slab small{alloc_slab(16 * n_), state_in.key_set()};
-                copy = carve(small, 0, at::kFloat, {n_, 4});
-            } else {
-                copy = carve(slab, o_copy_, at::kFloat, {n_, 4});
-            }
-        }
+        if (push.has_value()) copy = carve(slab, o_copy_, at::kFloat, {n_, 4});
         if (want_term) term = carve(slab, o_term, at::kFloat, {n_, obs_width_});
         const int rc = vf_env_step_fwd(
             params_, spec_, int(n_), substeps_, integrator_, action_type_, flags_, unsigned(env_flags),
