@@ -401,7 +401,10 @@ const char* vf_sensor_last_error(void);
  * Deterministic actor of the analytic-gradient trainers (SURVEY.md §8 row n3 / BASELINE configs[2]): the policy the
  * reference's BPTT / SHAC loops evaluate once per env step (utils/algorithms/BPTT.py:107-115, shac.py:213-222)
  *     action = clip(tanh(W3 tanh(W2 tanh(W1 x + b1) + b2) + b3), lo, hi)      x (n, d <= 32), hidden h in {32, 64}
- * forward and backward as one launch each (csrc/vf_policy.cu) instead of ~40 library launches per env step.
+ * forward and backward as one launch each instead of ~40 library launches per env step — on the 5th-generation tensor
+ * cores (tcgen05, accumulators in tensor memory, 3xTF32: every operand split into tf32 hi + lo, every product issued as
+ * hi*hi + lo*hi + hi*lo, results at fp32 accuracy; csrc/vf_policy_tc.cuh) for observation widths <= 32 forward and <= 16
+ * backward, on the CUDA cores otherwise (csrc/vf_policy.cu; VF_POLICY_NO_TC=1 forces them).
  * The observation may be handed over in two row-major pieces x = [xa (n, da) | xb (n, db)], d = da + db (the obs dict
  * of NavigationEnv is {state (n,13), target (n,3)}; no concatenated copy is made); db = 0, xb = NULL for one piece.
  * Weights: vf_policy_pack converts the six torch.nn.Linear tensors (row-major W1 (h, d), b1, W2 (h, h), b2,
