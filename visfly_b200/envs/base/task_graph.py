@@ -105,8 +105,17 @@ class TaskStepGraph:
         self.replays = 0
 
     def matches(self, action: th.Tensor) -> bool:
-        return (self.fz.spec_gen == self.spec_gen and action.shape == self.a_in.shape
-                and len(self.dyn._pre_action) == len(self.fifo) and self.fz.t_off is None)
+        """False => the recording no longer fits the env (spec rebuilt, FIFO depth changed, a carried attribute was
+        deleted or re-bound to something of another shape): the caller records a new one."""
+        if not (self.fz.spec_gen == self.spec_gen and action.shape == self.a_in.shape
+                and len(self.dyn._pre_action) == len(self.fifo) and self.fz.t_off is None):
+            return False
+        for o, k, holder in self.carried:
+            cur = o.__dict__.get(k)
+            if cur is not holder and not (isinstance(cur, th.Tensor) and cur.shape == holder.shape
+                                          and cur.dtype == holder.dtype and cur.device == holder.device):
+                return False
+        return all(a.shape == h.shape for a, h in zip(self.dyn._pre_action, self.fifo))
 
     def replay(self, action: th.Tensor, copy: bool):
         env, fz, dyn = self.env, self.fz, self.dyn
