@@ -17,7 +17,8 @@ class BPTT(AnalyticGradientBase):
         """One horizon with autograd history; returns the mean actor loss (reference BPTT.py:107-127)."""
         n = self.num_envs
         rewards, discounts = [], []
-        discount = th.ones((n,), dtype=th.float32, device=self.device)
+        ones = th.ones((n,), dtype=th.float32, device=self.device)
+        discount = ones
         for _ in range(self.H):
             obs = self.env.get_observation()
             action = self._act(obs)
@@ -27,7 +28,7 @@ class BPTT(AnalyticGradientBase):
             # step here instead of eight with their autograd nodes); the discount restarts at 1 where an episode ended
             rewards.append(reward)
             discounts.append(discount)
-            discount = th.where(done, 1.0, discount * self.gamma)
+            discount = th.where(done, ones, discount * self.gamma)
         return -(th.stack(rewards) * th.stack(discounts)).sum(0).mean()
 
     # -- the whole update as one CUDA graph -------------------------------------------------------------------------

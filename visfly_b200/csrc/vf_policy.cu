@@ -22,7 +22,10 @@
 
 #include <cstdint>
 #include <cstdlib>
+#include <mutex>
+#include <set>
 #include <string>
+#include <utility>
 
 #include "../../include/visfly_b200.h"
 
@@ -443,9 +446,22 @@ int policy_fail(const char* what, cudaError_t err) {
     return 1;
 }
 
+// opt-in to > 48 KB of dynamic shared memory: once per kernel and device (the attribute is per device), not per launch
 template <class K> int allow_smem(K kernel, size_t bytes) {
+    static std::mutex lock;
+    static std::set<std::pair<int, const void*>> done;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const std::pair<int, const void*> key(dev, reinterpret_cast<const void*>(kernel));
+    {
+        std::lock_guard<std::mutex> g(lock);
+        if (done.count(key)) return 0;
+    }
     const cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes));
-    return err == cudaSuccess ? 0 : policy_fail("cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed", err);
+    if (err != cudaSuccess) return policy_fail("cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed", err);
+    std::lock_guard<std::mutex> g(lock);
+    done.insert(key);
+    return 0;
 }
 
 // VF_POLICY_NO_TC=1 keeps the CUDA-core kernels (A/B measurements, profiles/)
