@@ -26,12 +26,6 @@ constexpr int TILE = 128;
 __host__ __device__ constexpr int blk(int r, int c, int C) {          // float index in the blocked K-major layout
     return ((r / 8) * (C / 4) + c / 4) * 32 + (r % 8) * 4 + (c % 4);
 }
-// float index of (feature f, agent a) in an (F x 128) K = agents operand: [a / 32][f][32 floats], 16-byte chunks ^ f % 8
-__device__ __forceinline__ int sw128(int f, int a, int F) {
-    const int l = a & 31;
-    return (a >> 5) * F * 32 + f * 32 + ((((l >> 2) ^ (f & 7)) << 2) | (l & 3));
-}
-
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
 
 __device__ __forceinline__ uint64_t desc_kmajor(uint32_t addr, uint32_t lbo, uint32_t sbo) {
@@ -136,7 +130,6 @@ template <int H> struct PackedTc {
     float w1_16[2][H * 16];      // blocked (H x 16):  W1[j][k], k < d <= 16 (zero beyond d)
     float w1_32[2][H * 32];      // blocked (H x 32):  the same for 16 < d <= 32
     float w2[2][H * H];          // blocked (H x H):   W2[j][i]
-    float w3[2][16 * H];         // blocked (16 x H):  W3[o][k], rows >= 4 zero
     float w1t[2][32 * H];        // blocked (32 x H):  W1[j][k] at (k, j)      (dx = dZ1 W1; the first 16 rows serve d <= 16)
     float w2t[2][H * H];         // blocked (H x H):   W2[j][i] at (i, j)      (dZ1 = dZ2 W2)
     float b1[H], b2[H], b3[4], w3n[4][H];
@@ -160,12 +153,7 @@ __device__ void pack_tc(int e, int d, const float* __restrict__ w1, const float*
         p.w2[0][blk(j, i, H)] = hi; p.w2[1][blk(j, i, H)] = lo;
         p.w2t[0][blk(i, j, H)] = hi; p.w2t[1][blk(i, j, H)] = lo;
     }
-    if (e < 16 * H) {
-        const int o = e / H, k = e % H;
-        split(o < NA ? w3[o * H + k] : 0.f, hi, lo);
-        p.w3[0][blk(o, k, H)] = hi; p.w3[1][blk(o, k, H)] = lo;
-        if (o < NA) p.w3n[o][k] = w3[o * H + k];
-    }
+    if (e < NA * H) p.w3n[e / H][e % H] = w3[e];          // the output layer runs on the CUDA cores
     if (e < H) { p.b1[e] = b1[e]; p.b2[e] = b2[e]; }
     if (e < NA) p.b3[e] = b3[e];
 }
