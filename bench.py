@@ -10,15 +10,19 @@
 One JSON line on stdout (rank 0).  What is measured
   value     env.step throughput with actions and state resident in HBM (tensor mode): exactly K steps inside
             barrier + synchronize, 16 independent env replicas taking turns so that every step's inputs are evicted
-            from L2 (inputs larger than L2, no flush kernel in the timed region); max over ranks; the median of five
-            consecutive such brackets (all listed in bracket_ms).  Two diagnostics
+            from L2 (inputs larger than L2, no flush kernel in the timed region); device time between two CUDA events
+            on the launching stream, max over ranks; the median of five consecutive such brackets (all listed in
+            bracket_ms, wall times beside them in bracket_detail_rank0).  Two diagnostics
             ride along: one env with a 256 MiB flush + CUDA-event pair per step (cold_l2_device_value) and one env
             back to back (hot_l2_bracketed_value).
   e2e       the same env driven like an SB3/numpy training loop: actions arrive in (pinned) host memory every step,
             observation / reward / done come back as numpy arrays — host<->device copies inside the timed region.
   roofline  the dominant kernel (the fused control step) timed alone, cold L2, against the measured HBM peak.
-  cpu_baseline  the oracle port of the reference (oracle/env_oracle.py, same aten-op sequence as the reference
-            incl. its per-agent Python loops) on this box's host cores, on a bounded sample of the same workload.
+  cpu_baseline  the real reference (baseline/_ref: unmodified VisFly sources + the runtime patches of
+            baseline/REF_PATCHES.md) on this box's host cores, on a bounded sample of the same workload; the oracle port
+            (oracle/env_oracle.py) is timed beside it.
+  apg / racing / custom_task  sub-objects: a whole BPTT update (BASELINE configs[2]) as one CUDA-graph replay, RacingEnv
+            weak + strong scaling (configs[4]), a task env with its own reward code (recorded step / two-launch / generic).
 `--impl reference` runs only that CPU arm for K steps and prints the same line with "impl": "reference".
 """
 from __future__ import annotations
