@@ -15,21 +15,24 @@ class BPTT(AnalyticGradientBase):
 
     def rollout_loss(self) -> th.Tensor:
         """One horizon with autograd history; returns the mean actor loss (reference BPTT.py:107-127)."""
-        n = self.num_envs
-        rewards, discounts = [], []
-        ones = th.ones((n,), dtype=th.float32, device=self.device)
-        discount = ones
-        for _ in range(self.H):
+        n, H = self.num_envs, self.H
+        rewards, dones = [], []
+        for _ in range(H):
             obs = self.env.get_observation()
             action = self._act(obs)
             obs, reward, done, info = self.env.step(action)
             self.num_timesteps += n
-            # actor_loss -= reward * discount, kept as two lists and evaluated once per horizon (two small launches per
-            # step here instead of eight with their autograd nodes); the discount restarts at 1 where an episode ended
             rewards.append(reward)
-            discounts.append(discount)
-            discount = th.where(done, ones, discount * self.gamma)
-        return -(th.stack(rewards) * th.stack(discounts)).sum(0).mean()
+            dones.append(done)
+        # actor_loss = -sum_t reward_t * discount_t with discount_0 = 1, discount_{t+1} = 1 if done_t else gamma * discount_t
+        # (reference BPTT.py:116-127), evaluated once per horizon from the stacked rewards and dones instead of eight small
+        # launches (and their autograd nodes) per step: discount_t = gamma ** (steps since the last episode end before t)
+        done_t = th.stack(dones)                                                    # (H, n)
+        step_no = th.arange(1, H + 1, device=self.device, dtype=th.int32).view(H, 1)
+        last_end = th.cummax(th.where(done_t, step_no, 0), dim=0).values            # 1 + index of the last done_j, j <= t
+        since = step_no - 1 - th.cat([last_end.new_zeros((1, n)), last_end[:-1]])   # t - (1 + last j < t with done_j)
+        discounts = th.pow(th.full((), self.gamma, device=self.device, dtype=th.float32), since.to(th.float32))
+        return -(th.stack(rewards) * discounts).sum(0).mean()
 
     # -- the whole update as one CUDA graph -------------------------------------------------------------------------
     # What makes an update replayable: (i) everything that carries over from one update to the next — packed state,
